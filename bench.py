@@ -1,0 +1,403 @@
+#!/usr/bin/env python
+"""Benchmark of the IIC MI loss hot path (BASELINE.json: "IIC MI loss fwd+bwd Mpixels/s").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+
+Workload at every N (weak scaling, per-GPU work fixed) = BASELINE config 2: global + local IIC
+(padding 1, patch 512, i.e. one patch) on Up_conv2-shaped maps, per GPU 32 x 10 x 224 x 224 float32
+probability maps for the two views plus the (32, 10) global head, forward + backward to both inputs.
+One "step" = local small-patch loss + global IIDLoss, summed, backward.  A pixel = one (n, u, v) site
+of one loss call.
+
+The JSON line carries, beyond the base contract:
+  value     device-timed throughput, inputs resident in HBM (CUDA-graph replay of the public-API step)
+  e2e       the same through the public modules with HOST (pinned) inputs: H2D of both views and the
+            global rows, forward, backward, D2H of the loss, every step
+  roofline  the dominant kernel (local_bwd_kernel, two launches per step): algorithmic bytes per
+            launch (8*K bytes/px: read one K-channel map, write one K-channel gradient) over its
+            CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+  cpu_baseline  oracle/torch_port.py (the reference's operator sequence) on the host cores, bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CFG = dict(B=32, K=10, H=224, W=224, pad=1, patch=512)
+METRIC = "iic_mi_loss_fwd_bwd_mpixels_per_s"
+UNIT = "Mpx/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA-graph replay")
+    ap.add_argument("--cpu-sample-batch", type=int, default=2)
+    return ap.parse_args()
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)", float(d.get("sm_max_mhz", 1965.0))
+    return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi during the timed region)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# synthetic inputs (correlated views so MI is O(0.1-1))
+# ---------------------------------------------------------------------------------------------------
+def make_inputs(torch, device, seed, B, K, H, W):
+    g = torch.Generator(device=device).manual_seed(seed)
+    base = torch.randn(B, K, H // 8, W // 8, device=device, generator=g) * 3
+    base = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False)
+    x = (base + 0.5 * torch.randn(B, K, H, W, device=device, generator=g)).softmax(1)
+    y = (base + 0.5 * torch.randn(B, K, H, W, device=device, generator=g)).softmax(1)
+    gb = torch.randn(B, K, device=device, generator=g) * 2
+    gx = (gb + 0.7 * torch.randn(B, K, device=device, generator=g)).softmax(1)
+    gy = (gb + 0.7 * torch.randn(B, K, device=device, generator=g)).softmax(1)
+    return x.contiguous(), y.contiguous(), gx.contiguous(), gy.contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: oracle/torch_port.py on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_throughput(batch, reps, threads=None):
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import torch_port as TP
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    K, H, W, pad, patch = CFG["K"], CFG["H"], CFG["W"], CFG["pad"], CFG["patch"]
+    g = torch.Generator().manual_seed(1236)
+    base = torch.nn.functional.interpolate(torch.randn(batch, K, H // 8, W // 8, generator=g) * 3, size=(H, W),
+                                           mode="bilinear", align_corners=False)
+    l1 = base + 0.5 * torch.randn(batch, K, H, W, generator=g)
+    l2 = base + 0.5 * torch.randn(batch, K, H, W, generator=g)
+    g1, g2 = torch.randn(batch, K, generator=g), torch.randn(batch, K, generator=g)
+    x, y, gx, gy = l1.softmax(1), l2.softmax(1), g1.softmax(1), g2.softmax(1)
+
+    def step():
+        xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+        ar, br = gx.clone().requires_grad_(True), gy.clone().requires_grad_(True)
+        loss = TP.iid_segmentation_small_path_loss(xr, yr, pad, patch) + TP.iid_loss(ar, br)[0]
+        loss.backward()
+        return loss.item()
+
+    step()  # warm
+    times = []
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+    px = batch * H * W + batch
+    best = min(times)
+    return px / best / 1e6, threads, best, times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(args.steps, 1), args.warmup
+    batch = args.cpu_sample_batch
+    # bound the whole run: at ~1 Mpx/s a batch-2 step is ~0.1-0.2 s
+    reps = min(steps, 20)
+    for _ in range(min(warm, 3)):
+        pass
+    v, threads, best, times = cpu_port_throughput(batch, reps)
+    ms = statistics.mean(times) * 1e3
+    sample = (f"config-2 shape at batch {batch} (of 32) x {CFG['K']} x {CFG['H']} x {CFG['W']}, local p=1 + global, "
+              f"fwd+bwd, best of {reps} steps, {threads} threads")
+    line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": reps, "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: global+local IIC (padding=1, patch 512) batch 32 fp32 [CPU sample]",
+                       "batch_sample": batch, "K": CFG["K"], "H": CFG["H"], "W": CFG["W"], "padding": CFG["pad"]},
+            "cpu_baseline": {"value": round(v, 4), "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": round(v, 4), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    import iic_b200
+    from iic_b200 import ops as iops
+
+    iic_b200.set_check_mode("deferred")       # checks run on the device; flags are read after the timed region
+    iic_b200.set_data_parallel(world > 1)
+    B, K, H, W, pad, patch = (CFG[k] for k in ("B", "K", "H", "W", "pad", "patch"))
+    hbm_peak, peak_src, sm_max = peaks()
+    px_step = B * H * W + B
+
+    local = iic_b200.IIDSegmentationSmallPathLoss(padding=pad, patch_size=patch)
+    glob = iic_b200.IIDLoss()
+
+    # 4 rotating input sets (4 x 128 MB of maps) so every step's inputs come from HBM, not from L2
+    NSETS = 4
+    sets = []
+    for s in range(NSETS):
+        x, y, gx, gy = make_inputs(torch, dev, 1236 + 17 * s + 1000 * rank, B, K, H, W)
+        sets.append([t.requires_grad_(True) for t in (x, y, gx, gy)])
+
+    def step(inp):
+        x, y, gx, gy = inp
+        loss = local(x, y) + glob(gx, gy)[0]
+        grads = torch.autograd.grad(loss, (x, y, gx, gy))
+        return loss, grads
+
+    # ---- CUDA graphs of the public-API step (one per input set) ----
+    graphs, use_graph = [], not args.no_graph
+    side = torch.cuda.Stream(device=dev)
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for inp in sets:
+            for _ in range(2):
+                out = step(inp)
+    torch.cuda.current_stream().wait_stream(side)
+    torch.cuda.synchronize()
+    if use_graph:
+        try:
+            for inp in sets:
+                gph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(gph, stream=side):
+                    out = step(inp)
+                graphs.append((gph, out))
+        except Exception as e:  # noqa: BLE001
+            if rank == 0:
+                print(f"[bench] CUDA graph capture failed ({type(e).__name__}: {e}); timing eager launches",
+                      file=sys.stderr)
+            graphs, use_graph = [], False
+            torch.cuda.synchronize()
+
+    def run_one(i):
+        if use_graph:
+            graphs[i % NSETS][0].replay()
+        else:
+            step(sets[i % NSETS])
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        run_one(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_wall0 = time.perf_counter()
+    e0.record()
+    for i in range(args.steps):
+        run_one(i)
+    e1.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    ms_total = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_step = ms_total / args.steps
+    value = world * px_step / (ms_step * 1e-3) / 1e6
+    iic_b200.raise_if_flagged(dev)           # the deferred simplex / NaN checks of every step above
+
+    # ---- per-kernel timing, eager, events on the launching stream ----
+    reps = 20
+    x, y, gx, gy = sets[0]
+    xd, yd = x.detach(), y.detach()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+    one = torch.ones((), device=dev)
+    t_joint = t_epi = t_bwd = 0.0
+    for r in range(reps + 3):
+        xs, ys = sets[r % NSETS][0].detach(), sets[r % NSETS][1].detach()
+        a, b, c, d = ev(), ev(), ev(), ev()
+        a.record()
+        J = iops.ops.local_joint(xs, ys, None, pad, patch, patch, patch // 2, patch // 2)
+        b.record()
+        loss, Wx, Wy = iops.ops.local_epilogue(J, K, pad, 1.0)
+        c.record()
+        gxx, gyy = iops.ops.local_backward(xs, ys, None, Wx, Wy, one, pad, patch, patch, patch // 2, patch // 2)
+        d.record()
+        torch.cuda.synchronize()
+        if r >= 3:
+            t_joint += a.elapsed_time(b)
+            t_epi += b.elapsed_time(c)
+            t_bwd += c.elapsed_time(d)
+    t_joint, t_epi, t_bwd = t_joint / reps, t_epi / reps, t_bwd / reps
+    bwd_launch_ms = t_bwd / 2.0                               # two sweeps = two launches of local_bwd_kernel
+    alg_bytes_launch = 8.0 * K * B * H * W                    # read one map + write one gradient, fp32
+    achieved = alg_bytes_launch / (bwd_launch_ms * 1e-3) / 1e9
+    sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
+    fma_per_launch = K * K * (2 * pad + 1) ** 2 * B * H * W   # useful FMAs of one sweep
+    fp32_peak = 148 * 128 * sm_mhz * 1e6                      # FMA/s at the observed clock
+    roofline = {"kernel": "local_bwd_kernel<3,10>", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
+                "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
+                "launch_ms": round(bwd_launch_ms, 4),
+                "note": "kernel is FP32-FMA bound (AI = K*T^2/4 = 22.5 flop/B > ridge); fp32_fma_frac is its fraction "
+                        "of 148 SM x 128 FMA/clk at the sampled SM clock",
+                "fp32_fma_frac": round(fma_per_launch / (bwd_launch_ms * 1e-3) / fp32_peak, 4),
+                "step_breakdown_ms": {"local_joint+reduce": round(t_joint, 4), "local_epilogue": round(t_epi, 4),
+                                      "local_backward(2 launches)": round(t_bwd, 4)},
+                "whole_step_hbm_frac": round(24.0 * K * B * H * W / (ms_step * 1e-3) / 1e9 / hbm_peak, 4)}
+
+    # ---- end to end through the public API with HOST buffers ----
+    hx, hy, hgx, hgy = (t.detach().cpu().pin_memory() for t in sets[0])
+    dx, dy = torch.empty_like(hx, device=dev), torch.empty_like(hy, device=dev)
+    dgx, dgy = torch.empty_like(hgx, device=dev), torch.empty_like(hgy, device=dev)
+    hloss = torch.empty((), dtype=torch.float32).pin_memory()
+    h2d = sum(t.numel() * 4 for t in (hx, hy, hgx, hgy))
+
+    def e2e_step():
+        dx.copy_(hx, non_blocking=True)
+        dy.copy_(hy, non_blocking=True)
+        dgx.copy_(hgx, non_blocking=True)
+        dgy.copy_(hgy, non_blocking=True)
+        a, b = dx.requires_grad_(True), dy.requires_grad_(True)
+        c, d = dgx.requires_grad_(True), dgy.requires_grad_(True)
+        loss = local(a, b) + glob(c, d)[0]
+        torch.autograd.grad(loss, (a, b, c, d))
+        hloss.copy_(loss.detach(), non_blocking=True)
+
+    e2e_steps = min(args.steps, 20)
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    f0, f1 = ev(), ev()
+    f0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    f1.record()
+    barrier()
+    te = torch.tensor([f0.elapsed_time(f1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_ms = float(te.item()) / e2e_steps
+    e2e_val = world * px_step / (e2e_ms * 1e-3) / 1e6
+    iic_b200.raise_if_flagged(dev)
+
+    if rank == 0:
+        cpu_v, cpu_threads, cpu_best, cpu_times = cpu_port_throughput(args.cpu_sample_batch, 5)
+        # launches per step: local = simplex + joint + reduce + epilogue + 2 x backward (6);
+        # global = 2 x simplex + joint + reduce + epilogue + backward (6)
+        launches = 12 * args.steps
+        line = {
+            "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "config2: global+local IIC (padding=1, patch 512) on Up_conv2-shaped maps, "
+                                   "batch 32 fp32 per GPU, fwd+bwd",
+                       "B_per_gpu": B, "K": K, "H": H, "W": W, "padding": pad, "patch_size": patch,
+                       "pixels_per_step_per_gpu": px_step,
+                       "launch": "cuda_graph_replay" if use_graph else "eager",
+                       "l2": f"inputs rotate over {NSETS} sets ({NSETS * 128} MB of maps) > 126 MB L2",
+                       "checks": "deferred (device-side simplex + NaN flags, read after the timed region)",
+                       "multi_gpu": "batch sharded; one NCCL all-reduce of the fp64 joints per loss call" if world > 1
+                       else "single GPU"},
+            "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+                    "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": {"value": round(cpu_v, 4), "unit": UNIT, "cores": cpu_threads, "kind": "port",
+                             "sample": f"config-2 shape at batch {args.cpu_sample_batch} (of 32), fwd+bwd, best of 5, "
+                                       f"oracle/torch_port.py"},
+            "wall_s_timed_region": round(t_wall, 4),
+        }
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

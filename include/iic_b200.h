@@ -1,0 +1,141 @@
+/*
+ * iic_b200.h -- C ABI of libiic_b200.so: the B200 (sm_100a) kernels behind the IIC
+ * mutual-information losses and the UDA consistency term.
+ *
+ * The reference (jizongFox/MI-based-Regularized-Semi-supervised-Segmentation) is pure Python and has
+ * no FFI of its own; the boundary it exposes is the loss-module API in
+ * contrastyou/losses/iic_loss.py.  Each entry point below states which reference lines it replaces.
+ * The Python host (package dir, ops.py) binds these with ctypes and wraps them as torch custom ops;
+ * INTEGRATION.md shows the stub.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - tensors are float32, innermost (W, or K for the (N,K) global case) stride 1, other strides
+ *     given in ELEMENTS;
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing synchronises;
+ *   - return value 0 = ok, non-zero = error (never throws); iic_b200_last_error() gives the text of
+ *     the calling thread's last error;
+ *   - no entry point has a CPU fallback: without a CUDA device every compute call fails.
+ */
+#ifndef IIC_B200_H_
+#define IIC_B200_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define IIC_B200_ABI_VERSION 1
+
+/* flag bits written (OR-ed) into the int* `flags` words by the kernels */
+#define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
+#define IIC_FLAG_NOT_SIMPLEX 2   /* dc2:utils/assertion.py:56-65 -> AssertionError on the host */
+
+int iic_b200_abi_version(void);
+const char* iic_b200_last_error(void);
+/* number of SMs of `device` (148 on B200); <0 on error */
+int iic_b200_sm_count(int device);
+
+/* ------------------------------------------------------------------------------------------------
+ * simplex assertion: flags |= IIC_FLAG_NOT_SIMPLEX unless |sum_c t[o,c,i] - 1| <= 2e-4 everywhere
+ * (NaN fails).  t is viewed as (outer, C, inner) with element strides (s_outer, s_c, 1).
+ * Replaces dc2:deepclustering2/utils/assertion.py:56-65 as called at iic_loss.py:50-51,82-83,113.
+ * ---------------------------------------------------------------------------------------------- */
+int iic_simplex_check(const float* t, long long outer, int C, long long inner,
+                      long long s_outer, long long s_c, int* flags, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Local (shifted-window) IIC.  Replaces IIDSegmentationLoss.__call__ (iic_loss.py:107-149) and the
+ * patch loop of IIDSegmentationSmallPathLoss.__call__ (iic_loss.py:171-186).
+ *
+ * Patches follow patch_generator (iic_loss.py:152-160): windows of (patch_h, patch_w) at steps
+ * (step_h, step_w) plus a last window flush with the border; patch_h >= H and patch_w >= W means one
+ * window = the whole map.  iic_local_num_patches returns how many windows that is.
+ * T = 2*pad + 1.  J is laid out [patch][dy][dx][i][j] (the reference's conv output permuted as at
+ * iic_loss.py:127).
+ * ---------------------------------------------------------------------------------------------- */
+int iic_local_num_patches(int H, int W, int patch_h, int patch_w, int step_h, int step_w);
+
+/* bytes of scratch iic_local_joint needs (per-CTA partial joints) */
+size_t iic_local_joint_workspace_bytes(int device, int B, int K, int H, int W, int pad,
+                                       int patch_h, int patch_w, int step_h, int step_w);
+
+/* J[patch][dy][dx][i][j] = sum_{n,u,v} x[n,i,u+dy-pad,v+dx-pad] * y[n,j,u,v]  over the patch, x zero
+ * outside the patch (iic_loss.py:120-123, the F.conv2d).  mask (nullable; (B,1|K,H,W), m_sc = 0 for
+ * one channel) multiplies both maps first (iic_loss.py:116-118).  Partial sums are fp32 inside one
+ * CTA, combined across CTAs in fp64 in a fixed order (deterministic). J_out is float64. */
+int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                    const float* y, long long y_sn, long long y_sc, long long y_sh,
+                    const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                    int B, int K, int H, int W, int pad,
+                    int patch_h, int patch_w, int step_h, int step_w,
+                    double* J_out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* number of floats in each of the Wx / Wy coefficient buffers written by iic_local_epilogue */
+size_t iic_local_coeff_floats(int K, int pad, int n_patches);
+
+/* From the (all-reduced) joint: min-shift, per-displacement normalise, symmetrise, marginals, entropy
+ * (iic_loss.py:124-146), mean over patches (iic_loss.py:186), and the analytic dL/dJ.
+ *   loss_out[0]  float32 loss;  loss64_out[0] (nullable) the same in float64
+ *   Wx, Wy       backward coefficients, dL/dJ re-laid for the two gradient sweeps
+ *   GA_out       (nullable) dL/dJ in J's layout, float64
+ *   flags        |= IIC_FLAG_NAN_LOSS if the loss is NaN
+ *   workspace    >= iic_local_epilogue_workspace_bytes, zero-initialised once by the caller */
+size_t iic_local_epilogue_workspace_bytes(int K, int pad, int n_patches);
+int iic_local_epilogue(const double* J, int K, int pad, int n_patches, double lamda,
+                       float* loss_out, double* loss64_out, float* Wx, float* Wy, double* GA_out,
+                       int* flags, void* workspace, void* stream);
+
+/* Both input gradients (what autograd's convolution_backward yields for iic_loss.py:123):
+ *   gx[n,i,a,b] (+)= g * mask * sum_{d,j} dL/dJ[d,i,j] * (mask*y)[n,j,a-dy+pad,b-dx+pad]
+ *   gy[n,j,u,v] (+)= g * mask * sum_{d,i} dL/dJ[d,i,j] * (mask*x)[n,i,u+dy-pad,v+dx-pad]
+ * g = *grad_loss (device scalar; NULL means 1).  gx/gy are dense NCHW (B,K,H,W); with more than one
+ * patch the caller zero-fills them first and every patch accumulates. */
+int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                       const float* y, long long y_sn, long long y_sc, long long y_sh,
+                       const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                       int B, int K, int H, int W, int pad,
+                       int patch_h, int patch_w, int step_h, int step_w,
+                       const float* Wx, const float* Wy, const float* grad_loss,
+                       float* gx, float* gy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Global IIC on (N,K) simplex rows.  Replaces compute_joint (iic_loss.py:74-94) and IIDLoss.forward
+ * (iic_loss.py:43-71).
+ * ---------------------------------------------------------------------------------------------- */
+size_t iic_global_joint_workspace_bytes(int device, long long N, int K);
+/* J[i][j] = sum_n x[n,i]*y[n,j]  (iic_loss.py:88-89), float64 out, deterministic */
+int iic_global_joint(const float* x, long long x_sn, const float* y, long long y_sn,
+                     long long N, int K, double* J_out, void* workspace, size_t workspace_bytes,
+                     void* stream);
+/* P = sym(J)/sum (iic_loss.py:91-92; symmetric=0 skips the symmetrisation), and when losses_out is
+ * non-NULL the two entropy expressions of iic_loss.py:63-69: losses_out[0]=loss(lamb),
+ * losses_out[1]=loss_no_lamb.  P_out is float32 (K,K). */
+int iic_global_epilogue(const double* J, int K, double lamb, int symmetric,
+                        float* losses_out, float* P_out, int* flags, void* stream);
+/* gradients of  g[0]*loss + g[1]*loss_no_lamb + <gP, P>  w.r.t. x and y, from the saved J.
+ * g (2 floats, nullable = {1,0}) and gP ((K,K) float32, nullable) are device pointers. */
+int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
+                        long long N, int K, const double* J, double lamb, int symmetric,
+                        const float* g, const float* gP, float* gx, float* gy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * UDA consistency on (outer, C, inner) contiguous maps.  kind 0 = torch.nn.MSELoss() mean over all
+ * elements; kind 1 = KL_div(reduction="mean") (dc2:deepclustering2/loss/kl_losses.py:107-126):
+ * sum_c -t*log((p+eps)/(t+eps)) * w_c, mean over outer*inner.  Call site semi_seg/epocher.py:221-224.
+ * from_logits != 0: prob/target hold logits and the channel softmax (epocher.py:222-223) is fused in;
+ * the gradient is then w.r.t. the prob logits.  The gradient flows to `prob` only.
+ * ---------------------------------------------------------------------------------------------- */
+size_t iic_uda_workspace_bytes(int device);
+int iic_uda_forward(const float* prob, const float* target, long long outer, int C, long long inner,
+                    int kind, double eps, const float* weight, int from_logits,
+                    float* loss_out, int* flags, int check_simplex, void* workspace, void* stream);
+int iic_uda_backward(const float* prob, const float* target, long long outer, int C, long long inner,
+                     int kind, double eps, const float* weight, int from_logits,
+                     const float* grad_loss, float* grad_prob, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IIC_B200_H_ */

@@ -1,0 +1,16 @@
+"""B200-native IIC mutual-information losses + UDA consistency (drop-in for the reference's loss API).
+
+Import as ``iic_b200`` (the importable alias at the repo root); this directory carries the name the
+project layout asks for, which is not a valid Python identifier.
+"""
+from . import _lib, checks, ops  # noqa: F401
+from .checks import check_mode, get_check_mode, raise_if_flagged, set_check_mode  # noqa: F401
+from .losses.iic_loss import (IIDLoss, IIDSegmentationLoss, IIDSegmentationSmallPathLoss, compute_joint,  # noqa: F401
+                              patch_generator)
+from .losses.kl_losses import KL_div, MSELoss, uda_from_logits  # noqa: F401
+from .ops import set_data_parallel  # noqa: F401
+from .semi_seg._utils import IICLossWrapper  # noqa: F401
+
+__all__ = ["IIDLoss", "IIDSegmentationLoss", "IIDSegmentationSmallPathLoss", "compute_joint", "patch_generator",
+           "KL_div", "MSELoss", "uda_from_logits", "IICLossWrapper", "set_check_mode", "get_check_mode",
+           "check_mode", "raise_if_flagged", "set_data_parallel"]

@@ -1,0 +1,428 @@
+// Small-matrix stages of the IIC losses, all in float64:
+//   * local epilogue: min-shift, per-displacement normalise, symmetrise, marginals, entropy and the
+//     analytic dL/dJ                                    (contrastyou/losses/iic_loss.py:124-146,186)
+//   * global joint / epilogue / backward on (N,K) rows  (contrastyou/losses/iic_loss.py:43-94)
+#include "common.cuh"
+
+namespace iic {
+
+// ======================================================================================================
+// local epilogue: one CTA per (patch, displacement)
+// ======================================================================================================
+struct EpiWorkspace {       // lives at the start of the caller-provided workspace
+  unsigned int ticket;      // self-resetting arrival counter
+  unsigned int pad_;
+};
+// followed by double partial_loss[n_patches * T * T]
+
+__global__ void __launch_bounds__(256) local_epilogue_kernel(
+    const double* __restrict__ J, int K, int T, int n_patches, double lamda, float* __restrict__ loss_out,
+    double* __restrict__ loss64_out, float* __restrict__ Wx, float* __restrict__ Wy,
+    double* __restrict__ GA_out, int* __restrict__ flags, EpiWorkspace* ws) {
+  extern __shared__ __align__(16) double sm[];
+  double* scratch = sm;            // 33
+  double* marg = sm + 40;          // K : marginal (row sum == column sum of the symmetric P)
+  double* lm = marg + K;           // K : log(marg + eps)
+  double* gm = lm + K;             // K : log(marg + eps) + marg / (marg + eps)
+  double* partial_loss = reinterpret_cast<double*>(ws + 1);
+
+  const int T2 = T * T;
+  const int patch = blockIdx.x / T2, d = blockIdx.x % T2;
+  const int dy = d / T, dx = d % T;
+  const size_t KK = (size_t)K * K;
+  const double* Jp = J + (size_t)patch * T2 * KK;
+  const double* Jd = Jp + (size_t)d * KK;
+  const double eps = 1e-16;
+  const int Kp = (K + 3) & ~3;
+  const int tid = threadIdx.x, nt = blockDim.x;
+
+  // 1. m = min over every displacement and both cluster axes of this patch (iic_loss.py:124)
+  double mn = __longlong_as_double(0x7ff0000000000000LL);
+  bool has_nan = false;
+  for (size_t e = tid; e < (size_t)T2 * KK; e += nt) {
+    const double v = Jp[e];
+    has_nan |= (v != v);
+    mn = fmin(mn, v);
+  }
+  const double m = block_min_nan(mn, has_nan, scratch);
+
+  // 2. A = J_d - m + 1e-16 ; s = sum A ; marginals of P = (A + A^T) / (2 s)
+  for (int k = tid; k < K; k += nt) {
+    double rs = 0.0, cs = 0.0;
+    for (int q = 0; q < K; ++q) {
+      rs += Jd[(size_t)k * K + q] - m + 1e-16;
+      cs += Jd[(size_t)q * K + k] - m + 1e-16;
+    }
+    marg[k] = rs + cs;        // scaled by 1/(2s) below
+    lm[k] = rs;               // stash the row sum for the total
+  }
+  __syncthreads();
+  double part = 0.0;
+  for (int k = tid; k < K; k += nt) part += lm[k];
+  const double s = block_sum(part, scratch);
+  for (int k = tid; k < K; k += nt) {
+    const double mk = marg[k] / (2.0 * s);
+    marg[k] = mk;
+    lm[k] = log(mk + eps);
+    gm[k] = lm[k] + mk / (mk + eps);
+  }
+  __syncthreads();
+
+  // 3. loss_d and tot = sum_ij GQ_ij Q_ij.  P is symmetric and its row and column marginals agree, so
+  //    GP (d loss / d P) is symmetric too and GQ = (GP + GP^T)/2 = GP.
+  double l_part = 0.0, t_part = 0.0;
+  for (size_t e = tid; e < KK; e += nt) {
+    const int i = (int)(e / K), j = (int)(e % K);
+    const double a = Jd[e] - m + 1e-16, at = Jd[(size_t)j * K + i] - m + 1e-16;
+    const double q = a / s;
+    const double p = (a + at) / (2.0 * s);
+    const double lp = log(p + eps);
+    l_part += -p * (lp - lamda * lm[j] - lamda * lm[i]);
+    const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
+    t_part += gq * q;
+  }
+  const double loss_d = block_sum(l_part, scratch);
+  const double tot = block_sum(t_part, scratch);
+
+  // 4. GA = dL/dJ_d = (GQ - tot) / s, scaled by 1/(T^2 n_patches); write the two sweep layouts
+  //    Wy[patch][cin=i][dy*T+dx][j]            (gy[j] += Wy * x_i shifted by (dy-pad, dx-pad))
+  //    Wx[patch][cin=j][(T-1-dy)*T+(T-1-dx)][i] (gx[i] += Wx * y_j shifted by (pad-dy, pad-dx))
+  const double scale = 1.0 / ((double)T2 * (double)n_patches);
+  float* Wxp = Wx + (size_t)patch * K * T2 * Kp;
+  float* Wyp = Wy + (size_t)patch * K * T2 * Kp;
+  const int dflip = (T - 1 - dy) * T + (T - 1 - dx);
+  for (size_t e = tid; e < (size_t)K * Kp; e += nt) {
+    const int a_ = (int)(e / Kp), b_ = (int)(e % Kp);   // a_ = cin, b_ = cout (padded)
+    float wy = 0.f, wx = 0.f;
+    if (b_ < K) {
+      // Wy: cin = i = a_, cout = j = b_ ; Wx: cin = j = a_, cout = i = b_.  GA is symmetric in (i,j)
+      // only through GQ; (GQ - tot)/s is symmetric as well, so one evaluation serves both.
+      const int i = a_, j = b_;
+      const double a = Jd[(size_t)i * K + j] - m + 1e-16, at = Jd[(size_t)j * K + i] - m + 1e-16;
+      const double p = (a + at) / (2.0 * s);
+      const double lp = log(p + eps);
+      const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
+      const double ga = (gq - tot) / s * scale;
+      wy = (float)ga;
+      wx = (float)ga;
+      if (GA_out) {
+        GA_out[((size_t)patch * T2 + d) * KK + (size_t)i * K + j] = ga;
+      }
+    }
+    Wyp[((size_t)a_ * T2 + d) * Kp + b_] = wy;
+    Wxp[((size_t)a_ * T2 + dflip) * Kp + b_] = wx;
+  }
+
+  // 5. last CTA sums the per-displacement losses in index order (deterministic)
+  __shared__ bool is_last;
+  if (tid == 0) {
+    partial_loss[blockIdx.x] = loss_d;
+    __threadfence();
+    const unsigned int prev = atomicAdd(&ws->ticket, 1u);
+    is_last = (prev == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last && tid == 0) {
+    __threadfence();
+    double total = 0.0;
+    const volatile double* pl = partial_loss;
+    for (unsigned int b = 0; b < gridDim.x; ++b) total += pl[b];
+    total *= scale;
+    loss_out[0] = (float)total;
+    if (loss64_out) loss64_out[0] = total;
+    if (total != total) atomicOr(flags, IIC_FLAG_NAN_LOSS);
+    ws->ticket = 0;
+  }
+}
+
+// ======================================================================================================
+// global IIC on (N,K) rows
+// ======================================================================================================
+// Each thread owns output entries e = tid, tid + nt, ... (at most GLOBAL_EPT) and walks the CTA's rows,
+// staged in shared memory; float64 accumulation (the contraction is tiny).
+constexpr int GLOBAL_EPT = 16;
+constexpr int GLOBAL_ROWS = 32;
+
+__global__ void __launch_bounds__(1024) global_joint_kernel(const float* __restrict__ x, long long x_sn,
+                                                            const float* __restrict__ y, long long y_sn,
+                                                            long long N, int K, long long rows_per_cta,
+                                                            double* __restrict__ partial) {
+  extern __shared__ __align__(16) float gsm[];
+  float* xs = gsm;                       // [GLOBAL_ROWS][K]
+  float* ys = gsm + GLOBAL_ROWS * K;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int KK = K * K;
+  double acc[GLOBAL_EPT];
+#pragma unroll
+  for (int q = 0; q < GLOBAL_EPT; ++q) acc[q] = 0.0;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > N) r1 = N;
+  for (long long rb = r0; rb < r1; rb += GLOBAL_ROWS) {
+    const int nr = (int)((r1 - rb) < GLOBAL_ROWS ? (r1 - rb) : GLOBAL_ROWS);
+    __syncthreads();
+    for (int e = tid; e < nr * K; e += nt) {
+      const int r = e / K, c = e % K;
+      xs[e] = x[(rb + r) * x_sn + c];
+      ys[e] = y[(rb + r) * y_sn + c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < GLOBAL_EPT; ++q) {
+      const int e = tid + q * nt;
+      if (e < KK) {
+        const int i = e / K, j = e % K;
+        double a = acc[q];
+        for (int r = 0; r < nr; ++r) a += (double)xs[r * K + i] * (double)ys[r * K + j];
+        acc[q] = a;
+      }
+    }
+  }
+#pragma unroll
+  for (int q = 0; q < GLOBAL_EPT; ++q) {
+    const int e = tid + q * nt;
+    if (e < KK) partial[(size_t)blockIdx.x * KK + e] = acc[q];
+  }
+}
+
+__global__ void global_reduce_kernel(const double* __restrict__ partial, int ncta, int KK,
+                                     double* __restrict__ J) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= KK) return;
+  double s = 0.0;
+  for (int c = 0; c < ncta; ++c) s += partial[(size_t)c * KK + e];
+  J[e] = s;
+}
+
+// shared derivation for the global epilogue / backward: from J build S, marginals of P
+struct GlobalStats { double S; };
+
+// single CTA: P = sym(J)/S ; losses (iic_loss.py:56-69)
+__global__ void __launch_bounds__(1024) global_epilogue_kernel(const double* __restrict__ J, int K,
+                                                               double lamb, int symmetric,
+                                                               float* __restrict__ losses_out,
+                                                               float* __restrict__ P_out,
+                                                               int* __restrict__ flags) {
+  extern __shared__ __align__(16) double sm[];
+  double* scratch = sm;      // 33
+  double* pi = sm + 40;      // K  row marginals    p_i = sum_j P[i][j]
+  double* pj = pi + K;       // K  column marginals p_j = sum_i P[i][j]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t KK = (size_t)K * K;
+  const double eps = 1e-10;
+  auto Jsym = [&](int i, int j) {
+    return symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
+  };
+  double part = 0.0;
+  for (size_t e = tid; e < KK; e += nt) part += Jsym((int)(e / K), (int)(e % K));
+  const double S = block_sum(part, scratch);
+  for (int k = tid; k < K; k += nt) {
+    double r = 0.0, c = 0.0;
+    for (int q = 0; q < K; ++q) {
+      r += Jsym(k, q);
+      c += Jsym(q, k);
+    }
+    pi[k] = r / S;
+    pj[k] = c / S;
+  }
+  __syncthreads();
+  double l1 = 0.0, l2 = 0.0;
+  for (size_t e = tid; e < KK; e += nt) {
+    const int i = (int)(e / K), j = (int)(e % K);
+    const double p = Jsym(i, j) / S;
+    if (P_out) P_out[e] = (float)p;
+    if (losses_out) {
+      const double lp = log(p + eps), lj = log(pj[j] + eps), li = log(pi[i] + eps);
+      l1 += -p * (lp - lamb * lj - lamb * li);
+      l2 += -p * (lp - lj - li);
+    }
+  }
+  if (losses_out) {
+    const double L1 = block_sum(l1, scratch);
+    const double L2 = block_sum(l2, scratch);
+    if (tid == 0) {
+      losses_out[0] = (float)L1;
+      losses_out[1] = (float)L2;
+      if (L1 != L1 || L2 != L2) atomicOr(flags, IIC_FLAG_NAN_LOSS);
+    }
+  }
+}
+
+// Every CTA rebuilds GJ = d(objective)/dJ in shared memory (K*K doubles -> floats), then produces a
+// slab of rows of gx = y GJ^T and gy = x GJ.
+__global__ void __launch_bounds__(256) global_backward_kernel(
+    const float* __restrict__ x, long long x_sn, const float* __restrict__ y, long long y_sn, long long N,
+    int K, const double* __restrict__ J, double lamb, int symmetric, const float* __restrict__ g,
+    const float* __restrict__ gP, float* __restrict__ gx, float* __restrict__ gy,
+    long long rows_per_cta) {
+  extern __shared__ __align__(16) double sm[];
+  double* scratch = sm;            // 33
+  double* pi = sm + 40;            // K
+  double* pj = pi + K;             // K
+  double* gi = pj + K;             // K : log(pi+eps) + pi/(pi+eps)
+  double* gj = gi + K;             // K
+  float* GJ = reinterpret_cast<float*>(gj + K);   // K*K floats : dObj/dJ[i][j]
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const size_t KK = (size_t)K * K;
+  const double eps = 1e-10;
+  const double g1 = g ? (double)g[0] : 1.0, g2 = g ? (double)g[1] : 0.0;
+  auto Jsym = [&](int i, int j) {
+    return symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
+  };
+  double part = 0.0;
+  for (size_t e = tid; e < KK; e += nt) part += Jsym((int)(e / K), (int)(e % K));
+  const double S = block_sum(part, scratch);
+  for (int k = tid; k < K; k += nt) {
+    double r = 0.0, c = 0.0;
+    for (int q = 0; q < K; ++q) {
+      r += Jsym(k, q);
+      c += Jsym(q, k);
+    }
+    pi[k] = r / S;
+    pj[k] = c / S;
+    gi[k] = log(pi[k] + eps) + pi[k] / (pi[k] + eps);
+    gj[k] = log(pj[k] + eps) + pj[k] / (pj[k] + eps);
+  }
+  __syncthreads();
+  // GP = g1*GP(lamb) + g2*GP(1) + gP ;  tot = sum GP * P
+  auto GP = [&](int i, int j) {
+    const double p = Jsym(i, j) / S;
+    const double base = -log(p + eps) - p / (p + eps);
+    const double mterm = gj[j] + gi[i];
+    double v = g1 * (base + lamb * mterm) + g2 * (base + mterm);
+    if (gP) v += (double)gP[(size_t)i * K + j];
+    return v;
+  };
+  double t_part = 0.0;
+  for (size_t e = tid; e < KK; e += nt) {
+    const int i = (int)(e / K), j = (int)(e % K);
+    t_part += GP(i, j) * (Jsym(i, j) / S);
+  }
+  const double tot = block_sum(t_part, scratch);
+  for (size_t e = tid; e < KK; e += nt) {
+    const int i = (int)(e / K), j = (int)(e % K);
+    double v;
+    if (symmetric) v = ((GP(i, j) - tot) / S + (GP(j, i) - tot) / S) / 2.0;   // adjoint of (J + J^T)/2
+    else v = (GP(i, j) - tot) / S;
+    GJ[e] = (float)v;
+  }
+  __syncthreads();
+  // gx[n][i] = sum_j GJ[i][j] y[n][j] ; gy[n][j] = sum_i GJ[i][j] x[n][i]
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > N) r1 = N;
+  const long long total = (r1 - r0) * K;
+  for (long long e = tid; e < total; e += nt) {
+    const long long n = r0 + e / K;
+    const int c = (int)(e % K);
+    const float* xr = x + n * x_sn;
+    const float* yr = y + n * y_sn;
+    float ax = 0.f, ay = 0.f;
+    for (int q = 0; q < K; ++q) {
+      ax = fmaf(GJ[(size_t)c * K + q], yr[q], ax);
+      ay = fmaf(GJ[(size_t)q * K + c], xr[q], ay);
+    }
+    gx[n * K + c] = ax;
+    gy[n * K + c] = ay;
+  }
+}
+
+static int global_grid(int device, long long N, long long* rows_per_cta) {
+  int sms = sm_count_cached(device);
+  if (sms <= 0) sms = 148;
+  long long ctas = (N + 255) / 256;          // >= 256 rows per CTA before spreading over more SMs
+  if (ctas > sms) ctas = sms;
+  if (ctas < 1) ctas = 1;
+  *rows_per_cta = (N + ctas - 1) / ctas;
+  return (int)((N + *rows_per_cta - 1) / *rows_per_cta);
+}
+
+}  // namespace iic
+
+using namespace iic;
+
+extern "C" size_t iic_local_coeff_floats(int K, int pad, int n_patches) {
+  const int T = 2 * pad + 1, Kp = (K + 3) & ~3;
+  return (size_t)n_patches * K * T * T * Kp;
+}
+
+extern "C" size_t iic_local_epilogue_workspace_bytes(int K, int pad, int n_patches) {
+  (void)K;
+  const int T = 2 * pad + 1;
+  return sizeof(EpiWorkspace) + (size_t)n_patches * T * T * sizeof(double);
+}
+
+extern "C" int iic_local_epilogue(const double* J, int K, int pad, int n_patches, double lamda,
+                                  float* loss_out, double* loss64_out, float* Wx, float* Wy,
+                                  double* GA_out, int* flags, void* workspace, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(J && loss_out && Wx && Wy && flags && workspace, "iic_local_epilogue: null pointer");
+  IIC_REQUIRE(K > 0 && pad >= 0 && n_patches > 0, "iic_local_epilogue: bad sizes K=%d pad=%d patches=%d",
+              K, pad, n_patches);
+  const int T = 2 * pad + 1;
+  const size_t smem = (40 + 3 * (size_t)K) * sizeof(double);
+  local_epilogue_kernel<<<n_patches * T * T, 256, smem, st>>>(J, K, T, n_patches, lamda, loss_out,
+                                                               loss64_out, Wx, Wy, GA_out, flags,
+                                                               (EpiWorkspace*)workspace);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" size_t iic_global_joint_workspace_bytes(int device, long long N, int K) {
+  long long rpc;
+  const int ctas = global_grid(device, N > 0 ? N : 1, &rpc);
+  return (size_t)ctas * K * K * sizeof(double);
+}
+
+extern "C" int iic_global_joint(const float* x, long long x_sn, const float* y, long long y_sn,
+                                long long N, int K, double* J_out, void* workspace,
+                                size_t workspace_bytes, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(x && y && J_out, "iic_global_joint: null pointer");
+  IIC_REQUIRE(N > 0 && K > 0, "iic_global_joint: empty input (N=%lld K=%d)", N, K);
+  IIC_REQUIRE((long long)K * K <= 1024LL * GLOBAL_EPT, "iic_global_joint: K=%d too large (max 128)", K);
+  long long rpc;
+  const int ctas = global_grid(current_device(), N, &rpc);
+  const size_t need = (size_t)ctas * K * K * sizeof(double);
+  IIC_REQUIRE(workspace && workspace_bytes >= need, "iic_global_joint: workspace too small (%zu < %zu)",
+              workspace_bytes, need);
+  int nt = K * K;
+  nt = nt > 1024 ? 1024 : ((nt + 31) & ~31);
+  const size_t smem = 2 * (size_t)GLOBAL_ROWS * K * sizeof(float);
+  global_joint_kernel<<<ctas, nt, smem, st>>>(x, x_sn, y, y_sn, N, K, rpc, (double*)workspace);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  global_reduce_kernel<<<(K * K + 255) / 256, 256, 0, st>>>((const double*)workspace, ctas, K * K, J_out);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int iic_global_epilogue(const double* J, int K, double lamb, int symmetric,
+                                   float* losses_out, float* P_out, int* flags, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(J && K > 0, "iic_global_epilogue: bad arguments");
+  IIC_REQUIRE(!losses_out || flags, "iic_global_epilogue: flags required with losses_out");
+  const size_t smem = (40 + 2 * (size_t)K) * sizeof(double);
+  int nt = K * K;
+  nt = nt > 1024 ? 1024 : ((nt + 31) & ~31);
+  global_epilogue_kernel<<<1, nt, smem, st>>>(J, K, lamb, symmetric, losses_out, P_out, flags);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
+                                   long long N, int K, const double* J, double lamb, int symmetric,
+                                   const float* g, const float* gP, float* gx, float* gy, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(x && y && J && gx && gy, "iic_global_backward: null pointer");
+  IIC_REQUIRE(N > 0 && K > 0 && K <= 128, "iic_global_backward: bad sizes N=%lld K=%d", N, K);
+  long long rpc;
+  const int ctas = global_grid(current_device(), N, &rpc);
+  const size_t smem = (40 + 4 * (size_t)K) * sizeof(double) + (size_t)K * K * sizeof(float);
+  auto kern = global_backward_kernel;
+  if (smem > 48 * 1024) {
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g, gP, gx, gy, rpc);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,400 @@
+"""torch custom ops (namespace ``iic_b200``) over the C-ABI CUDA library, plus their autograd glue.
+
+Every op is CUDA-only and calls straight into libiic_b200.so through ctypes with raw device pointers
+and the current CUDA stream; there is no eager/PyTorch fallback.  Nothing here synchronises the host,
+so a whole loss forward+backward can be captured in a CUDA graph.
+
+The mathematical contract of each op (reference file:line) is stated in include/iic_b200.h.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+_LIBDEF = torch.library.Library("iic_b200", "DEF")
+_LIBDEF.define("local_joint(Tensor x, Tensor y, Tensor? mask, int pad, int patch_h, int patch_w, "
+               "int step_h, int step_w) -> Tensor")
+_LIBDEF.define("local_epilogue(Tensor J, int K, int pad, float lamda) -> (Tensor, Tensor, Tensor)")
+_LIBDEF.define("local_backward(Tensor x, Tensor y, Tensor? mask, Tensor Wx, Tensor Wy, Tensor grad, int pad, "
+               "int patch_h, int patch_w, int step_h, int step_w) -> (Tensor, Tensor)")
+_LIBDEF.define("global_joint(Tensor x, Tensor y) -> Tensor")
+_LIBDEF.define("global_epilogue(Tensor J, float lamb, bool symmetric, bool want_losses) -> (Tensor, Tensor)")
+_LIBDEF.define("global_backward(Tensor x, Tensor y, Tensor J, float lamb, bool symmetric, Tensor? g, Tensor? gP) "
+               "-> (Tensor, Tensor)")
+_LIBDEF.define("uda_forward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
+               "bool check_simplex) -> Tensor")
+_LIBDEF.define("uda_backward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
+               "Tensor grad) -> Tensor")
+_LIBDEF.define("simplex_check(Tensor t, int axis) -> ()")
+
+
+# ---- per (device, stream) persistent state ---------------------------------------------------------
+class _StreamState:
+    """Sticky flag word + small zero-initialised, self-resetting kernel workspaces."""
+
+    def __init__(self, device: torch.device):
+        lib = _lib.load()
+        self.flags = torch.zeros(1, dtype=torch.int32, device=device)
+        self.uda_ws = torch.zeros(lib.iic_uda_workspace_bytes(device.index or 0), dtype=torch.uint8, device=device)
+        self.epi_ws = {}
+
+    def epilogue_ws(self, K: int, pad: int, n_patches: int, device) -> torch.Tensor:
+        key = (pad, n_patches)
+        ws = self.epi_ws.get(key)
+        if ws is None:
+            nbytes = _lib.load().iic_local_epilogue_workspace_bytes(K, pad, n_patches)
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+            self.epi_ws[key] = ws
+        return ws
+
+
+_states = {}
+
+
+def _state(device: torch.device) -> _StreamState:
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    st = _states.get(key)
+    if st is None:
+        st = _StreamState(device)
+        _states[key] = st
+    return st
+
+
+def flags_tensor(device) -> torch.Tensor:
+    """The sticky int32 flag word (IIC_FLAG_*) of the current stream of `device`."""
+    return _state(torch.device(device)).flags
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _require_cuda_f32(name: str, t: torch.Tensor):
+    if not t.is_cuda:
+        raise _lib.IICLibraryError(f"iic_b200: `{name}` must be a CUDA tensor (there is no CPU path); got {t.device}")
+    if t.dtype != torch.float32:
+        raise TypeError(f"iic_b200: `{name}` must be float32, got {t.dtype}")
+
+
+def _w_contig(t: torch.Tensor) -> torch.Tensor:
+    """The kernels need unit innermost stride; anything else is copied (patch views are fine)."""
+    return t if t.stride(-1) == 1 else t.contiguous()
+
+
+def _mask_args(mask: Optional[torch.Tensor], x: torch.Tensor):
+    if mask is None:
+        return None, 0, 0, 0
+    _require_cuda_f32("mask", mask)
+    B, K, H, W = x.shape
+    if mask.dim() != 4 or mask.shape[0] != B or mask.shape[2:] != x.shape[2:] or mask.shape[1] not in (1, K):
+        raise ValueError(f"iic_b200: mask shape {tuple(mask.shape)} does not broadcast to {tuple(x.shape)}")
+    mask = _w_contig(mask)
+    return mask, mask.stride(0), (0 if mask.shape[1] == 1 else mask.stride(1)), mask.stride(2)
+
+
+# ---- op implementations ------------------------------------------------------------------------------
+def _local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w):
+    lib = _lib.load()
+    _require_cuda_f32("x_out", x)
+    _require_cuda_f32("x_tf_out", y)
+    if x.dim() != 4 or x.shape != y.shape:
+        raise ValueError(f"iic_b200.local_joint: shapes {tuple(x.shape)} vs {tuple(y.shape)}")
+    x, y = _w_contig(x), _w_contig(y)
+    B, K, H, W = x.shape
+    m, msn, msc, msh = _mask_args(mask, x)
+    npatch = lib.iic_local_num_patches(H, W, patch_h, patch_w, step_h, step_w)
+    if npatch <= 0:
+        _lib.check(1, "iic_local_num_patches")
+    T = 2 * pad + 1
+    dev = x.device.index
+    nbytes = lib.iic_local_joint_workspace_bytes(dev, B, K, H, W, pad, patch_h, patch_w, step_h, step_w)
+    if nbytes == 0:
+        _lib.check(1, "iic_local_joint_workspace_bytes")
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    J = torch.empty((npatch, T, T, K, K), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.iic_local_joint(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                 y.data_ptr(), y.stride(0), y.stride(1), y.stride(2),
+                                 _ptr(m), msn, msc, msh, B, K, H, W, pad, patch_h, patch_w, step_h, step_w,
+                                 J.data_ptr(), ws.data_ptr(), nbytes, _stream(x.device))
+    _lib.check(rc, "iic_local_joint")
+    return J
+
+
+def _local_epilogue(J, K, pad, lamda):
+    lib = _lib.load()
+    if not J.is_cuda or J.dtype != torch.float64 or not J.is_contiguous():
+        raise TypeError("iic_b200.local_epilogue: J must be a contiguous CUDA float64 tensor")
+    npatch = J.shape[0]
+    st = _state(J.device)
+    loss = torch.empty((), dtype=torch.float32, device=J.device)
+    n = lib.iic_local_coeff_floats(K, pad, npatch)
+    Wx = torch.empty(n, dtype=torch.float32, device=J.device)
+    Wy = torch.empty(n, dtype=torch.float32, device=J.device)
+    ws = st.epilogue_ws(K, pad, npatch, J.device)
+    with torch.cuda.device(J.device):
+        rc = lib.iic_local_epilogue(J.data_ptr(), K, pad, npatch, float(lamda), loss.data_ptr(), None,
+                                    Wx.data_ptr(), Wy.data_ptr(), None, st.flags.data_ptr(), ws.data_ptr(),
+                                    _stream(J.device))
+    _lib.check(rc, "iic_local_epilogue")
+    return loss, Wx, Wy
+
+
+def _local_backward(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, step_w):
+    lib = _lib.load()
+    x, y = _w_contig(x), _w_contig(y)
+    B, K, H, W = x.shape
+    m, msn, msc, msh = _mask_args(mask, x)
+    npatch = lib.iic_local_num_patches(H, W, patch_h, patch_w, step_h, step_w)
+    alloc = torch.zeros if npatch > 1 else torch.empty
+    gx = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
+    gy = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
+    grad = grad.to(torch.float32).reshape(())
+    with torch.cuda.device(x.device):
+        rc = lib.iic_local_backward(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                    y.data_ptr(), y.stride(0), y.stride(1), y.stride(2),
+                                    _ptr(m), msn, msc, msh, B, K, H, W, pad, patch_h, patch_w, step_h, step_w,
+                                    Wx.data_ptr(), Wy.data_ptr(), grad.data_ptr(), gx.data_ptr(), gy.data_ptr(),
+                                    _stream(x.device))
+    _lib.check(rc, "iic_local_backward")
+    return gx, gy
+
+
+def _global_joint(x, y):
+    lib = _lib.load()
+    _require_cuda_f32("x_out", x)
+    _require_cuda_f32("x_tf_out", y)
+    if x.dim() != 2 or x.shape != y.shape:
+        raise ValueError(f"iic_b200.global_joint: shapes {tuple(x.shape)} vs {tuple(y.shape)}")
+    x, y = _w_contig(x), _w_contig(y)
+    N, K = x.shape
+    nbytes = lib.iic_global_joint_workspace_bytes(x.device.index, N, K)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    J = torch.empty((K, K), dtype=torch.float64, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.iic_global_joint(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N, K, J.data_ptr(),
+                                  ws.data_ptr(), nbytes, _stream(x.device))
+    _lib.check(rc, "iic_global_joint")
+    return J
+
+
+def _global_epilogue(J, lamb, symmetric, want_losses):
+    lib = _lib.load()
+    K = J.shape[0]
+    st = _state(J.device)
+    losses = torch.empty(2, dtype=torch.float32, device=J.device)
+    P = torch.empty((K, K), dtype=torch.float32, device=J.device)
+    with torch.cuda.device(J.device):
+        rc = lib.iic_global_epilogue(J.data_ptr(), K, float(lamb), int(symmetric),
+                                     losses.data_ptr() if want_losses else None, P.data_ptr(),
+                                     st.flags.data_ptr(), _stream(J.device))
+    _lib.check(rc, "iic_global_epilogue")
+    return losses, P
+
+
+def _global_backward(x, y, J, lamb, symmetric, g, gP):
+    lib = _lib.load()
+    x, y = _w_contig(x), _w_contig(y)
+    N, K = x.shape
+    gx = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    gy = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    if g is not None:
+        g = g.to(torch.float32).contiguous()
+    if gP is not None:
+        gP = gP.to(torch.float32).contiguous()
+    with torch.cuda.device(x.device):
+        rc = lib.iic_global_backward(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N, K, J.data_ptr(),
+                                     float(lamb), int(symmetric), _ptr(g), _ptr(gP), gx.data_ptr(), gy.data_ptr(),
+                                     _stream(x.device))
+    _lib.check(rc, "iic_global_backward")
+    return gx, gy
+
+
+def _as_oci(t: torch.Tensor) -> Tuple[int, int, int]:
+    outer, C = t.shape[0], t.shape[1]
+    inner = 1
+    for s in t.shape[2:]:
+        inner *= s
+    return outer, C, inner
+
+
+def _uda_forward(prob, target, kind, eps, weight, from_logits, check_simplex):
+    lib = _lib.load()
+    _require_cuda_f32("prob", prob)
+    _require_cuda_f32("target", target)
+    if prob.shape != target.shape or prob.dim() < 2:
+        raise ValueError(f"iic_b200.uda_forward: shapes {tuple(prob.shape)} vs {tuple(target.shape)}")
+    prob, target = prob.contiguous(), target.contiguous()
+    outer, C, inner = _as_oci(prob)
+    st = _state(prob.device)
+    loss = torch.empty((), dtype=torch.float32, device=prob.device)
+    if weight is not None:
+        weight = weight.to(device=prob.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(prob.device):
+        rc = lib.iic_uda_forward(prob.data_ptr(), target.data_ptr(), outer, C, inner, kind, float(eps), _ptr(weight),
+                                 int(from_logits), loss.data_ptr(), st.flags.data_ptr(), int(check_simplex),
+                                 st.uda_ws.data_ptr(), _stream(prob.device))
+    _lib.check(rc, "iic_uda_forward")
+    return loss
+
+
+def _uda_backward(prob, target, kind, eps, weight, from_logits, grad):
+    lib = _lib.load()
+    prob, target = prob.contiguous(), target.contiguous()
+    outer, C, inner = _as_oci(prob)
+    out = torch.empty_like(prob)
+    grad = grad.to(torch.float32).reshape(())
+    if weight is not None:
+        weight = weight.to(device=prob.device, dtype=torch.float32).contiguous()
+    with torch.cuda.device(prob.device):
+        rc = lib.iic_uda_backward(prob.data_ptr(), target.data_ptr(), outer, C, inner, kind, float(eps), _ptr(weight),
+                                  int(from_logits), grad.data_ptr(), out.data_ptr(), _stream(prob.device))
+    _lib.check(rc, "iic_uda_backward")
+    return out
+
+
+def _simplex_check(t, axis):
+    lib = _lib.load()
+    _require_cuda_f32("tensor", t)
+    if axis != 1:
+        raise ValueError("iic_b200.simplex_check: only axis=1 is used by the reference path")
+    t = t.contiguous()
+    outer, C, inner = _as_oci(t)
+    st = _state(t.device)
+    with torch.cuda.device(t.device):
+        rc = lib.iic_simplex_check(t.data_ptr(), outer, C, inner, C * inner, inner, st.flags.data_ptr(),
+                                   _stream(t.device))
+    _lib.check(rc, "iic_simplex_check")
+
+
+_LIBIMPL = torch.library.Library("iic_b200", "IMPL", "CUDA")
+_LIBIMPL.impl("local_joint", _local_joint)
+_LIBIMPL.impl("local_epilogue", _local_epilogue)
+_LIBIMPL.impl("local_backward", _local_backward)
+_LIBIMPL.impl("global_joint", _global_joint)
+_LIBIMPL.impl("global_epilogue", _global_epilogue)
+_LIBIMPL.impl("global_backward", _global_backward)
+_LIBIMPL.impl("uda_forward", _uda_forward)
+_LIBIMPL.impl("uda_backward", _uda_backward)
+_LIBIMPL.impl("simplex_check", _simplex_check)
+
+
+def _cpu_refusal(name):
+    def fn(*a, **k):
+        raise _lib.IICLibraryError(
+            f"iic_b200::{name} has no CPU implementation: this package is the B200 CUDA path only. "
+            "Move the tensors to a CUDA device.")
+    return fn
+
+
+_LIBCPU = torch.library.Library("iic_b200", "IMPL", "CPU")
+for _n in ("local_joint", "local_epilogue", "local_backward", "global_joint", "global_epilogue",
+           "global_backward", "uda_forward", "uda_backward", "simplex_check"):
+    _LIBCPU.impl(_n, _cpu_refusal(_n))
+
+ops = torch.ops.iic_b200
+
+
+# ---- data-parallel hook: one all-reduce of the partial joints ---------------------------------------
+_process_group = None
+_dist_enabled = False
+
+
+def set_data_parallel(enabled: bool, group=None):
+    """When enabled, every joint (local and global) is summed over `group` with ONE all-reduce before
+    the epilogue: each rank then holds the loss of the GLOBAL batch and the gradient of that loss with
+    respect to its own shard."""
+    global _process_group, _dist_enabled
+    _dist_enabled = bool(enabled)
+    _process_group = group
+
+
+def _maybe_allreduce(J: torch.Tensor) -> torch.Tensor:
+    if _dist_enabled:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(_process_group) > 1:
+            dist.all_reduce(J, op=dist.ReduceOp.SUM, group=_process_group)
+    return J
+
+
+# ---- autograd ------------------------------------------------------------------------------------------
+class LocalIICFunction(torch.autograd.Function):
+    """loss = mean over patches of the shifted-window IIC loss (iic_loss.py:107-149, 171-186)."""
+
+    @staticmethod
+    def forward(ctx, x, y, mask, pad, patch_h, patch_w, step_h, step_w, lamda):
+        J = ops.local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w)
+        J = _maybe_allreduce(J)
+        loss, Wx, Wy = ops.local_epilogue(J, x.shape[1], pad, lamda)
+        ctx.save_for_backward(x, y, mask, Wx, Wy)
+        ctx.geom = (pad, patch_h, patch_w, step_h, step_w)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        x, y, mask, Wx, Wy = ctx.saved_tensors
+        gx, gy = ops.local_backward(x, y, mask, Wx, Wy, grad.contiguous(), *ctx.geom)
+        return gx, gy, None, None, None, None, None, None, None
+
+
+class GlobalIICFunction(torch.autograd.Function):
+    """(loss, loss_no_lamb, P) of IIDLoss.forward (iic_loss.py:43-71)."""
+
+    @staticmethod
+    def forward(ctx, x, y, lamb):
+        J = _maybe_allreduce(ops.global_joint(x, y))
+        losses, P = ops.global_epilogue(J, lamb, True, True)
+        ctx.save_for_backward(x, y, J)
+        ctx.lamb = lamb
+        return losses[0], losses[1], P
+
+    @staticmethod
+    def backward(ctx, g1, g2, gP):
+        x, y, J = ctx.saved_tensors
+        g = torch.stack([g1.reshape(()), g2.reshape(())]).to(torch.float32)
+        gx, gy = ops.global_backward(x, y, J, ctx.lamb, True, g, gP)
+        return gx, gy, None
+
+
+class JointFunction(torch.autograd.Function):
+    """P = compute_joint(x, y, symmetric) (iic_loss.py:74-94)."""
+
+    @staticmethod
+    def forward(ctx, x, y, symmetric):
+        J = _maybe_allreduce(ops.global_joint(x, y))
+        _, P = ops.global_epilogue(J, 1.0, symmetric, False)
+        ctx.save_for_backward(x, y, J)
+        ctx.symmetric = symmetric
+        return P
+
+    @staticmethod
+    def backward(ctx, gP):
+        x, y, J = ctx.saved_tensors
+        g = torch.zeros(2, dtype=torch.float32, device=x.device)
+        gx, gy = ops.global_backward(x, y, J, 1.0, ctx.symmetric, g, gP)
+        return gx, gy, None
+
+
+class UDAFunction(torch.autograd.Function):
+    """MSE / KL consistency (semi_seg/epocher.py:221-224); the gradient flows to `prob` only."""
+
+    @staticmethod
+    def forward(ctx, prob, target, kind, eps, weight, from_logits, check_simplex):
+        loss = ops.uda_forward(prob, target, kind, eps, weight, from_logits, check_simplex)
+        ctx.save_for_backward(prob, target, weight)
+        ctx.cfg = (kind, eps, from_logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        prob, target, weight = ctx.saved_tensors
+        kind, eps, from_logits = ctx.cfg
+        g = ops.uda_backward(prob, target, kind, eps, weight, from_logits, grad.contiguous())
+        return g, None, None, None, None, None, None

@@ -1,0 +1,317 @@
+"""Parity of the CUDA path (through the public loss modules -> torch ops -> C ABI) with the oracle.
+
+Tolerances (BASELINE.json north_star): loss relative error <= 1e-5, gradients <= 1e-4 (max-norm
+relative), both against the float64 run of the reference (golden ``*_f64``) / the float64 oracle.
+The reference's own float32 deviation (golden ``loss_f32``, ``gerr_f32``) is printed next to ours.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import ROOT, golden_names, load_golden, relmax
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import iic_oracle as O  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def _loss_close(got, ref):
+    # independent-view cases have MI ~ 0: use an absolute floor there
+    return abs(got - ref) <= LOSS_RTOL * max(abs(ref), 0.05)
+
+
+def views(rng, B, K, H, W, noise=0.5):
+    ch, cw = max(H // 8, 1), max(W // 8, 1)
+    coarse = rng.standard_normal((B, K, ch, cw)) * 3.0
+    ys = np.arange(H) * ch // H
+    xs = np.arange(W) * cw // W
+    base = coarse[:, :, ys][:, :, :, xs]
+    x = O.softmax(base + noise * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    y = O.softmax(base + noise * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    return x, y
+
+
+@pytest.fixture(scope="module")
+def iic(cuda_device):
+    import iic_b200
+    return iic_b200
+
+
+# ---------------------------------------------------------------------------------------------------
+# golden vectors (outputs of the reference itself)
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("local"))
+def test_local_golden(iic, cuda_device, name):
+    g = load_golden(name)
+    pad, lamda, patch = int(g["padding"]), float(g["lamda"]), int(g["patch_size"])
+    x = torch.from_numpy(g["x"]).to(cuda_device).requires_grad_(True)
+    y = torch.from_numpy(g["y"]).to(cuda_device).requires_grad_(True)
+    mask = torch.from_numpy(g["mask"]).to(cuda_device) if "mask" in g else None
+    if patch < 0:
+        crit = iic.IIDSegmentationLoss(lamda=lamda, padding=pad)
+    else:
+        crit = iic.IIDSegmentationSmallPathLoss(lamda=lamda, padding=pad, patch_size=patch)
+    loss = crit(x, y, mask) if mask is not None else crit(x, y)
+    loss.backward()
+    ref = float(g["loss_f64"])
+    ex, ey = relmax(x.grad.cpu().numpy(), g["gx_f64"]), relmax(y.grad.cpu().numpy(), g["gy_f64"])
+    print(f"{name}: loss err {abs(loss.item()-ref)/max(abs(ref),1e-30):.2e} (ref fp32 "
+          f"{abs(float(g['loss_f32'])-ref)/max(abs(ref),1e-30):.2e}); grad err {max(ex,ey):.2e} "
+          f"(ref fp32 {float(g['gerr_f32']):.2e})")
+    assert _loss_close(loss.item(), ref), (loss.item(), ref)
+    assert ex <= GRAD_RTOL and ey <= GRAD_RTOL, (ex, ey)
+
+
+@pytest.mark.parametrize("name", golden_names("global"))
+def test_global_golden(iic, cuda_device, name):
+    g = load_golden(name)
+    x = torch.from_numpy(g["x"]).to(cuda_device).requires_grad_(True)
+    y = torch.from_numpy(g["y"]).to(cuda_device).requires_grad_(True)
+    loss, loss_nl, P = iic.IIDLoss(lamb=float(g["lamb"]))(x, y)
+    assert _loss_close(loss.item(), float(g["loss_f64"]))
+    assert _loss_close(loss_nl.item(), float(g["loss_no_lamb_f64"]))
+    assert relmax(P.detach().cpu().numpy(), g["P_f64"]) < 1e-6
+    K = P.shape[0]
+    w = torch.linspace(-1.0, 1.0, K * K, device=cuda_device).reshape(K, K)
+    full = 0.7 * loss - 0.3 * loss_nl + (w * P).sum()
+    gx, gy = torch.autograd.grad(full, (x, y), retain_graph=True)
+    assert relmax(gx.cpu().numpy(), g["fullgx_f64"]) <= GRAD_RTOL
+    assert relmax(gy.cpu().numpy(), g["fullgy_f64"]) <= GRAD_RTOL
+    gx, gy = torch.autograd.grad(loss, (x, y))
+    assert relmax(gx.cpu().numpy(), g["gx_f64"]) <= GRAD_RTOL
+    assert relmax(gy.cpu().numpy(), g["gy_f64"]) <= GRAD_RTOL
+    # compute_joint, non-symmetric variant (iic_loss.py:74-94)
+    Pn = iic.compute_joint(x.detach(), y.detach(), symmetric=False)
+    assert relmax(Pn.cpu().numpy(), g["joint_nosym_f64"]) < 1e-6
+
+
+@pytest.mark.parametrize("name", golden_names("uda"))
+def test_uda_golden(iic, cuda_device, name):
+    g = load_golden(name)
+    p = torch.from_numpy(g["prob"]).to(cuda_device).requires_grad_(True)
+    t = torch.from_numpy(g["target"]).to(cuda_device)
+    if str(g["kind"]) == "mse":
+        crit = iic.MSELoss()
+    else:
+        w = g["weight"].tolist() if "weight" in g else None
+        crit = iic.KL_div(weight=w, verbose=False)
+    loss = crit(p, t)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_f64"])) <= LOSS_RTOL * abs(float(g["loss_f64"]))
+    assert relmax(p.grad.cpu().numpy(), g["g_f64"]) <= GRAD_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# seeded inputs against the oracle, at sizes that exercise every kernel variant
+# ---------------------------------------------------------------------------------------------------
+LOCAL_CASES = [
+    # B, K, H, W, pad, patch
+    (4, 10, 64, 96, 1, 512),      # the headline variant (T=3, one job per warp)
+    (2, 10, 224, 224, 1, 512),    # ACDC Up_conv2 shape, reduced batch
+    (2, 20, 40, 48, 3, 1024),     # yaml default K=20, p=3 (multi-round, T=7)
+    (2, 20, 56, 56, 1, 1024),     # K=20, p=1
+    (2, 4, 33, 45, 2, 512),       # T=5, odd sizes, W % 4 != 0
+    (1, 3, 30, 70, 0, 512),       # T=1
+    (1, 5, 20, 40, 4, 512),       # T=9 (row jobs)
+    (1, 4, 18, 33, 7, 512),       # the reference's default padding
+    (1, 40, 20, 36, 1, 512),      # K > 32: channel-chunked launches
+    (2, 5, 56, 56, 1, 32),        # 3x3 overlapping patches (the 56^2 / patch 32 case of SURVEY A5)
+    (2, 6, 37, 50, 2, 16),        # ragged patch grid
+]
+
+
+@pytest.mark.parametrize("B,K,H,W,pad,patch", LOCAL_CASES)
+def test_local_vs_oracle(iic, cuda_device, B, K, H, W, pad, patch):
+    rng = np.random.default_rng(1234 + B * 7 + K * 13 + H + pad)
+    x, y = views(rng, B, K, H, W)
+    xd = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+    yd = torch.from_numpy(y).to(cuda_device).requires_grad_(True)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=pad, patch_size=patch)
+    loss = crit(xd, yd)
+    loss.backward()
+    ol, ogx, ogy = O.iid_segmentation_small_path_loss(x, y, pad, patch, with_grads=True)
+    ex, ey = relmax(xd.grad.cpu().numpy(), ogx), relmax(yd.grad.cpu().numpy(), ogy)
+    print(f"loss err {abs(loss.item()-ol)/abs(ol):.2e}, grad err {max(ex, ey):.2e}")
+    assert _loss_close(loss.item(), ol), (loss.item(), ol)
+    assert ex <= GRAD_RTOL and ey <= GRAD_RTOL, (ex, ey)
+
+
+@pytest.mark.parametrize("B,K,H,W,pad", [(2, 10, 50, 70, 1), (1, 20, 30, 40, 3), (1, 36, 16, 40, 1), (1, 6, 20, 24, 5)])
+def test_joint_kernel_vs_oracle(iic, cuda_device, B, K, H, W, pad):
+    """The raw joint (the F.conv2d of iic_loss.py:123) straight from the op, before any epilogue."""
+    rng = np.random.default_rng(99 + K + pad)
+    x, y = views(rng, B, K, H, W)
+    J = torch.ops.iic_b200.local_joint(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device),
+                                       None, pad, H, W, H, W)
+    ref = O.local_joint(x, y, pad)
+    assert J.shape == (1, 2 * pad + 1, 2 * pad + 1, K, K)
+    assert relmax(J[0].cpu().numpy(), ref) < 2e-6
+
+
+def test_local_mask_and_lambda(iic, cuda_device):
+    rng = np.random.default_rng(5)
+    x, y = views(rng, 2, 6, 40, 44)
+    for mshape in ((2, 1, 40, 44), (2, 6, 40, 44)):
+        mask = (rng.random(mshape) > 0.3).astype(np.float32)
+        xd = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+        yd = torch.from_numpy(y).to(cuda_device).requires_grad_(True)
+        loss = iic.IIDSegmentationLoss(lamda=1.7, padding=2)(xd, yd, torch.from_numpy(mask).to(cuda_device))
+        loss.backward()
+        ol, ogx, ogy = O.iid_segmentation_loss(x, y, 2, 1.7, mask, with_grads=True)
+        assert _loss_close(loss.item(), ol)
+        assert relmax(xd.grad.cpu().numpy(), ogx) <= GRAD_RTOL and relmax(yd.grad.cpu().numpy(), ogy) <= GRAD_RTOL
+
+
+def test_local_noncontiguous_views_and_upstream_grad(iic, cuda_device):
+    """Inputs as the epocher produces them: chunk() halves of one head output; loss scaled upstream."""
+    rng = np.random.default_rng(6)
+    x, y = views(rng, 3, 5, 24, 40)
+    both = torch.from_numpy(np.concatenate([x, y], 0)).to(cuda_device).requires_grad_(True)
+    p1, p2 = torch.chunk(both, 2, 0)
+    loss = 0.1 * iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=1024)(p1, p2)
+    loss.backward()
+    ol, ogx, ogy = O.iid_segmentation_small_path_loss(x, y, 1, 1024, with_grads=True)
+    assert _loss_close(loss.item(), 0.1 * ol)
+    g = both.grad.cpu().numpy()
+    assert relmax(g[:3], 0.1 * ogx) <= GRAD_RTOL and relmax(g[3:], 0.1 * ogy) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("N,K", [(4, 10), (64, 20), (10, 128), (5000, 10), (1, 3)])
+def test_global_vs_oracle(iic, cuda_device, N, K):
+    rng = np.random.default_rng(N + K)
+    base = rng.standard_normal((N, K)) * 2
+    x = O.softmax(base + 0.7 * rng.standard_normal((N, K))).astype(np.float32)
+    y = O.softmax(base + 0.7 * rng.standard_normal((N, K))).astype(np.float32)
+    xd = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+    yd = torch.from_numpy(y).to(cuda_device).requires_grad_(True)
+    loss, loss_nl, P = iic.IIDLoss(lamb=1.3)(xd, yd)
+    loss.backward()
+    o1, o2, oP = O.iid_loss(x, y, 1.3)
+    ox, oy = O.iid_loss_grads(x, y, 1.3)
+    assert _loss_close(loss.item(), o1) and _loss_close(loss_nl.item(), o2)
+    assert relmax(P.detach().cpu().numpy(), oP) < 1e-6
+    assert relmax(xd.grad.cpu().numpy(), ox) <= GRAD_RTOL and relmax(yd.grad.cpu().numpy(), oy) <= GRAD_RTOL
+
+
+@pytest.mark.parametrize("kind", ["mse", "kl"])
+@pytest.mark.parametrize("shape", [(4, 4, 224, 224), (3, 4, 37, 53), (5, 7), (2, 8, 9, 9)])
+def test_uda_vs_oracle(iic, cuda_device, kind, shape):
+    rng = np.random.default_rng(len(shape) + shape[1])
+    lp = (rng.standard_normal(shape) * 2).astype(np.float32)
+    lt = (rng.standard_normal(shape) * 2).astype(np.float32)
+    p, t = O.softmax(lp).astype(np.float32), O.softmax(lt).astype(np.float32)
+    pd = torch.from_numpy(p).to(cuda_device).requires_grad_(True)
+    crit = iic.MSELoss() if kind == "mse" else iic.KL_div(verbose=False)
+    loss = crit(pd, torch.from_numpy(t).to(cuda_device))
+    (3.0 * loss).backward()
+    fn = O.mse_loss if kind == "mse" else O.kl_div
+    ol, og = fn(p, t, with_grads=True)
+    assert abs(loss.item() - ol) <= LOSS_RTOL * abs(ol)
+    assert relmax(pd.grad.cpu().numpy(), 3.0 * og) <= GRAD_RTOL
+    # fused-softmax variant: criterion(softmax(a), softmax(b).detach()) with d/d(logits)
+    ld = torch.from_numpy(lp).to(cuda_device).requires_grad_(True)
+    lf = iic.uda_from_logits(ld, torch.from_numpy(lt).to(cuda_device), kind)
+    lf.backward()
+    p64, t64 = O.softmax(lp), O.softmax(lt)
+    ol2, og2 = fn(p64, t64, with_grads=True)
+    assert abs(lf.item() - ol2) <= LOSS_RTOL * abs(ol2)
+    assert relmax(ld.grad.cpu().numpy(), O.softmax_backward(p64, og2)) <= GRAD_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE config-2 size (32 x 10 x 224 x 224, padding 1)
+# ---------------------------------------------------------------------------------------------------
+def test_full_size_properties(iic, cuda_device):
+    B, K, H, W, pad = 32, 10, 224, 224, 1
+    gen = torch.Generator(device=cuda_device).manual_seed(1236)
+    base = torch.randn(B, K, H // 8, W // 8, device=cuda_device, generator=gen) * 3
+    base = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False)
+    x = (base + 0.5 * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    y = (base + 0.5 * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    J = torch.ops.iic_b200.local_joint(x, y, None, pad, H, W, H, W)[0]
+    # (1) checksum: sum_ij J_d[i,j] = #pixel pairs in range, because both maps are simplexes
+    T = 2 * pad + 1
+    for dy in range(T):
+        for dx in range(T):
+            expect = B * (H - abs(dy - pad)) * (W - abs(dx - pad))
+            assert abs(J[dy, dx].sum().item() - expect) <= 2e-6 * expect
+    # (2) swapping the views transposes the cluster axes and mirrors the displacement
+    Js = torch.ops.iic_b200.local_joint(y, x, None, pad, H, W, H, W)[0]
+    assert torch.allclose(Js, J.flip(0, 1).transpose(2, 3), rtol=1e-9, atol=0)
+    # (3) determinism: bit-identical on a re-run
+    assert torch.equal(J, torch.ops.iic_b200.local_joint(x, y, None, pad, H, W, H, W)[0])
+    # (4) the joint is linear in each argument
+    J2 = torch.ops.iic_b200.local_joint(0.5 * x, y, None, pad, H, W, H, W)[0]
+    assert torch.allclose(J2, 0.5 * J, rtol=1e-6, atol=0)
+    # (5) loss/gradient identities: <gx, x> == <gy, y> (both equal sum_d <dL/dJ_d, J_d>), and the loss
+    #     is invariant under a permutation of the cluster channels
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=pad, patch_size=512)
+    loss = crit(xr, yr)
+    loss.backward()
+    a, b = (xr.grad.double() * x.double()).sum().item(), (yr.grad.double() * y.double()).sum().item()
+    assert abs(a - b) <= 1e-4 * max(abs(a), abs(b), 1e-3), (a, b)
+    perm = torch.randperm(K, device=cuda_device)
+    xp, yp = x[:, perm].contiguous().requires_grad_(True), y[:, perm].contiguous().requires_grad_(True)
+    lp = crit(xp, yp)
+    assert abs(lp.item() - loss.item()) <= 1e-6 * abs(loss.item())
+    # (6) against the oracle on the first 4 samples' share: the loss of a sub-batch is what the
+    #     oracle says (full-batch oracle would take minutes)
+    xs, ys = x[:4].contiguous().requires_grad_(True), y[:4].contiguous().requires_grad_(True)
+    ls = crit(xs, ys)
+    ol = O.iid_segmentation_small_path_loss(xs.detach().cpu().numpy(), ys.detach().cpu().numpy(), pad, 512)
+    assert _loss_close(ls.item(), ol)
+
+
+# ---------------------------------------------------------------------------------------------------
+# error conventions
+# ---------------------------------------------------------------------------------------------------
+def test_error_conventions(iic, cuda_device):
+    x = torch.rand(2, 4, 16, 16, device=cuda_device).softmax(1)
+    y = torch.rand(2, 4, 16, 16, device=cuda_device).softmax(1)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=512)
+    with pytest.raises(AssertionError):               # requires_grad assert, iic_loss.py:110
+        crit(x, y)
+    xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+    with pytest.raises(AssertionError):               # mask must not require grad, :112
+        crit(xr, yr, torch.ones(2, 1, 16, 16, device=cuda_device, requires_grad=True))
+    with pytest.raises(AssertionError):               # not a simplex, :113
+        crit((x * 1.01).requires_grad_(True), yr)
+    bad = x.clone()
+    bad[0, 0, 0, 0] = float("nan")
+    with pytest.raises((AssertionError, RuntimeError)):
+        crit(bad.requires_grad_(True), yr)
+    with iic.check_mode("off"):                       # NaN loss still raises RuntimeError in strict...
+        out = crit(bad.clone().requires_grad_(True), yr)
+        assert torch.isnan(out)
+    with pytest.raises((AssertionError, RuntimeError)):
+        iic.raise_if_flagged(cuda_device)             # ...and the sticky flag reports it when asked
+    with pytest.raises(AssertionError):
+        iic.IIDLoss()(torch.rand(4, 5, device=cuda_device), torch.rand(4, 5, device=cuda_device))
+    with pytest.raises(AssertionError):
+        iic.KL_div(verbose=False)(torch.rand(2, 4, 8, 8, device=cuda_device).requires_grad_(True),
+                                  torch.rand(2, 4, 8, 8, device=cuda_device))
+    # deferred mode never synchronises and reports on demand
+    with iic.check_mode("deferred"):
+        crit((x * 1.01).requires_grad_(True), yr)
+        with pytest.raises(AssertionError):
+            iic.raise_if_flagged(cuda_device)
+    iic.raise_if_flagged(cuda_device)                 # clean again
+    # CPU tensors are refused loudly: there is no fallback
+    with pytest.raises(Exception):
+        crit(x.cpu().requires_grad_(True), y.cpu().requires_grad_(True))
+
+
+def test_modules_are_parameter_free(iic):
+    for m in (iic.IIDLoss(), iic.IIDSegmentationLoss(), iic.IIDSegmentationSmallPathLoss(), iic.KL_div(verbose=False),
+              iic.MSELoss(), iic.IICLossWrapper(["Conv5", "Up_conv3", "Up_conv2"], [1, 3], 1024)):
+        assert len(m.state_dict()) == 0
+    assert repr(iic.IIDSegmentationSmallPathLoss(padding=3, patch_size=32)) == \
+        "IIDSegmentationSmallPathLoss with patch_size=(32, 32) and padding=3."

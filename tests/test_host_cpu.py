@@ -1,0 +1,99 @@
+"""CPU-side checks: the C-ABI library loads and exports every declared symbol, the host mirror keeps the
+reference's API surface, and nothing silently falls back to the CPU."""
+import inspect
+import os
+import re
+import sys
+
+import pytest
+import torch
+
+from conftest import ROOT, load_golden
+
+PKG = os.path.join(ROOT, "mi-based-regularized-semi-supervised-segmentation_b200")
+
+
+@pytest.fixture(scope="module")
+def built():
+    sys.path.insert(0, ROOT)
+    import __graft_entry__ as ge
+    ge.build()
+    import iic_b200
+    return iic_b200
+
+
+def test_library_exports_every_declared_symbol(built):
+    import ctypes
+    hdr = open(os.path.join(ROOT, "include", "iic_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(iic_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 15
+    lib = ctypes.CDLL(os.path.join(PKG, "libiic_b200.so"))
+    for name in declared:
+        assert hasattr(lib, name), f"libiic_b200.so does not export {name}"
+    assert declared == set(built._lib.PROTOTYPES), declared ^ set(built._lib.PROTOTYPES)
+    assert built._lib.load().iic_b200_abi_version() == 1
+
+
+def test_patch_count_matches_reference_windows(built):
+    lib = built._lib.load()
+    g = load_golden("patch_windows")
+    for key, wins in g.items():
+        hw, ps = key.split("_p")
+        h, w = (int(v) for v in hw.split("x"))
+        ps = int(ps)
+        assert lib.iic_local_num_patches(h, w, ps, ps, ps // 2, ps // 2) == len(wins), key
+    assert lib.iic_local_num_patches(10, 10, 4, 4, 0, 0) == -1      # step 0 with patch < map is an error
+
+
+def test_api_surface_matches_reference(built):
+    iic = built
+    sig = inspect.signature
+    assert list(sig(iic.IIDLoss.__init__).parameters) == ["self", "lamb", "eps"]
+    assert list(sig(iic.IIDLoss.forward).parameters) == ["self", "x_out", "x_tf_out"]
+    assert list(sig(iic.compute_joint).parameters) == ["x_out", "x_tf_out", "symmetric"]
+    assert list(sig(iic.IIDSegmentationLoss.__init__).parameters) == ["self", "lamda", "padding", "eps"]
+    assert sig(iic.IIDSegmentationLoss.__init__).parameters["padding"].default == 7
+    assert list(sig(iic.IIDSegmentationLoss.__call__).parameters) == ["self", "x_out", "x_tf_out", "mask"]
+    assert list(sig(iic.IIDSegmentationSmallPathLoss.__init__).parameters) == ["self", "lamda", "padding", "eps",
+                                                                               "patch_size"]
+    assert sig(iic.IIDSegmentationSmallPathLoss.__init__).parameters["patch_size"].default == 32
+    assert list(sig(iic.patch_generator).parameters) == ["feature_map", "patch_size", "step_size"]
+    assert list(sig(iic.KL_div.__init__).parameters) == ["self", "reduction", "eps", "weight", "verbose"]
+    m = iic.IIDLoss(lamb=2.0)
+    assert m.lamb == 2.0 and hasattr(m, "eps") and m.torch_vision == torch.__version__
+    w = iic.IICLossWrapper(["Conv5", "Up_conv3", "Up_conv2"], [1, 3], [1024, 1024])
+    assert w.feature_names == ["Conv5", "Up_conv3", "Up_conv2"]
+    assert type(w["Conv5"]).__name__ == "IIDLoss" and w["Up_conv2"].padding == 3
+    assert [k for k, _ in w.items()] == ["Conv5", "Up_conv3", "Up_conv2"]
+    with pytest.raises(IndexError):
+        w["Conv1"]
+
+
+def test_patch_generator_views(built):
+    g = load_golden("patch_windows")
+    for key, wins in g.items():
+        hw, ps = key.split("_p")
+        h, w = (int(v) for v in hw.split("x"))
+        ps = int(ps)
+        fm = torch.arange(h * w, dtype=torch.float32).reshape(1, 1, h, w)
+        got = [(int(p[0, 0, 0, 0]) // w, int(p[0, 0, 0, 0]) // w + p.shape[2], int(p[0, 0, 0, 0]) % w,
+                int(p[0, 0, 0, 0]) % w + p.shape[3]) for p in built.patch_generator(fm, (ps, ps), (ps // 2, ps // 2))]
+        assert got == [tuple(r) for r in wins.tolist()]
+
+
+def test_no_cpu_fallback(built):
+    x = torch.rand(2, 4, 8, 8).softmax(1).requires_grad_(True)
+    with pytest.raises(Exception) as ei:
+        built.IIDSegmentationLoss(padding=1)(x, x.detach().clone().requires_grad_(True))
+    assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
+    with pytest.raises(Exception):
+        built.MSELoss()(x, x.detach())
+
+
+def test_product_never_imports_oracle():
+    for dirpath, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in src.replace("the oracle", ""), f"{f} mentions the oracle"
