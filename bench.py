@@ -335,8 +335,8 @@ def run_b200(args):
         dy.copy_(hy, non_blocking=True)
         dgx.copy_(hgx, non_blocking=True)
         dgy.copy_(hgy, non_blocking=True)
-        a, b = dx.requires_grad_(True), dy.requires_grad_(True)
-        c, d = dgx.requires_grad_(True), dgy.requires_grad_(True)
+        a, b = dx.detach().requires_grad_(True), dy.detach().requires_grad_(True)
+        c, d = dgx.detach().requires_grad_(True), dgy.detach().requires_grad_(True)
         loss = local(a, b) + glob(c, d)[0]
         torch.autograd.grad(loss, (a, b, c, d))
         hloss.copy_(loss.detach(), non_blocking=True)

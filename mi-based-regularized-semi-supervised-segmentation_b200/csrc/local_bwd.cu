@@ -10,6 +10,8 @@
 // in registers); the T x T taps for all output channels are warp-uniform and come from shared memory
 // as broadcast 128-bit loads, so the inner loop is FMA-issue bound.  Input tiles (with halo, zero
 // outside the patch) are staged in shared memory by input-channel chunks.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace iic {
@@ -196,6 +198,12 @@ static int dispatch_ocb(int ocb, const LocalBwdParams& P, dim3 grid, size_t smem
 
 }  // namespace iic
 
+namespace iic {
+int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                      long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                      const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
+                      cudaStream_t st);
+}
 using namespace iic;
 
 extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -216,6 +224,13 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
   const int n_patches = g.nh * g.nw;
   const int sms = sm_count_cached(current_device());
   IIC_REQUIRE(sms > 0, "iic_local_backward: no device");
+
+  // fast path: one patch, no mask, TMA-describable rows, small window (local_bwd_tma.cu)
+  if (n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
+    const int rc = local_bwd_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                     gx, gy, sms, st);
+    if (rc >= 0) return rc;
+  }
 
   LocalBwdParams P;
   P.m = {mask, m_sn, m_sc, m_sh};

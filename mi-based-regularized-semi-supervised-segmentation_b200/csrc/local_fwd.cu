@@ -13,6 +13,8 @@
 // fp32 accumulation runs are short (one CTA's share of the pixels, per lane); lanes are combined
 // with warp shuffles and CTAs in fp64 in a fixed order (reduce_partials_kernel), so the result is
 // deterministic and its error is well below the reference's own fp32 error (DESIGN.md "numerics").
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace iic {
@@ -251,9 +253,14 @@ __global__ void reduce_partials_kernel(const float* __restrict__ partial, int nc
   const int patch = blockIdx.y;
   if (e >= E) return;
   const float* src = partial + (size_t)patch * ncta * E + e;
-  double s = 0.0;
-  for (int c = 0; c < ncta; ++c) s += (double)src[(size_t)c * E];
-  J[(size_t)patch * E + e] = s;
+  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  int c = 0;
+  for (; c + 8 <= ncta; c += 8) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) s[q] += (double)__ldg(src + (size_t)(c + q) * E);
+  }
+  for (int q = 0; c < ncta; ++c, ++q) s[q] += (double)__ldg(src + (size_t)c * E);
+  J[(size_t)patch * E + e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -262,6 +269,7 @@ struct FwdPlan {
   int kchunk;        // channels per launch (<= 32)
   int TH, TWS, tiles_h, tiles_w, XR, XP;
   int ctas_per_patch;
+  int slots_per_patch;
   int n_patches;
   size_t smem_bytes;
 };
@@ -302,6 +310,7 @@ static bool make_fwd_plan(int device, int B, int K, const PatchGrid& g, int pad,
   long long items = (long long)B * pl->tiles_h * pl->tiles_w;
   long long per = sms / pl->n_patches;
   if (per < 1) per = 1;
+  pl->slots_per_patch = (int)per;          // workspace is sized for this many partial slots per patch
   if (per > items) per = items;
   pl->ctas_per_patch = (int)per;
   return true;
@@ -340,7 +349,13 @@ extern "C" size_t iic_local_joint_workspace_bytes(int device, int B, int K, int 
   FwdPlan pl;
   if (!make_patch_grid(H, W, patch_h, patch_w, step_h, step_w, &g)) return 0;
   if (!make_fwd_plan(device, B, K, g, pad, &pl)) return 0;
-  return (size_t)pl.n_patches * pl.ctas_per_patch * pl.T * pl.T * K * K * sizeof(float);
+  return (size_t)pl.n_patches * pl.slots_per_patch * pl.T * pl.T * K * K * sizeof(float);
+}
+
+namespace iic {
+int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                        float* partial, int max_ctas, int* ncta, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -361,9 +376,24 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   FwdPlan pl;
   IIC_REQUIRE(make_fwd_plan(device, B, K, g, pad, &pl), "iic_local_joint: cannot plan launch");
   const size_t E = (size_t)pl.T * pl.T * K * K;
-  const size_t need = (size_t)pl.n_patches * pl.ctas_per_patch * E * sizeof(float);
+  const size_t need = (size_t)pl.n_patches * pl.slots_per_patch * E * sizeof(float);
   IIC_REQUIRE(workspace && workspace_bytes >= need, "iic_local_joint: workspace too small (%zu < %zu)",
               workspace_bytes, need);
+
+  // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
+  if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
+    int ncta = 0;
+    const int rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
+                                       (float*)workspace, pl.slots_per_patch, &ncta, st);
+    if (rc > 0) return rc;
+    if (rc == 0) {
+      const int threads = 256;
+      dim3 rgrid((unsigned)((E + threads - 1) / threads), 1);
+      reduce_partials_kernel<<<rgrid, threads, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+      IIC_CHECK_CUDA(cudaGetLastError());
+      return 0;
+    }
+  }
 
   LocalFwdParams P;
   P.x = {x, x_sn, x_sc, x_sh};

@@ -244,7 +244,7 @@ def test_full_size_properties(iic, cuda_device):
             assert abs(J[dy, dx].sum().item() - expect) <= 2e-6 * expect
     # (2) swapping the views transposes the cluster axes and mirrors the displacement
     Js = torch.ops.iic_b200.local_joint(y, x, None, pad, H, W, H, W)[0]
-    assert torch.allclose(Js, J.flip(0, 1).transpose(2, 3), rtol=1e-9, atol=0)
+    assert torch.allclose(Js, J.flip(0, 1).transpose(2, 3), rtol=1e-6, atol=0)   # fp32 partial sums, other order
     # (3) determinism: bit-identical on a re-run
     assert torch.equal(J, torch.ops.iic_b200.local_joint(x, y, None, pad, H, W, H, W)[0])
     # (4) the joint is linear in each argument
