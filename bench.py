@@ -13,8 +13,8 @@ The JSON line carries, beyond the base contract:
   value     device-timed throughput, inputs resident in HBM (CUDA-graph replay of the public-API step)
   e2e       the same through the public modules with HOST (pinned) inputs: H2D of both views and the
             global rows, forward, backward, D2H of the loss, every step
-  roofline  the dominant kernel (local_bwd_kernel, two launches per step): algorithmic bytes per
-            launch (8*K bytes/px: read one K-channel map, write one K-channel gradient) over its
+  roofline  the dominant kernel (local_bwd_tma_kernel, one launch per step): algorithmic bytes per
+            launch (16*K bytes/px: read both K-channel maps, write both gradients) over its
             CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  oracle/torch_port.py (the reference's operator sequence) on the host cores, bounded sample
 """
@@ -307,20 +307,20 @@ def run_b200(args):
             t_epi += b.elapsed_time(c)
             t_bwd += c.elapsed_time(d)
     t_joint, t_epi, t_bwd = t_joint / reps, t_epi / reps, t_bwd / reps
-    bwd_launch_ms = t_bwd / 2.0                               # two sweeps = two launches of local_bwd_kernel
-    alg_bytes_launch = 8.0 * K * B * H * W                    # read one map + write one gradient, fp32
+    bwd_launch_ms = t_bwd                                     # ONE launch of local_bwd_tma_kernel does both sweeps
+    alg_bytes_launch = 16.0 * K * B * H * W                   # read both maps + write both gradients, fp32
     achieved = alg_bytes_launch / (bwd_launch_ms * 1e-3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
-    fma_per_launch = K * K * (2 * pad + 1) ** 2 * B * H * W   # useful FMAs of one sweep
+    fma_per_launch = 2 * K * K * (2 * pad + 1) ** 2 * B * H * W   # useful FMAs of both sweeps
     fp32_peak = 148 * 128 * sm_mhz * 1e6                      # FMA/s at the observed clock
-    roofline = {"kernel": "local_bwd_kernel<3,10>", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
+    roofline = {"kernel": "local_bwd_tma_kernel<3,10>", "bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak,
                 "unit": "GB/s", "frac": round(achieved / hbm_peak, 4), "traffic": None, "peak_source": peak_src,
                 "launch_ms": round(bwd_launch_ms, 4),
                 "note": "kernel is FP32-FMA bound (AI = K*T^2/4 = 22.5 flop/B > ridge); fp32_fma_frac is its fraction "
                         "of 148 SM x 128 FMA/clk at the sampled SM clock",
                 "fp32_fma_frac": round(fma_per_launch / (bwd_launch_ms * 1e-3) / fp32_peak, 4),
                 "step_breakdown_ms": {"local_joint+reduce": round(t_joint, 4), "local_epilogue": round(t_epi, 4),
-                                      "local_backward(2 launches)": round(t_bwd, 4)},
+                                      "local_backward": round(t_bwd, 4)},
                 "whole_step_hbm_frac": round(24.0 * K * B * H * W / (ms_step * 1e-3) / 1e9 / hbm_peak, 4)}
 
     # ---- end to end through the public API with HOST buffers ----
@@ -360,9 +360,9 @@ def run_b200(args):
 
     if rank == 0:
         cpu_v, cpu_threads, cpu_best, cpu_times = cpu_port_throughput(args.cpu_sample_batch, 5)
-        # launches per step: local = simplex + joint + reduce + epilogue + 2 x backward (6);
+        # launches per step: local = simplex + joint + reduce + epilogue + backward (5);
         # global = 2 x simplex + joint + reduce + epilogue + backward (6)
-        launches = 12 * args.steps
+        launches = 11 * args.steps
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,

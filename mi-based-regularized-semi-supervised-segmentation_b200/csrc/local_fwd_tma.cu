@@ -213,7 +213,11 @@ int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long lon
   if (W % 4 != 0) return -1;
   FwdTmaParams P;
   P.B = B; P.K = K; P.H = H; P.W = W; P.pad = pad;
-  P.TWS = W > 40 ? 2 : 1;
+  // 32-column strips per tile: 2 unless 1 wastes fewer lanes at this width (e.g. 224 = 7 x 32)
+  {
+    const int w1 = ((W + 31) / 32) * 32, w2 = ((W + 63) / 64) * 64;
+    P.TWS = (W > 32 && w2 <= w1) ? 2 : 1;
+  }
   const int TW = P.TWS * 32;
   P.LP = (pad + 3) & ~3;
   P.XP = P.LP + TW + ((pad + 3) & ~3);
@@ -223,7 +227,8 @@ int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long lon
     *xr = (*xb + 127u) & ~127u;
     return *xr + ((*yb + 127u) & ~127u);
   };
-  int TH = 16;
+  int TH = 32;
+  while (TH > 8 && TH / 2 >= H) TH >>= 1;      // small maps: do not stage rows that do not exist
   unsigned xb, yb, xr, sb;
   while (true) {
     sb = stage_bytes(TH, &xb, &yb, &xr);
