@@ -203,6 +203,10 @@ int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long 
                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
                       cudaStream_t st);
+int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
+                       cudaStream_t st);
 }
 using namespace iic;
 
@@ -227,8 +231,12 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
 
   // fast path: one patch, no mask, TMA-describable rows, small window (local_bwd_tma.cu)
   if (n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
-    const int rc = local_bwd_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                     gx, gy, sms, st);
+    int rc = getenv("IIC_B200_NO_FAST") ? -1
+                 : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
+                                      grad_loss, gx, gy, sms, st);
+    if (rc < 0)
+      rc = local_bwd_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                             gx, gy, sms, st);
     if (rc >= 0) return rc;
   }
 

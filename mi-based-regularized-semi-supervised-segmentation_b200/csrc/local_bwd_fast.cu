@@ -1,0 +1,288 @@
+// Specialised local backward (the convolution_backward of contrastyou/losses/iic_loss.py:123) for the
+// 3 x 3 window, channel counts that are multiples of 10 and maps at most 248 pixels wide (one patch, no
+// mask) -- the shapes of the reference's udaiic configuration.  Both gradients come out of ONE launch:
+//   gx[i](px) = sum_{j,tap} Wx[j][tap][i] * y[j](px + tap)      gy[j](px) = sum_{i,tap} Wy[i][tap][j] * x[i](px + tap)
+// (Wx / Wy = dL/dJ re-laid by the epilogue kernel).
+//
+// Work decomposition.  The B*H image rows are dealt out in equal contiguous shares to the persistent
+// CTAs (one per SM), so no SM idles in a last partial wave; a CTA walks its share in chunks of CR whole
+// rows (CR * W/4 <= 512).  A thread owns one row x 4 pixels x 10 output channels = 20 float2
+// accumulators (pairs over adjacent output channels); 16 consumer warps = 4 per SM sub-partition.  Per input channel a thread loads its 3 x 6 window (three
+// LDS.128, the two halo columns come from the neighbouring lanes by shuffle).  The weights are warp-uniform,
+// so they never touch a vector register or the LSU: the host copies dL/dJ (Wx, Wy) device-to-device
+// into __constant__ memory in front of the launch and every update is one
+//   FFMA2 acc, window.F32 (scalar), UR.F32x2 (weight pair, LDCU.64 from the constant bank), acc
+// i.e. per input channel 180 FFMA2 + 45 uniform-datapath loads + ~15 shared-memory instructions.
+// (IIC_B200_BWD_CFG=1 selects 24 consumer warps with a 3-slot ring, for experiments.)
+//
+// Input tiles (CR + 2 rows, full width + halo, 5 channels per stage) stream through a TMA ring with
+// full/empty mbarriers per slot, refilled by a dedicated producer warp; the hardware zero-fills rows and
+// columns outside the map, which is the conv's padding.  (The producer must be its own warp: a
+// one-thread spin on an mbarrier inside the consumers' loop makes the compiler treat the loop counters
+// as divergent, and the weight loads then fall off the uniform datapath -- LDC instead of LDCU.)
+// With the weights in uniform registers a consumer needs ~70 registers, so 17 warps fit.
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace iic {
+
+namespace bwdfast {
+constexpr int KB = 10;                 // output-channel block
+constexpr int LP = 4;                  // halo columns staged left and right (keeps rows 16-byte aligned)
+constexpr int T2 = 9;
+}  // namespace bwdfast
+
+// dL/dJ for the two sweeps, [slot][sweep][cin][tap][Kp] (57.6 KB of the 64 KB bank).  Launches on one
+// stream are ordered, so one slot would do; the two slots, used round-robin, keep two interleaved
+// streams apart.  More than two streams running this backward concurrently are not supported.
+constexpr int WC_SLOT_FLOATS = 2 * 20 * 9 * 20;
+__constant__ float2 g_wc[2 * WC_SLOT_FLOATS / 2];
+
+struct BwdFastParams {
+  int wc_base;               // float2 index of this launch's slot in g_wc
+  int B, K, Kp, H, W;
+  int QW, CR, XP, XR;        // thread tiles per row, rows per chunk, tile pitch (floats) and rows
+  int plane;                 // floats per channel plane of a stage
+  long long rows_total;      // B * H
+  unsigned stage_bytes, box_bytes;
+  const float* Wx;           // [K][9][Kp]
+  const float* Wy;
+  const float* grad_loss;
+  float* gx;
+  float* gy;
+};
+
+// v = shared[addr] where pred != 0 (a predicated LDS: no divergent branch around a one-lane load)
+__device__ __forceinline__ void lds_if(float& v, uint32_t addr, int pred) {
+  asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.s32 p, %2, 0;\n\t@p ld.shared.f32 %0, [%1];\n\t}" : "+f"(v) : "r"(addr), "r"(pred));
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// PXQ = pixel quads per thread (a thread owns one row x 4*PXQ pixels x 10 output channels); NWARPS consumer
+// warps + one producer warp.
+template <int K, int PXQ, int NWARPS, int STAGES, int CB>
+__global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
+local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
+                      const BwdFastParams P) {
+  using namespace bwdfast;
+  constexpr int NPX = 4 * PXQ;
+  constexpr int Kp = (K + 3) & ~3;                        // row pitch of Wx / Wy
+  constexpr int nchunk = K / CB;                            // stages per sweep
+  constexpr int per_chunk = 2 * nchunk;                     // stages per row chunk (two sweeps)
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int oc0 = blockIdx.y * KB;                          // this CTA's output-channel block
+  const long long R0 = (long long)blockIdx.x * P.rows_total / gridDim.x;
+  const long long R1 = (long long)(blockIdx.x + 1) * P.rows_total / gridDim.x;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NWARPS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // (a warp vote makes the role test provably warp-uniform, so the consumers' loops stay on uniform
+  // control flow and their weight loads on the uniform datapath)
+  if (__any_sync(0xffffffffu, wid == NWARPS)) {
+    // ===== producer warp: one lane walks the same (chunk, sweep, channel block) sequence as the consumers,
+    // a ring slot is refilled as soon as every consumer warp has released it =====
+    if (lane == 0) {
+      tma_prefetch_desc(&mapx);
+      tma_prefetch_desc(&mapy);
+      unsigned k = 0;
+      for (long long r = R0; r < R1;) {
+        const int n = (int)(r / P.H), h0 = (int)(r - (long long)n * P.H);
+        int nr = P.CR;
+        if (nr > P.H - h0) nr = P.H - h0;
+        if (nr > R1 - r) nr = (int)(R1 - r);
+        for (int st = 0; st < per_chunk; ++st, ++k) {
+          const int sweep = st / nchunk, cb = st - sweep * nchunk;
+          const int s = k % STAGES;
+          if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) & 1u) ^ 1u);
+          mbar_arrive_expect_tx(&full_bar[s], P.box_bytes);
+          tma_load_4d(smem_raw + (size_t)s * P.stage_bytes, sweep == 0 ? &mapy : &mapx, &full_bar[s], -LP, h0 - 1,
+                      cb * CB, n);                          // gx reads y, gy reads x
+        }
+        r += nr;
+      }
+    }
+    return;
+  }
+
+  // ===== consumer warps =====
+  const float g = P.grad_loss ? __ldg(P.grad_loss) : 1.f;
+  const int rr = threadIdx.x / P.QW, q = threadIdx.x - rr * P.QW;
+  const bool in_tile = rr < P.CR;
+  const int rr_c = in_tile ? rr : P.CR - 1;                 // idle threads read valid rows, store nothing
+  const uint32_t toff = (uint32_t)(rr_c * P.XP + LP + NPX * q) * 4u;
+  // the halo columns come from the neighbouring lanes, except at the warp's and the row's ends, where
+  // they are read from the tile (columns -1 and W hold the zero fill = the conv's padding)
+  const int ld_left = (lane == 0) | (q == 0), ld_right = (lane == 31) | (q == P.QW - 1);
+  const uint32_t xp4 = (uint32_t)P.XP * 4u, plane4 = (uint32_t)P.plane * 4u;
+  const uint32_t smem_base = smem_u32(smem_raw);
+
+  float2 acc[KB / 2][NPX];
+  unsigned k = 0;
+  for (long long r = R0; r < R1;) {
+    const int n = (int)(r / P.H), h0 = (int)(r - (long long)n * P.H);
+    int nr = P.CR;
+    if (nr > P.H - h0) nr = P.H - h0;
+    if (nr > R1 - r) nr = (int)(R1 - r);
+    const bool active = in_tile && rr < nr;
+    const bool warp_active = __any_sync(0xffffffffu, active);
+    for (int sweep = 0; sweep < 2; ++sweep) {
+#pragma unroll
+      for (int c = 0; c < KB / 2; ++c)
+#pragma unroll
+        for (int p = 0; p < NPX; ++p) acc[c][p] = make_float2(0.f, 0.f);
+      for (int cb = 0; cb < nchunk; ++cb, ++k) {
+        const int s = k % STAGES;
+        mbar_wait(&full_bar[s], (k / STAGES) & 1u);
+        if (warp_active) {
+          uint32_t cp = smem_base + (uint32_t)s * P.stage_bytes + toff;
+#pragma unroll 1
+          for (int ch = 0; ch < CB; ++ch, cp += plane4) {
+            // weight pairs of this sweep, input channel and output block: g_wc[wq + tap * Kp / 2 + c]
+            const int wq = P.wc_base + (sweep * K * T2 * Kp + oc0) / 2 + (cb * CB + ch) * (T2 * Kp / 2);
+            float win[3][NPX + 2];
+#pragma unroll
+            for (int wr = 0; wr < 3; ++wr) {
+              const uint32_t rp = cp + wr * xp4;
+#pragma unroll
+              for (int v4 = 0; v4 < PXQ; ++v4) {
+                const float4 v = lds128(rp + 16 * v4);
+                win[wr][1 + 4 * v4] = v.x; win[wr][2 + 4 * v4] = v.y;
+                win[wr][3 + 4 * v4] = v.z; win[wr][4 + 4 * v4] = v.w;
+              }
+              float l = __shfl_up_sync(0xffffffffu, win[wr][NPX], 1);
+              float rt = __shfl_down_sync(0xffffffffu, win[wr][1], 1);
+              lds_if(l, rp - 4, ld_left);
+              lds_if(rt, rp + 4 * NPX, ld_right);
+              win[wr][0] = l;
+              win[wr][NPX + 1] = rt;
+            }
+#pragma unroll
+            for (int ry = 0; ry < 3; ++ry)
+#pragma unroll
+              for (int rx = 0; rx < 3; ++rx) {
+                float2 wp[KB / 2];
+#pragma unroll
+                for (int c = 0; c < KB / 2; ++c) wp[c] = g_wc[wq + (ry * 3 + rx) * (Kp / 2) + c];
+#pragma unroll
+                for (int p = 0; p < NPX; ++p) {
+                  const float a = win[ry][p + rx];
+                  const float2 a2 = make_float2(a, a);
+#pragma unroll
+                  for (int c = 0; c < KB / 2; ++c) acc[c][p] = __ffma2_rn(a2, wp[c], acc[c][p]);
+                }
+              }
+          }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+      if (active) {
+        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + NPX * q;
+        const size_t cs = (size_t)P.H * P.W;
+#pragma unroll
+        for (int c = 0; c < KB / 2; ++c)
+#pragma unroll
+          for (int v4 = 0; v4 < PXQ; ++v4) {
+            *reinterpret_cast<float4*>(out + (size_t)(2 * c) * cs + 4 * v4) =
+                make_float4(g * acc[c][4 * v4].x, g * acc[c][4 * v4 + 1].x, g * acc[c][4 * v4 + 2].x, g * acc[c][4 * v4 + 3].x);
+            *reinterpret_cast<float4*>(out + (size_t)(2 * c + 1) * cs + 4 * v4) =
+                make_float4(g * acc[c][4 * v4].y, g * acc[c][4 * v4 + 1].y, g * acc[c][4 * v4 + 2].y, g * acc[c][4 * v4 + 3].y);
+          }
+      }
+    }
+    r += nr;
+  }
+}
+
+template <int K, int PXQ, int NWARPS, int STAGES, int CB>
+static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const BwdFastParams& P, dim3 grid,
+                           size_t smem, cudaStream_t st) {
+  auto kern = local_bwd_fast_kernel<K, PXQ, NWARPS, STAGES, CB>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+    attr_set = true;
+  }
+  kern<<<grid, (NWARPS + 1) * 32, smem, st>>>(mx, my, P);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// 0 = launched, 1 = error, -1 = not eligible (caller falls back to the other kernels)
+int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
+                       cudaStream_t st) {
+  using namespace bwdfast;
+  if (pad != 1 || (K != 10 && K != 20)) return -1;
+  if (W % 4 != 0 || W > 248 || W < 4) return -1;
+  if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
+  // launch shape: 0 = 16 consumer warps x 4 stages, 1 = 24 consumer warps x 3 stages
+  int cfg = 0;
+  if (const char* e = getenv("IIC_B200_BWD_CFG")) cfg = atoi(e);
+  if (cfg < 0 || cfg > 1) cfg = 0;
+  const int pxq = 1, CB = 5;
+  const int nthreads = cfg == 0 ? 512 : 768, stages = cfg == 0 ? 4 : 3;
+  BwdFastParams P;
+  P.B = B; P.K = K; P.Kp = (K + 3) & ~3; P.H = H; P.W = W;
+  P.QW = W / (4 * pxq);
+  P.CR = nthreads / P.QW;
+  if (P.CR > 62) P.CR = 62;
+  if (P.CR > H) P.CR = H;
+  P.XP = W + 2 * LP;
+  P.XR = P.CR + 2;
+  P.plane = P.XR * P.XP;
+  P.rows_total = (long long)B * H;
+  P.box_bytes = (unsigned)((size_t)CB * P.plane * 4);
+  P.stage_bytes = (P.box_bytes + 127u) & ~127u;
+  const size_t smem = (size_t)P.stage_bytes * stages;
+  if (smem > 226 * 1024) return -1;
+  P.Wx = Wx; P.Wy = Wy; P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
+  CUtensorMap mx, my;
+  if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, P.XP, P.XR, CB)) return -1;
+  if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, P.XP, P.XR, CB)) return -1;
+  const int nob = K / KB;
+  int gxd = sms / nob;
+  if (gxd < 1) gxd = 1;
+  if (gxd > P.rows_total) gxd = (int)P.rows_total;
+  const dim3 grid(gxd, nob);
+  // dL/dJ -> constant bank (device-to-device, stream ordered, capturable as a memcpy node)
+  static unsigned slot_counter = 0;
+  const int slot = (int)(slot_counter++ & 1u);
+  const size_t wfloats = (size_t)K * T2 * P.Kp;
+  P.wc_base = slot * (WC_SLOT_FLOATS / 2);
+  const size_t off = (size_t)slot * WC_SLOT_FLOATS * sizeof(float);
+  if (Wy == Wx + wfloats) {
+    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wx, 2 * wfloats * sizeof(float), off, cudaMemcpyDeviceToDevice, st));
+  } else {
+    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wx, wfloats * sizeof(float), off, cudaMemcpyDeviceToDevice, st));
+    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wy, wfloats * sizeof(float), off + wfloats * sizeof(float),
+                                           cudaMemcpyDeviceToDevice, st));
+  }
+#define IIC_BWD_LAUNCH(KK)                                                              \
+  switch (cfg) {                                                                        \
+    case 1: return launch_bwd_fast<KK, 1, 24, 3, 5>(mx, my, P, grid, smem, st);         \
+    default: return launch_bwd_fast<KK, 1, 16, 4, 5>(mx, my, P, grid, smem, st);        \
+  }
+  if (K == 10) { IIC_BWD_LAUNCH(10) }
+  IIC_BWD_LAUNCH(20)
+#undef IIC_BWD_LAUNCH
+}
+
+}  // namespace iic

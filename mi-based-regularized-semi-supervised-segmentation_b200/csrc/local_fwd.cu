@@ -246,21 +246,34 @@ __global__ void __launch_bounds__(384, 1) local_joint_kernel(const LocalFwdParam
   }
 }
 
-// J[p][e] = sum over CTAs of partial[p][cta][e], in CTA order, in float64
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int ncta, long long E,
-                                       double* __restrict__ J) {
-  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+// J[p][e] = sum over CTAs of partial[p][cta][e] in float64, in a fixed order: a block is 32 slot groups x
+// 32 consecutive elements (coalesced 128-byte reads); group g adds slots g, g+32, ... in order, then the 32
+// group sums are added in order.
+constexpr int RED_GROUPS = 32;
+__global__ void __launch_bounds__(RED_GROUPS * 32)
+reduce_partials_kernel(const float* __restrict__ partial, int ncta, long long E, double* __restrict__ J) {
+  __shared__ double sm[RED_GROUPS][33];
+  const int le = threadIdx.x & 31, sg = threadIdx.x >> 5;
+  const long long e = (long long)blockIdx.x * 32 + le;
   const int patch = blockIdx.y;
-  if (e >= E) return;
-  const float* src = partial + (size_t)patch * ncta * E + e;
-  double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  int c = 0;
-  for (; c + 8 <= ncta; c += 8) {
+  double s[4] = {0, 0, 0, 0};
+  if (e < E) {
+    const float* src = partial + (size_t)patch * ncta * E + e;
+    int c = sg;
+    for (; c + 3 * RED_GROUPS < ncta; c += 4 * RED_GROUPS) {
 #pragma unroll
-    for (int q = 0; q < 8; ++q) s[q] += (double)__ldg(src + (size_t)(c + q) * E);
+      for (int q = 0; q < 4; ++q) s[q] += (double)__ldg(src + (size_t)(c + q * RED_GROUPS) * E);
+    }
+    for (int q = 0; c < ncta; c += RED_GROUPS, ++q) s[q] += (double)__ldg(src + (size_t)c * E);
   }
-  for (int q = 0; c < ncta; ++c, ++q) s[q] += (double)__ldg(src + (size_t)c * E);
-  J[(size_t)patch * E + e] = ((s[0] + s[1]) + (s[2] + s[3])) + ((s[4] + s[5]) + (s[6] + s[7]));
+  sm[sg][le] = (s[0] + s[1]) + (s[2] + s[3]);
+  __syncthreads();
+  if (sg == 0 && e < E) {
+    double t = 0;
+#pragma unroll
+    for (int g = 0; g < RED_GROUPS; ++g) t += sm[g][le];
+    J[(size_t)patch * E + e] = t;
+  }
 }
 
 // ---- host side ------------------------------------------------------------------------------------
@@ -356,6 +369,9 @@ namespace iic {
 int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                         long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                         float* partial, int max_ctas, int* ncta, cudaStream_t st);
+int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                         long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                         float* partial, int max_ctas, int* ncta, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -383,13 +399,16 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
   if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
     int ncta = 0;
-    const int rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
-                                       (float*)workspace, pl.slots_per_patch, &ncta, st);
+    int rc = getenv("IIC_B200_NO_FAST") ? -1
+                 : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
+                                        (float*)workspace, pl.slots_per_patch, &ncta, st);
+    if (rc < 0)
+      rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
+                               (float*)workspace, pl.slots_per_patch, &ncta, st);
     if (rc > 0) return rc;
     if (rc == 0) {
-      const int threads = 256;
-      dim3 rgrid((unsigned)((E + threads - 1) / threads), 1);
-      reduce_partials_kernel<<<rgrid, threads, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+      dim3 rgrid((unsigned)((E + 31) / 32), 1);
+      reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
       IIC_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
@@ -444,10 +463,9 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
     }
   }
   {
-    const int threads = 256;
-    dim3 rgrid((unsigned)((E + threads - 1) / threads), pl.n_patches);
-    reduce_partials_kernel<<<rgrid, threads, 0, st>>>((const float*)workspace, pl.ctas_per_patch,
-                                                      (long long)E, J_out);
+    dim3 rgrid((unsigned)((E + 31) / 32), pl.n_patches);
+    reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, pl.ctas_per_patch,
+                                                             (long long)E, J_out);
     IIC_CHECK_CUDA(cudaGetLastError());
   }
   return 0;

@@ -1,0 +1,229 @@
+// Specialised local joint (contrastyou/losses/iic_loss.py:120-123) for the 3 x 3 window (padding = 1) and
+// channel counts that are multiples of 10 -- the shapes of the reference's udaiic configuration
+// (config/semi.yaml: 10 or 20 clusters, paddings [1, ...]).  Same output-stationary scheme as
+// local_fwd_tma.cu, but every extent is a compile-time constant so that the inner loop is nothing but
+// shared-memory loads at immediate offsets and packed FP32 FMAs:
+//   * a 10 x 10 block of (x channel, y channel) pairs is cut into 10 jobs of 2 x 5 channels; a job keeps
+//     its 2 x 5 x 9 sums as 45 float2 accumulators (pairs over the two x channels) and is owned by one warp,
+//     lanes = the 32 pixel columns of the tile, walking down the 16 tile rows with a rolling 3-row window:
+//     per row 6 + 5 LDS.32, 5 MOV and 45 FFMA2;
+//   * 10 jobs do not spread evenly over the SM's 4 sub-partitions (3,3,2,2 warps), so jobs 0 and 1 are
+//     split by rows between their own warp and a helper warp (warps 10, 11): every sub-partition then
+//     issues exactly 40 row-jobs per tile;
+//   * 12 warps = 3 per sub-partition leaves 168 registers per thread, so there is no dedicated producer
+//     warp (a 13th warp would cap the kernel at 128 registers and spill the accumulators): lane 0 of
+//     helper warp 10, which has half a job's work and therefore slack, issues the TMA loads -- rank-4
+//     boxes of the x tile (with halo) and the y tile into a 4-stage full/empty mbarrier ring, out-of-range
+//     elements zero-filled by the hardware (= the conv padding);
+//   * K = 20, 30, ...: blockIdx.y selects the (x block, y block) pair, the tensor-map channel coordinate
+//     does the slicing.
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace iic {
+
+namespace fwdfast {
+constexpr int T = 3, PAD = 1, TH = 16, TW = 32, LP = 4, XP = LP + TW + 4, XR = TH + 2 * PAD;
+constexpr int KB = 10;                 // channel block
+constexpr int JT = 5;                  // y channels per job
+constexpr int NJOBS = (KB / 2) * (KB / JT);        // 10
+constexpr int NHELP = 2;               // helper warps (jobs 0 and 1 are split by rows)
+constexpr int NCONS = NJOBS + NHELP;   // 12 consumer warps
+constexpr int NTHREADS = NCONS * 32;
+constexpr int PRODUCER_WARP = NJOBS;   // helper warp 10
+constexpr int STAGES = 4;
+constexpr unsigned X_BYTES = KB * XR * XP * 4;
+constexpr unsigned Y_BYTES = KB * TH * TW * 4;
+constexpr unsigned X_REGION = (X_BYTES + 127u) & ~127u;
+constexpr unsigned STAGE_BYTES = X_REGION + ((Y_BYTES + 127u) & ~127u);
+constexpr int XPLANE = XR * XP, YPLANE = TH * TW;
+}  // namespace fwdfast
+
+struct FwdFastParams {
+  int B, K, tiles_h, tiles_w;
+  float* partial;           // [gridDim.x][9][K][K]
+};
+
+// rows [0, NROWS) of a job; xa/xb point at (window row 0, dx 0) of the job's two x channels for this
+// lane, y0 at (row 0) of the job's first y channel for this lane.
+template <int NROWS>
+__device__ __forceinline__ void sweep_rows(const float* __restrict__ xa, const float* __restrict__ xb,
+                                           const float* __restrict__ y0, float2 (&acc)[fwdfast::JT][3][3]) {
+  using namespace fwdfast;
+  float2 xw[3][3];
+#pragma unroll
+  for (int r = 0; r < 2; ++r)
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) xw[r][dx] = make_float2(xa[r * XP + dx], xb[r * XP + dx]);
+
+  auto row = [&](const int u, const int slot_new, const float* pa, const float* pb, const float* py) {
+    // pa/pb/py are the loop-carried bases; u is the static row offset inside the unrolled body
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx)
+      xw[slot_new][dx] = make_float2(pa[(u + 2) * XP + dx], pb[(u + 2) * XP + dx]);
+    float2 yv[JT];
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj) {
+      const float v = py[jj * YPLANE + u * TW];
+      yv[jj] = make_float2(v, v);
+    }
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+          acc[jj][dy][dx] = __ffma2_rn(xw[(slot_new + 1 + dy) % 3][dx], yv[jj], acc[jj][dy][dx]);
+  };
+
+  constexpr int NLOOP = NROWS / 3;
+#pragma unroll 1
+  for (int it = 0; it < NLOOP; ++it) {
+    row(0, 2, xa, xb, y0);
+    row(1, 0, xa, xb, y0);
+    row(2, 1, xa, xb, y0);
+    xa += 3 * XP; xb += 3 * XP; y0 += 3 * TW;
+  }
+  if constexpr (NROWS % 3 >= 1) row(0, 2, xa, xb, y0);
+  if constexpr (NROWS % 3 == 2) row(1, 0, xa, xb, y0);
+}
+
+__global__ void __launch_bounds__(fwdfast::NTHREADS, 1)
+local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
+                        const FwdFastParams P) {
+  using namespace fwdfast;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[STAGES];
+  __shared__ __align__(8) uint64_t empty_bar[STAGES];
+  __shared__ float red[NCONS][JT * 9 * 2];          // per-warp reduced sums
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = P.B * P.tiles_h * P.tiles_w;
+  const int nblk = P.K / KB;
+  const int i_off = ((int)blockIdx.y / nblk) * KB, j_off = ((int)blockIdx.y % nblk) * KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], NCONS);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  auto issue = [&](int k) {          // stage the k-th work item of this CTA (if there is one)
+    const int it = blockIdx.x + k * gridDim.x;
+    if (it >= items) return;
+    const int s = k % STAGES;
+    const int n = it / (P.tiles_h * P.tiles_w);
+    const int tt = it - n * (P.tiles_h * P.tiles_w);
+    const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
+    unsigned char* base = smem_raw + (size_t)s * STAGE_BYTES;
+    mbar_arrive_expect_tx(&full_bar[s], X_BYTES + Y_BYTES);
+    tma_load_4d(base, &mapx, &full_bar[s], tw0 - LP, th0 - PAD, i_off, n);
+    tma_load_4d(base + X_REGION, &mapy, &full_bar[s], tw0, th0, j_off, n);
+  };
+  const bool producer = (wid == PRODUCER_WARP && lane == 0);
+  if (producer) {
+    tma_prefetch_desc(&mapx);
+    tma_prefetch_desc(&mapy);
+    for (int k = 0; k < STAGES; ++k) issue(k);
+  }
+  {
+    const int job = wid < NJOBS ? wid : wid - NJOBS;
+    const bool split = job < NHELP;                    // this job's rows are shared with a helper warp
+    const int r0 = (wid >= NJOBS) ? TH / 2 : 0;
+    const int ip = job / (KB / JT), jg = job % (KB / JT);
+    const int xoff = (2 * ip) * XPLANE + r0 * XP + (LP - PAD) + lane;
+    const int yoff = (jg * JT) * YPLANE + r0 * TW + lane;
+
+    float2 acc[JT][3][3];
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) acc[jj][dy][dx] = make_float2(0.f, 0.f);
+
+    int k = 0;
+    for (int it = blockIdx.x; it < items; it += gridDim.x, ++k) {
+      const int s = k % STAGES;
+      const unsigned use = (unsigned)(k / STAGES);
+      if (producer && k >= 1) {
+        // item k-1 has been consumed by every warp -> its stage takes item k-1+STAGES
+        mbar_wait(&empty_bar[(k - 1) % STAGES], ((unsigned)((k - 1) / STAGES)) & 1u);
+        issue(k - 1 + STAGES);
+      }
+      __syncwarp();
+      mbar_wait(&full_bar[s], use & 1u);
+      const float* xs = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES) + xoff;
+      const float* ys = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION) + yoff;
+      if (split) sweep_rows<TH / 2>(xs, xs + XPLANE, ys, acc);
+      else       sweep_rows<TH>(xs, xs + XPLANE, ys, acc);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[s]);
+    }
+
+    // lanes -> one value per accumulator
+    int a = 0;
+#pragma unroll
+    for (int jj = 0; jj < JT; ++jj)
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float v0 = warp_sum(acc[jj][dy][dx].x);
+          const float v1 = warp_sum(acc[jj][dy][dx].y);
+          if (lane == (a & 31)) {
+            red[wid][2 * a] = v0;
+            red[wid][2 * a + 1] = v1;
+          }
+          ++a;
+        }
+  }
+  __syncthreads();
+  // this CTA's partial block: slot[d][i_off + i][j_off + j]
+  float* slot = P.partial + (size_t)blockIdx.x * (9 * P.K * P.K);
+  for (int e = threadIdx.x; e < NJOBS * JT * 9 * 2; e += blockDim.x) {
+    const int job = e / (JT * 9 * 2), r = e - job * (JT * 9 * 2);
+    const int a = r >> 1, half = r & 1;
+    const int jj = a / 9, d = a - jj * 9;
+    const int ip = job / (KB / JT), jg = job % (KB / JT);
+    float v = red[job][r];
+    if (job < NHELP) v += red[NJOBS + job][r];
+    slot[((size_t)d * P.K + (i_off + 2 * ip + half)) * P.K + (j_off + jg * JT + jj)] = v;
+  }
+}
+
+// 0 = launched, 1 = error, -1 = not eligible.  *ncta = number of partial slots written.
+int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                         long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                         float* partial, int max_ctas, int* ncta, cudaStream_t st) {
+  using namespace fwdfast;
+  if (pad != PAD || K < KB || K % KB != 0 || K > 40) return -1;
+  if (W % 4 != 0) return -1;
+  CUtensorMap mx, my;
+  if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, XP, XR, KB)) return -1;
+  if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, TW, TH, KB)) return -1;
+  FwdFastParams P;
+  P.B = B; P.K = K;
+  P.tiles_h = (H + TH - 1) / TH;
+  P.tiles_w = (W + TW - 1) / TW;
+  P.partial = partial;
+  const int nblk = K / KB, npairs = nblk * nblk;
+  long long items = (long long)B * P.tiles_h * P.tiles_w;
+  int gx = max_ctas / npairs;
+  if (gx < 1) gx = 1;
+  if (gx > items) gx = (int)items;
+  *ncta = gx;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(STAGES * STAGE_BYTES)));
+    attr_set = true;
+  }
+  local_joint_fast_kernel<<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace iic
