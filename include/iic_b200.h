@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IIC_B200_ABI_VERSION 1
+#define IIC_B200_ABI_VERSION 2
 
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
@@ -64,13 +64,15 @@ size_t iic_local_joint_workspace_bytes(int device, int B, int K, int H, int W, i
 /* J[patch][dy][dx][i][j] = sum_{n,u,v} x[n,i,u+dy-pad,v+dx-pad] * y[n,j,u,v]  over the patch, x zero
  * outside the patch (iic_loss.py:120-123, the F.conv2d).  mask (nullable; (B,1|K,H,W), m_sc = 0 for
  * one channel) multiplies both maps first (iic_loss.py:116-118).  Partial sums are fp32 inside one
- * CTA, combined across CTAs in fp64 in a fixed order (deterministic). J_out is float64. */
+ * CTA, combined across CTAs in fp64 in a fixed order (deterministic). J_out is float64.
+ * flags (nullable): also run the simplex assertion of iic_loss.py:113 on x (needs x_sh == W); it is
+ * fused into the joint kernel where that kernel holds all K channels of a pixel, else one extra pass. */
 int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
                     const float* y, long long y_sn, long long y_sc, long long y_sh,
                     const float* mask, long long m_sn, long long m_sc, long long m_sh,
                     int B, int K, int H, int W, int pad,
                     int patch_h, int patch_w, int step_h, int step_w,
-                    double* J_out, void* workspace, size_t workspace_bytes, void* stream);
+                    double* J_out, void* workspace, size_t workspace_bytes, int* flags, void* stream);
 
 /* number of floats in each of the Wx / Wy coefficient buffers written by iic_local_epilogue */
 size_t iic_local_coeff_floats(int K, int pad, int n_patches);
@@ -105,20 +107,23 @@ int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long
  * (iic_loss.py:43-71).
  * ---------------------------------------------------------------------------------------------- */
 size_t iic_global_joint_workspace_bytes(int device, long long N, int K);
-/* J[i][j] = sum_n x[n,i]*y[n,j]  (iic_loss.py:88-89), float64 out, deterministic */
+/* J[i][j] = sum_n x[n,i]*y[n,j]  (iic_loss.py:88-89), float64 out, deterministic.
+ * flags (nullable): the simplex assertions of iic_loss.py:50-51 / 82-83 on x and y, fused. */
 int iic_global_joint(const float* x, long long x_sn, const float* y, long long y_sn,
                      long long N, int K, double* J_out, void* workspace, size_t workspace_bytes,
-                     void* stream);
+                     int* flags, void* stream);
 /* P = sym(J)/sum (iic_loss.py:91-92; symmetric=0 skips the symmetrisation), and when losses_out is
  * non-NULL the two entropy expressions of iic_loss.py:63-69: losses_out[0]=loss(lamb),
  * losses_out[1]=loss_no_lamb.  P_out is float32 (K,K). */
 int iic_global_epilogue(const double* J, int K, double lamb, int symmetric,
                         float* losses_out, float* P_out, int* flags, void* stream);
-/* gradients of  g[0]*loss + g[1]*loss_no_lamb + <gP, P>  w.r.t. x and y, from the saved J.
- * g (2 floats, nullable = {1,0}) and gP ((K,K) float32, nullable) are device pointers. */
+/* gradients of  g_loss*loss + g_no_lamb*loss_no_lamb + <gP, P>  w.r.t. x and y, from the saved J.
+ * g_loss, g_no_lamb (device scalars) and gP ((K,K) float32) are the upstream gradients of the three
+ * outputs of IIDLoss.forward; each is nullable and NULL means "no gradient flows into that output". */
 int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
                         long long N, int K, const double* J, double lamb, int symmetric,
-                        const float* g, const float* gP, float* gx, float* gy, void* stream);
+                        const float* g_loss, const float* g_no_lamb, const float* gP,
+                        float* gx, float* gy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * UDA consistency on (outer, C, inner) contiguous maps.  kind 0 = torch.nn.MSELoss() mean over all

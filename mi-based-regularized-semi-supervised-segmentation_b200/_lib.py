@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libiic_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 FLAG_NAN_LOSS = 1
 FLAG_NOT_SIMPLEX = 2
 
@@ -29,16 +29,16 @@ PROTOTYPES = {
     "iic_local_num_patches": (_i, [_i] * 6),
     "iic_local_joint_workspace_bytes": (_sz, [_i] * 10),
     "iic_local_joint": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
-                             _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p]),
+                             _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _sz, _p, _p]),
     "iic_local_coeff_floats": (_sz, [_i, _i, _i]),
     "iic_local_epilogue_workspace_bytes": (_sz, [_i, _i, _i]),
     "iic_local_epilogue": (_i, [_p, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "iic_local_backward": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
     "iic_global_joint_workspace_bytes": (_sz, [_i, _ll, _i]),
-    "iic_global_joint": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _sz, _p]),
+    "iic_global_joint": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _sz, _p, _p]),
     "iic_global_epilogue": (_i, [_p, _i, _d, _i, _p, _p, _p, _p]),
-    "iic_global_backward": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _d, _i, _p, _p, _p, _p, _p]),
+    "iic_global_backward": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _d, _i, _p, _p, _p, _p, _p, _p]),
     "iic_uda_workspace_bytes": (_sz, [_i]),
     "iic_uda_forward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _i, _p, _p]),
     "iic_uda_backward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _p]),

@@ -146,7 +146,7 @@ constexpr int GLOBAL_ROWS = 32;
 __global__ void __launch_bounds__(1024) global_joint_kernel(const float* __restrict__ x, long long x_sn,
                                                             const float* __restrict__ y, long long y_sn,
                                                             long long N, int K, long long rows_per_cta,
-                                                            double* __restrict__ partial) {
+                                                            double* __restrict__ partial, int* __restrict__ flags) {
   extern __shared__ __align__(16) float gsm[];
   float* xs = gsm;                       // [GLOBAL_ROWS][K]
   float* ys = gsm + GLOBAL_ROWS * K;
@@ -167,6 +167,13 @@ __global__ void __launch_bounds__(1024) global_joint_kernel(const float* __restr
       ys[e] = y[(rb + r) * y_sn + c];
     }
     __syncthreads();
+    if (flags != nullptr && tid < 2 * nr) {
+      // fused simplex assertions on both inputs (iic_loss.py:50-51,82-83): thread -> one staged row
+      const float* row = (tid < nr ? xs : ys) + (tid < nr ? tid : tid - nr) * K;
+      float sum = 0.f;
+      for (int c = 0; c < K; ++c) sum += row[c];
+      if (!(fabsf(sum - 1.f) <= 1e-4f + 1e-4f * 1.f)) atomicOr(flags, IIC_FLAG_NOT_SIMPLEX);
+    }
 #pragma unroll
     for (int q = 0; q < GLOBAL_EPT; ++q) {
       const int e = tid + q * nt;
@@ -252,8 +259,9 @@ __global__ void __launch_bounds__(1024) global_epilogue_kernel(const double* __r
 // slab of rows of gx = y GJ^T and gy = x GJ.
 __global__ void __launch_bounds__(256) global_backward_kernel(
     const float* __restrict__ x, long long x_sn, const float* __restrict__ y, long long y_sn, long long N,
-    int K, const double* __restrict__ J, double lamb, int symmetric, const float* __restrict__ g,
-    const float* __restrict__ gP, float* __restrict__ gx, float* __restrict__ gy,
+    int K, const double* __restrict__ J, double lamb, int symmetric, const float* __restrict__ g_loss,
+    const float* __restrict__ g_no_lamb, const float* __restrict__ gP, float* __restrict__ gx,
+    float* __restrict__ gy,
     long long rows_per_cta) {
   extern __shared__ __align__(16) double sm[];
   double* scratch = sm;            // 33
@@ -265,7 +273,7 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t KK = (size_t)K * K;
   const double eps = 1e-10;
-  const double g1 = g ? (double)g[0] : 1.0, g2 = g ? (double)g[1] : 0.0;
+  const double g1 = g_loss ? (double)g_loss[0] : 0.0, g2 = g_no_lamb ? (double)g_no_lamb[0] : 0.0;
   auto Jsym = [&](int i, int j) {
     return symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
   };
@@ -376,7 +384,7 @@ extern "C" size_t iic_global_joint_workspace_bytes(int device, long long N, int 
 
 extern "C" int iic_global_joint(const float* x, long long x_sn, const float* y, long long y_sn,
                                 long long N, int K, double* J_out, void* workspace,
-                                size_t workspace_bytes, void* stream) {
+                                size_t workspace_bytes, int* flags, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IIC_REQUIRE(x && y && J_out, "iic_global_joint: null pointer");
   IIC_REQUIRE(N > 0 && K > 0, "iic_global_joint: empty input (N=%lld K=%d)", N, K);
@@ -389,10 +397,15 @@ extern "C" int iic_global_joint(const float* x, long long x_sn, const float* y, 
   int nt = K * K;
   nt = nt > 1024 ? 1024 : ((nt + 31) & ~31);
   const size_t smem = 2 * (size_t)GLOBAL_ROWS * K * sizeof(float);
-  global_joint_kernel<<<ctas, nt, smem, st>>>(x, x_sn, y, y_sn, N, K, rpc, (double*)workspace);
+  if (nt < 2 * GLOBAL_ROWS) nt = 2 * GLOBAL_ROWS;          // one thread per staged row for the assertion
+  // a single CTA (N <= 256 rows, the udaiic case) writes J directly: no partial slots, no reduce launch
+  global_joint_kernel<<<ctas, nt, smem, st>>>(x, x_sn, y, y_sn, N, K, rpc, ctas == 1 ? J_out : (double*)workspace,
+                                              flags);
   IIC_CHECK_CUDA(cudaGetLastError());
-  global_reduce_kernel<<<(K * K + 255) / 256, 256, 0, st>>>((const double*)workspace, ctas, K * K, J_out);
-  IIC_CHECK_CUDA(cudaGetLastError());
+  if (ctas > 1) {
+    global_reduce_kernel<<<(K * K + 255) / 256, 256, 0, st>>>((const double*)workspace, ctas, K * K, J_out);
+    IIC_CHECK_CUDA(cudaGetLastError());
+  }
   return 0;
 }
 
@@ -411,7 +424,8 @@ extern "C" int iic_global_epilogue(const double* J, int K, double lamb, int symm
 
 extern "C" int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
                                    long long N, int K, const double* J, double lamb, int symmetric,
-                                   const float* g, const float* gP, float* gx, float* gy, void* stream) {
+                                   const float* g_loss, const float* g_no_lamb, const float* gP, float* gx,
+                                   float* gy, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IIC_REQUIRE(x && y && J && gx && gy, "iic_global_backward: null pointer");
   IIC_REQUIRE(N > 0 && K > 0 && K <= 128, "iic_global_backward: bad sizes N=%lld K=%d", N, K);
@@ -422,7 +436,7 @@ extern "C" int iic_global_backward(const float* x, long long x_sn, const float* 
   if (smem > 48 * 1024) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g, gP, gx, gy, rpc);
+  kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy, rpc);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

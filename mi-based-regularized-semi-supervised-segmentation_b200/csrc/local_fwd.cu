@@ -371,7 +371,7 @@ int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long lon
                         float* partial, int max_ctas, int* ncta, cudaStream_t st);
 int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                         float* partial, int max_ctas, int* ncta, cudaStream_t st);
+                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -379,9 +379,11 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
                                const float* mask, long long m_sn, long long m_sc, long long m_sh,
                                int B, int K, int H, int W, int pad,
                                int patch_h, int patch_w, int step_h, int step_w,
-                               double* J_out, void* workspace, size_t workspace_bytes, void* stream) {
+                               double* J_out, void* workspace, size_t workspace_bytes, int* flags,
+                               void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IIC_REQUIRE(x && y && J_out, "iic_local_joint: null pointer");
+  IIC_REQUIRE(!flags || x_sh == W, "iic_local_joint: the fused simplex assertion needs dense rows (x_sh == W)");
   IIC_REQUIRE(B > 0 && K > 0, "iic_local_joint: empty batch or channel dimension (B=%d K=%d)", B, K);
   IIC_REQUIRE(pad >= 0 && pad <= 7, "iic_local_joint: padding %d unsupported (0..7)", pad);
   PatchGrid g;
@@ -396,17 +398,25 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   IIC_REQUIRE(workspace && workspace_bytes >= need, "iic_local_joint: workspace too small (%zu < %zu)",
               workspace_bytes, need);
 
+  // simplex assertion on x when the joint kernel chosen below cannot fuse it: one streaming pass
+  auto simplex_pass = [&]() -> int {
+    if (!flags) return 0;
+    return iic_simplex_check(x, B, K, (long long)H * W, x_sn, x_sc, flags, stream);
+  };
+
   // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
   if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
-    int ncta = 0;
+    int ncta = 0, checked = 0;
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
-                                        (float*)workspace, pl.slots_per_patch, &ncta, st);
+                                        (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, st);
+    if (rc == 0 && checked) flags = nullptr;       // done inside the joint kernel
     if (rc < 0)
       rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                (float*)workspace, pl.slots_per_patch, &ncta, st);
     if (rc > 0) return rc;
     if (rc == 0) {
+      if (int e = simplex_pass()) return e;
       dim3 rgrid((unsigned)((E + 31) / 32), 1);
       reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
       IIC_CHECK_CUDA(cudaGetLastError());
@@ -414,6 +424,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
     }
   }
 
+  if (int e = simplex_pass()) return e;
   LocalFwdParams P;
   P.x = {x, x_sn, x_sc, x_sh};
   P.y = {y, y_sn, y_sc, y_sh};

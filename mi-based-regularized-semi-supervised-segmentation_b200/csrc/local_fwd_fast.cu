@@ -40,8 +40,9 @@ constexpr int XPLANE = XR * XP, YPLANE = TH * TW;
 }  // namespace fwdfast
 
 struct FwdFastParams {
-  int B, K, tiles_h, tiles_w;
+  int B, K, H, W, tiles_h, tiles_w;
   float* partial;           // [gridDim.x][9][K][K]
+  int* flags;               // non-null (and K == 10): also assert that x is a simplex over its channels
 };
 
 // rows [0, NROWS) of a job; xa/xb point at (window row 0, dx 0) of the job's two x channels for this
@@ -159,6 +160,26 @@ local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_c
       const float* ys = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION) + yoff;
       if (split) sweep_rows<TH / 2>(xs, xs + XPLANE, ys, acc);
       else       sweep_rows<TH>(xs, xs + XPLANE, ys, acc);
+      if (P.flags != nullptr && wid >= NJOBS) {
+        // simplex assertion on x (dc2:utils/assertion.py:56-65 as called at iic_loss.py:113), fused: the
+        // two helper warps have half a job each, so they also add up the K channels of every pixel of
+        // the tile (8 rows each) while it is in shared memory -- no second pass over the map in HBM.
+        const int n = it / (P.tiles_h * P.tiles_w);
+        const int tt = it - n * (P.tiles_h * P.tiles_w);
+        const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
+        const float* xc = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES) +
+                          (PAD + (wid - NJOBS) * (TH / 2)) * XP + LP + lane;
+        bool bad = false;
+#pragma unroll
+        for (int r = 0; r < TH / 2; ++r) {
+          float sum = 0.f;
+#pragma unroll
+          for (int c = 0; c < KB; ++c) sum += xc[c * XPLANE + r * XP];
+          const bool valid = (th0 + (wid - NJOBS) * (TH / 2) + r < P.H) && (tw0 + lane < P.W);
+          bad |= valid && !(fabsf(sum - 1.f) <= 1e-4f + 1e-4f * 1.f);     // allclose(sum, 1, 1e-4, 1e-4); NaN fails
+        }
+        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
@@ -195,9 +216,10 @@ local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_c
 }
 
 // 0 = launched, 1 = error, -1 = not eligible.  *ncta = number of partial slots written.
+// *checked = 1 when `flags` was given and the simplex assertion on x ran inside the kernel.
 int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                         float* partial, int max_ctas, int* ncta, cudaStream_t st) {
+                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, cudaStream_t st) {
   using namespace fwdfast;
   if (pad != PAD || K < KB || K % KB != 0 || K > 40) return -1;
   if (W % 4 != 0) return -1;
@@ -205,7 +227,9 @@ int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long lo
   if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, XP, XR, KB)) return -1;
   if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, TW, TH, KB)) return -1;
   FwdFastParams P;
-  P.B = B; P.K = K;
+  P.B = B; P.K = K; P.H = H; P.W = W;
+  P.flags = (K == KB) ? flags : nullptr;
+  *checked = P.flags != nullptr;
   P.tiles_h = (H + TH - 1) / TH;
   P.tiles_w = (W + TW - 1) / TW;
   P.partial = partial;

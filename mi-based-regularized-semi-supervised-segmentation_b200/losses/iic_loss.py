@@ -44,9 +44,9 @@ class IIDLoss(nn.Module):
     def forward(self, x_out: Tensor, x_tf_out: Tensor):
         """Returns ``(loss, loss_no_lamb, p_i_j)`` (iic_loss.py:43-71)."""
         assert x_out.dim() == 2 and x_tf_out.shape == x_out.shape, (x_out.shape, x_tf_out.shape)
-        checks.device_simplex(x_out)       # :50
-        checks.device_simplex(x_tf_out)    # :51
-        loss, loss_no_lamb, p_i_j = GlobalIICFunction.apply(x_out, x_tf_out, self.lamb)
+        # the simplex assertions of :50-51 run inside the joint kernel
+        loss, loss_no_lamb, p_i_j = GlobalIICFunction.apply(x_out, x_tf_out, self.lamb,
+                                                            checks.want_simplex_kernels())
         checks.finish(x_out.device, loss, "x_out / x_tf_out not normalized.")
         return loss, loss_no_lamb, p_i_j
 
@@ -55,9 +55,8 @@ def compute_joint(x_out: Tensor, x_tf_out: Tensor, symmetric=True) -> Tensor:
     """Joint probability of two (N, K) simplex batches; mirrors iic_loss.py:74-94."""
     bn, k = x_out.shape
     assert x_tf_out.size(0) == bn and x_tf_out.size(1) == k
-    checks.device_simplex(x_out)       # :82
-    checks.device_simplex(x_tf_out)    # :83
-    p_i_j = JointFunction.apply(x_out, x_tf_out, bool(symmetric))
+    # the simplex assertions of :82-83 run inside the joint kernel
+    p_i_j = JointFunction.apply(x_out, x_tf_out, bool(symmetric), checks.want_simplex_kernels())
     checks.finish(x_out.device, None, "x_out / x_tf_out not normalized.")
     return p_i_j
 
@@ -77,9 +76,10 @@ class IIDSegmentationLoss(nn.Module):
         if mask is not None:
             assert not mask.requires_grad                            # :112
         assert x_out.shape == x_tf_out.shape                         # :114
-        checks.device_simplex(x_out)                                 # :113 (x_out only, as in the reference)
+        # :113 asserts simplex(x_out) only; here it runs inside the joint kernel
         loss = LocalIICFunction.apply(x_out, x_tf_out, mask, int(self.padding), int(patch[0]), int(patch[1]),
-                                      int(step[0]), int(step[1]), float(self.lamda))
+                                      int(step[0]), int(step[1]), float(self.lamda),
+                                      checks.want_simplex_kernels())
         checks.finish(x_out.device, loss, "x_out is not a simplex over dim 1")
         return loss
 

@@ -16,14 +16,14 @@ from . import _lib
 
 _LIBDEF = torch.library.Library("iic_b200", "DEF")
 _LIBDEF.define("local_joint(Tensor x, Tensor y, Tensor? mask, int pad, int patch_h, int patch_w, "
-               "int step_h, int step_w) -> Tensor")
+               "int step_h, int step_w, bool check_simplex=False) -> Tensor")
 _LIBDEF.define("local_epilogue(Tensor J, int K, int pad, float lamda) -> (Tensor, Tensor, Tensor)")
 _LIBDEF.define("local_backward(Tensor x, Tensor y, Tensor? mask, Tensor Wx, Tensor Wy, Tensor grad, int pad, "
                "int patch_h, int patch_w, int step_h, int step_w) -> (Tensor, Tensor)")
-_LIBDEF.define("global_joint(Tensor x, Tensor y) -> Tensor")
+_LIBDEF.define("global_joint(Tensor x, Tensor y, bool check_simplex=False) -> Tensor")
 _LIBDEF.define("global_epilogue(Tensor J, float lamb, bool symmetric, bool want_losses) -> (Tensor, Tensor)")
-_LIBDEF.define("global_backward(Tensor x, Tensor y, Tensor J, float lamb, bool symmetric, Tensor? g, Tensor? gP) "
-               "-> (Tensor, Tensor)")
+_LIBDEF.define("global_backward(Tensor x, Tensor y, Tensor J, float lamb, bool symmetric, Tensor? g_loss, "
+               "Tensor? g_no_lamb, Tensor? gP) -> (Tensor, Tensor)")
 _LIBDEF.define("uda_forward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
                "bool check_simplex) -> Tensor")
 _LIBDEF.define("uda_backward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
@@ -100,7 +100,7 @@ def _mask_args(mask: Optional[torch.Tensor], x: torch.Tensor):
 
 
 # ---- op implementations ------------------------------------------------------------------------------
-def _local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w):
+def _local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w, check_simplex=False):
     lib = _lib.load()
     _require_cuda_f32("x_out", x)
     _require_cuda_f32("x_tf_out", y)
@@ -119,11 +119,19 @@ def _local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w):
         _lib.check(1, "iic_local_joint_workspace_bytes")
     ws = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     J = torch.empty((npatch, T, T, K, K), dtype=torch.float64, device=x.device)
+    flags = None
+    if check_simplex:
+        # the assertion on x_out (iic_loss.py:113) rides along with the joint kernel; rows that are not
+        # dense (a sliced view) take the stand-alone streaming check instead
+        if x.stride(2) == W:
+            flags = _state(x.device).flags.data_ptr()
+        else:
+            _simplex_check(x, 1)
     with torch.cuda.device(x.device):
         rc = lib.iic_local_joint(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
                                  y.data_ptr(), y.stride(0), y.stride(1), y.stride(2),
                                  _ptr(m), msn, msc, msh, B, K, H, W, pad, patch_h, patch_w, step_h, step_w,
-                                 J.data_ptr(), ws.data_ptr(), nbytes, _stream(x.device))
+                                 J.data_ptr(), ws.data_ptr(), nbytes, flags, _stream(x.device))
     _lib.check(rc, "iic_local_joint")
     return J
 
@@ -167,7 +175,7 @@ def _local_backward(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, ste
     return gx, gy
 
 
-def _global_joint(x, y):
+def _global_joint(x, y, check_simplex=False):
     lib = _lib.load()
     _require_cuda_f32("x_out", x)
     _require_cuda_f32("x_tf_out", y)
@@ -180,7 +188,8 @@ def _global_joint(x, y):
     J = torch.empty((K, K), dtype=torch.float64, device=x.device)
     with torch.cuda.device(x.device):
         rc = lib.iic_global_joint(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N, K, J.data_ptr(),
-                                  ws.data_ptr(), nbytes, _stream(x.device))
+                                  ws.data_ptr(), nbytes,
+                                  _state(x.device).flags.data_ptr() if check_simplex else None, _stream(x.device))
     _lib.check(rc, "iic_global_joint")
     return J
 
@@ -199,19 +208,22 @@ def _global_epilogue(J, lamb, symmetric, want_losses):
     return losses, P
 
 
-def _global_backward(x, y, J, lamb, symmetric, g, gP):
+def _global_backward(x, y, J, lamb, symmetric, g_loss, g_no_lamb, gP):
     lib = _lib.load()
     x, y = _w_contig(x), _w_contig(y)
     N, K = x.shape
     gx = torch.empty((N, K), dtype=torch.float32, device=x.device)
     gy = torch.empty((N, K), dtype=torch.float32, device=x.device)
-    if g is not None:
-        g = g.to(torch.float32).contiguous()
+    if g_loss is not None:
+        g_loss = g_loss.to(torch.float32).reshape(())
+    if g_no_lamb is not None:
+        g_no_lamb = g_no_lamb.to(torch.float32).reshape(())
     if gP is not None:
         gP = gP.to(torch.float32).contiguous()
     with torch.cuda.device(x.device):
         rc = lib.iic_global_backward(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N, K, J.data_ptr(),
-                                     float(lamb), int(symmetric), _ptr(g), _ptr(gP), gx.data_ptr(), gy.data_ptr(),
+                                     float(lamb), int(symmetric), _ptr(g_loss), _ptr(g_no_lamb), _ptr(gP),
+                                     gx.data_ptr(), gy.data_ptr(),
                                      _stream(x.device))
     _lib.check(rc, "iic_global_backward")
     return gx, gy
@@ -329,8 +341,8 @@ class LocalIICFunction(torch.autograd.Function):
     """loss = mean over patches of the shifted-window IIC loss (iic_loss.py:107-149, 171-186)."""
 
     @staticmethod
-    def forward(ctx, x, y, mask, pad, patch_h, patch_w, step_h, step_w, lamda):
-        J = ops.local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w)
+    def forward(ctx, x, y, mask, pad, patch_h, patch_w, step_h, step_w, lamda, check_simplex=False):
+        J = ops.local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w, check_simplex)
         J = _maybe_allreduce(J)
         loss, Wx, Wy = ops.local_epilogue(J, x.shape[1], pad, lamda)
         ctx.save_for_backward(x, y, mask, Wx, Wy)
@@ -341,34 +353,34 @@ class LocalIICFunction(torch.autograd.Function):
     def backward(ctx, grad):
         x, y, mask, Wx, Wy = ctx.saved_tensors
         gx, gy = ops.local_backward(x, y, mask, Wx, Wy, grad.contiguous(), *ctx.geom)
-        return gx, gy, None, None, None, None, None, None, None
+        return gx, gy, None, None, None, None, None, None, None, None
 
 
 class GlobalIICFunction(torch.autograd.Function):
     """(loss, loss_no_lamb, P) of IIDLoss.forward (iic_loss.py:43-71)."""
 
     @staticmethod
-    def forward(ctx, x, y, lamb):
-        J = _maybe_allreduce(ops.global_joint(x, y))
+    def forward(ctx, x, y, lamb, check_simplex=False):
+        J = _maybe_allreduce(ops.global_joint(x, y, check_simplex))
         losses, P = ops.global_epilogue(J, lamb, True, True)
         ctx.save_for_backward(x, y, J)
         ctx.lamb = lamb
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero tensors
         return losses[0], losses[1], P
 
     @staticmethod
     def backward(ctx, g1, g2, gP):
         x, y, J = ctx.saved_tensors
-        g = torch.stack([g1.reshape(()), g2.reshape(())]).to(torch.float32)
-        gx, gy = ops.global_backward(x, y, J, ctx.lamb, True, g, gP)
-        return gx, gy, None
+        gx, gy = ops.global_backward(x, y, J, ctx.lamb, True, g1, g2, gP)
+        return gx, gy, None, None
 
 
 class JointFunction(torch.autograd.Function):
     """P = compute_joint(x, y, symmetric) (iic_loss.py:74-94)."""
 
     @staticmethod
-    def forward(ctx, x, y, symmetric):
-        J = _maybe_allreduce(ops.global_joint(x, y))
+    def forward(ctx, x, y, symmetric, check_simplex=False):
+        J = _maybe_allreduce(ops.global_joint(x, y, check_simplex))
         _, P = ops.global_epilogue(J, 1.0, symmetric, False)
         ctx.save_for_backward(x, y, J)
         ctx.symmetric = symmetric
@@ -377,9 +389,8 @@ class JointFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, gP):
         x, y, J = ctx.saved_tensors
-        g = torch.zeros(2, dtype=torch.float32, device=x.device)
-        gx, gy = ops.global_backward(x, y, J, 1.0, ctx.symmetric, g, gP)
-        return gx, gy, None
+        gx, gy = ops.global_backward(x, y, J, 1.0, ctx.symmetric, None, None, gP)
+        return gx, gy, None, None
 
 
 class UDAFunction(torch.autograd.Function):
