@@ -1,0 +1,97 @@
+"""World-size-2 check of the data-parallel scheme on CPU with the gloo backend.
+
+The CUDA kernels cannot run here, so each rank builds its shard's partial joints with the oracle, the
+PRODUCT's exchange hook (``iic_b200.ops._maybe_allreduce`` under ``set_data_parallel(True)``) combines
+them, and the oracle's epilogue/backward finish locally.  What is asserted is the scheme itself
+(SURVEY.md section 8e): after ONE sum-all-reduce of the joints every rank holds the loss of the GLOBAL
+batch and the gradient of that loss with respect to its own shard.
+"""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _views(seed, B, K, H, W):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import iic_oracle as O
+    rng = np.random.default_rng(seed)
+    base = rng.standard_normal((B, K, H // 4, W // 4)).repeat(4, axis=2).repeat(4, axis=3) * 3
+    x = O.softmax(base + 0.5 * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    y = O.softmax(base + 0.5 * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    gx = O.softmax(rng.standard_normal((B, K)) * 2).astype(np.float32)
+    gy = O.softmax(rng.standard_normal((B, K)) * 2).astype(np.float32)
+    return x, y, gx, gy
+
+
+def _worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import iic_oracle as O
+    import iic_b200
+    from iic_b200 import ops as iops
+
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        B, K, H, W, pad = 4, 5, 16, 20, 1
+        x, y, gx, gy = _views(7, B, K, H, W)
+        lo, hi = rank * B // world, (rank + 1) * B // world
+        xs, ys = x[lo:hi], y[lo:hi]
+
+        iic_b200.set_data_parallel(True)
+        # local term: partial joint of the shard -> the product's exchange hook -> epilogue + backward locally
+        J = torch.from_numpy(O.local_joint(xs, ys, pad)[None])
+        J = iops._maybe_allreduce(J)
+        loss, GA = O.local_loss_from_joint(J[0].numpy(), 1.0)
+        dxs, dys = O.local_backward_from_GA(xs, ys, GA, pad)
+        # global term: J = x^T y
+        Jg = torch.from_numpy(gx[lo:hi].astype(np.float64).T @ gy[lo:hi].astype(np.float64))
+        Jg = iops._maybe_allreduce(Jg)
+        iic_b200.set_data_parallel(False)
+        # disabled hook must be the identity even with a process group up
+        same = torch.ones(3, dtype=torch.float64)
+        assert torch.equal(iops._maybe_allreduce(same.clone()), same)
+
+        full_loss, full_dx, full_dy = O.iid_segmentation_loss(x, y, pad, with_grads=True)
+        np.testing.assert_allclose(loss, full_loss, rtol=1e-12)
+        np.testing.assert_allclose(dxs, full_dx[lo:hi], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(dys, full_dy[lo:hi], rtol=1e-10, atol=1e-14)
+        np.testing.assert_allclose(Jg.numpy(), gx.astype(np.float64).T @ gy.astype(np.float64), rtol=1e-13)
+        out.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        out.put((rank, f"{type(e).__name__}: {e}"))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_sharded_joint_allreduce_world2():
+    if not dist.is_available() or not dist.is_gloo_available():
+        pytest.skip("gloo backend not available")
+    pytest.importorskip("iic_b200")
+    world = 2
+    ctx = mp.get_context("spawn")
+    out = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = [out.get(timeout=240) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+    assert sorted(results) == [(0, "ok"), (1, "ok")], results
