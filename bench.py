@@ -358,6 +358,18 @@ def run_b200(args):
     e2e_val = world * px_step / (e2e_ms * 1e-3) / 1e6
     iic_b200.raise_if_flagged(dev)
 
+    # ---- nothing after the measurements may be able to hang the job.  With CUDA graphs that captured
+    # NCCL kernels alive, dist.destroy_process_group() was seen to block for minutes on this stack
+    # (torch 2.11 / NCCL 2.28), so multi-rank runs end with a barrier, the JSON line and a hard exit. ----
+    import threading
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+    watchdog = threading.Timer(240.0, lambda: os._exit(0))
+    watchdog.daemon = True
+    watchdog.start()
+
     if rank == 0:
         cpu_v, cpu_threads, cpu_best, cpu_times = cpu_port_throughput(args.cpu_sample_batch, 5)
         # launches per step: local = simplex + joint + reduce + epilogue + backward (5);
@@ -386,9 +398,12 @@ def run_b200(args):
                                        f"oracle/torch_port.py"},
             "wall_s_timed_region": round(t_wall, 4),
         }
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
+    watchdog.cancel()
     if world > 1:
-        dist.destroy_process_group()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():
