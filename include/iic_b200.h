@@ -32,6 +32,9 @@ extern "C" {
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
 #define IIC_FLAG_NOT_SIMPLEX 2   /* dc2:utils/assertion.py:56-65 -> AssertionError on the host */
 
+/* return code of the *_from_logits entry points for shapes their fused kernels do not cover */
+#define IIC_UNSUPPORTED 3
+
 int iic_b200_abi_version(void);
 const char* iic_b200_last_error(void);
 /* number of SMs of `device` (148 on B200); <0 on error */
@@ -101,6 +104,26 @@ int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long
                        int patch_h, int patch_w, int step_h, int step_w,
                        const float* Wx, const float* Wy, const float* grad_loss,
                        float* gx, float* gy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cluster-head softmax fused into the local term.  lx, ly are the LOGITS of LocalClusterHead
+ * (contrastyou/trainer/_utils.py:137-168: 1x1 conv -> SoftmaxWithT, :15-23); the kernels apply
+ * softmax(logit * inv_temperature) over the K channels on the fly, so
+ *   iic_local_joint_from_logits(l1, l2)  ==  iic_local_joint(softmax(l1), softmax(l2))      (one patch, no mask)
+ * and the backward returns the gradients with respect to the logits.  Between the two calls the caller
+ * runs iic_local_epilogue exactly as for the probability path.  Covered shapes: padding 1, K == 10,
+ * W % 4 == 0, W <= 248, 16-byte aligned rows; anything else returns IIC_UNSUPPORTED (apply the softmax
+ * and use the probability entry points).  workspace: iic_b200_sm_count() * 9*K*K floats.
+ * ---------------------------------------------------------------------------------------------- */
+int iic_local_joint_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
+                                const float* ly, long long y_sn, long long y_sc, long long y_sh,
+                                int B, int K, int H, int W, int pad, float inv_temperature,
+                                double* J_out, void* workspace, size_t workspace_bytes, void* stream);
+int iic_local_backward_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
+                                   const float* ly, long long y_sn, long long y_sc, long long y_sh,
+                                   int B, int K, int H, int W, int pad, float inv_temperature,
+                                   const float* Wx, const float* Wy, const float* grad_loss,
+                                   float* g_lx, float* g_ly, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Global IIC on (N,K) simplex rows.  Replaces compute_joint (iic_loss.py:74-94) and IIDLoss.forward

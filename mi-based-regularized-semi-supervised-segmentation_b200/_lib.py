@@ -13,6 +13,7 @@ LIB_PATH = os.path.join(HERE, "libiic_b200.so")
 ABI_VERSION = 2
 FLAG_NAN_LOSS = 1
 FLAG_NOT_SIMPLEX = 2
+UNSUPPORTED = 3
 
 _p = C.c_void_p
 _ll = C.c_longlong
@@ -35,6 +36,10 @@ PROTOTYPES = {
     "iic_local_epilogue": (_i, [_p, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "iic_local_backward": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
                                 _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "iic_local_joint_from_logits": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, C.c_float,
+                                         _p, _p, _sz, _p]),
+    "iic_local_backward_from_logits": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, C.c_float,
+                                            _p, _p, _p, _p, _p, _p]),
     "iic_global_joint_workspace_bytes": (_sz, [_i, _ll, _i]),
     "iic_global_joint": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _sz, _p, _p]),
     "iic_global_epilogue": (_i, [_p, _i, _d, _i, _p, _p, _p, _p]),

@@ -206,7 +206,7 @@ int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long 
 int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                       cudaStream_t st);
+                       int from_logits, float inv_temp, cudaStream_t st);
 }
 using namespace iic;
 
@@ -233,7 +233,7 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
   if (n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
-                                      grad_loss, gx, gy, sms, st);
+                                      grad_loss, gx, gy, sms, 0, 1.f, st);
     if (rc < 0)
       rc = local_bwd_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                              gx, gy, sms, st);
@@ -284,4 +284,24 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
     if (rc) return rc;
   }
   return 0;
+}
+
+// Backward of iic_local_joint_from_logits: gradients with respect to the two logit maps
+extern "C" int iic_local_backward_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
+                                              const float* ly, long long y_sn, long long y_sc, long long y_sh,
+                                              int B, int K, int H, int W, int pad, float inv_temperature,
+                                              const float* Wx, const float* Wy, const float* grad_loss,
+                                              float* g_lx, float* g_ly, void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(lx && ly && Wx && Wy && g_lx && g_ly, "iic_local_backward_from_logits: null pointer");
+  const int sms = sm_count_cached(current_device());
+  IIC_REQUIRE(sms > 0, "iic_local_backward_from_logits: no device");
+  const int rc = local_bwd_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                    g_lx, g_ly, sms, 1, inv_temperature, st);
+  if (rc < 0) {
+    set_error("iic_local_backward_from_logits: shape not covered by the fused kernel (needs padding 1, K == 10, "
+              "W %% 4 == 0, W <= 248, 16-byte aligned rows)");
+    return IIC_UNSUPPORTED;
+  }
+  return rc;
 }

@@ -52,6 +52,10 @@ struct BwdFastParams {
   const float* grad_loss;
   float* gx;
   float* gy;
+  // FROM_LOGITS: the maps are logits; gx / gy receive the gradient with respect to the logits
+  const float* lx; long long lx_sn, lx_sc, lx_sh;
+  const float* ly; long long ly_sn, ly_sc, ly_sh;
+  float inv_temp;
 };
 
 // v = shared[addr] where pred != 0 (a predicated LDS: no divergent branch around a one-lane load)
@@ -66,7 +70,7 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
 
 // PXQ = pixel quads per thread (a thread owns one row x 4*PXQ pixels x 10 output channels); NWARPS consumer
 // warps + one producer warp.
-template <int K, int PXQ, int NWARPS, int STAGES, int CB>
+template <int K, int PXQ, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 __global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
 local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                       const BwdFastParams P) {
@@ -149,6 +153,29 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
       for (int cb = 0; cb < nchunk; ++cb, ++k) {
         const int s = k % STAGES;
         mbar_wait(&full_bar[s], (k / STAGES) & 1u);
+        if constexpr (FROM_LOGITS) {
+          // the staged tile holds logits: channel softmax in place (all K channels are in the stage, CB == K);
+          // rows and columns outside the map must stay zero (the conv's padding)
+          static_assert(!FROM_LOGITS || CB == K, "the fused softmax needs every channel of a pixel in one stage");
+          float* tile = reinterpret_cast<float*>(smem_raw + (size_t)s * P.stage_bytes);
+          const float k2 = P.inv_temp * 1.4426950408889634f;
+          const int npos = P.XR * P.XP;
+          for (int pos = threadIdx.x; pos < npos; pos += NWARPS * 32) {
+            const int tr = pos / P.XP, tc = pos - tr * P.XP;
+            const bool valid = (unsigned)(h0 - 1 + tr) < (unsigned)P.H && (unsigned)(tc - LP) < (unsigned)P.W;
+            float v[K];
+            float mx = -3.0e38f;
+#pragma unroll
+            for (int c = 0; c < K; ++c) { v[c] = tile[c * P.plane + pos]; mx = fmaxf(mx, v[c]); }
+            float sum = 0.f;
+#pragma unroll
+            for (int c = 0; c < K; ++c) { v[c] = exp2f((v[c] - mx) * k2); sum += v[c]; }
+            const float inv = valid ? 1.f / sum : 0.f;
+#pragma unroll
+            for (int c = 0; c < K; ++c) tile[c * P.plane + pos] = v[c] * inv;
+          }
+          asm volatile("bar.sync 1, %0;" ::"n"(NWARPS * 32) : "memory");     // consumers only
+        }
         if (warp_active) {
           uint32_t cp = smem_base + (uint32_t)s * P.stage_bytes + toff;
 #pragma unroll 1
@@ -190,7 +217,49 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           }
         }
         __syncwarp();
+        if constexpr (FROM_LOGITS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our writes vs the next TMA fill
         if (lane == 0) mbar_arrive(&empty_bar[s]);
+      }
+      if constexpr (FROM_LOGITS) {
+        // chain through the cluster head's softmax (contrastyou/trainer/_utils.py:15-23): the thread holds
+        // dL/dp for all K channels of its pixels, so  dL/dlogit = p * (dL/dp - sum_k dL/dp_k p_k) / T  is a
+        // per-thread epilogue; p is recomputed from the logits (one coalesced 16-byte load per channel)
+        if (active) {
+          const float* lg = sweep == 0 ? P.lx : P.ly;
+          const long long sn = sweep == 0 ? P.lx_sn : P.ly_sn, sc = sweep == 0 ? P.lx_sc : P.ly_sc,
+                          sh = sweep == 0 ? P.lx_sh : P.ly_sh;
+          const float* src = lg + (long long)n * sn + (long long)(h0 + rr) * sh + NPX * q;
+          const float k2 = P.inv_temp * 1.4426950408889634f;
+#pragma unroll
+          for (int v4 = 0; v4 < PXQ; ++v4) {
+            float4 l[K];
+#pragma unroll
+            for (int c = 0; c < K; ++c) l[c] = __ldg(reinterpret_cast<const float4*>(src + (long long)c * sc + 4 * v4));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float pv[K];
+              float mx = -3.0e38f;
+#pragma unroll
+              for (int c = 0; c < K; ++c) { pv[c] = (&l[c].x)[e]; mx = fmaxf(mx, pv[c]); }
+              float sum = 0.f;
+#pragma unroll
+              for (int c = 0; c < K; ++c) { pv[c] = exp2f((pv[c] - mx) * k2); sum += pv[c]; }
+              const float inv = 1.f / sum;
+              float dot = 0.f;
+#pragma unroll
+              for (int c = 0; c < K; ++c) {
+                pv[c] *= inv;
+                const float gc = (c & 1) ? acc[c / 2][4 * v4 + e].y : acc[c / 2][4 * v4 + e].x;
+                dot = fmaf(gc, pv[c], dot);
+              }
+#pragma unroll
+              for (int c = 0; c < K; ++c) {
+                float& gc = (c & 1) ? acc[c / 2][4 * v4 + e].y : acc[c / 2][4 * v4 + e].x;
+                gc = pv[c] * (gc - dot) * P.inv_temp;
+              }
+            }
+          }
+        }
       }
       if (active) {
         float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + NPX * q;
@@ -210,10 +279,10 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   }
 }
 
-template <int K, int PXQ, int NWARPS, int STAGES, int CB>
+template <int K, int PXQ, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const BwdFastParams& P, dim3 grid,
                            size_t smem, cudaStream_t st) {
-  auto kern = local_bwd_fast_kernel<K, PXQ, NWARPS, STAGES, CB>;
+  auto kern = local_bwd_fast_kernel<K, PXQ, NWARPS, STAGES, CB, FROM_LOGITS>;
   static bool attr_set = false;
   if (!attr_set) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -228,17 +297,19 @@ static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const B
 int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                       cudaStream_t st) {
+                       int from_logits, float inv_temp, cudaStream_t st) {
   using namespace bwdfast;
   if (pad != 1 || (K != 10 && K != 20)) return -1;
+  if (from_logits && K != 10) return -1;
   if (W % 4 != 0 || W > 248 || W < 4) return -1;
   if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
   // launch shape: 0 = 16 consumer warps x 4 stages, 1 = 24 consumer warps x 3 stages
   int cfg = 0;
   if (const char* e = getenv("IIC_B200_BWD_CFG")) cfg = atoi(e);
   if (cfg < 0 || cfg > 1) cfg = 0;
-  const int pxq = 1, CB = 5;
-  const int nthreads = cfg == 0 ? 512 : 768, stages = cfg == 0 ? 4 : 3;
+  if (from_logits) cfg = 0;
+  const int pxq = 1, CB = from_logits ? 10 : 5;    // the fused softmax needs all K channels in one stage
+  const int nthreads = cfg == 0 ? 512 : 768, stages = from_logits ? 2 : cfg == 0 ? 4 : 3;
   BwdFastParams P;
   P.B = B; P.K = K; P.Kp = (K + 3) & ~3; P.H = H; P.W = W;
   P.QW = W / (4 * pxq);
@@ -254,6 +325,12 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   const size_t smem = (size_t)P.stage_bytes * stages;
   if (smem > 226 * 1024) return -1;
   P.Wx = Wx; P.Wy = Wy; P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
+  P.lx = x; P.lx_sn = x_sn; P.lx_sc = x_sc; P.lx_sh = x_sh;
+  P.ly = y; P.ly_sn = y_sn; P.ly_sc = y_sc; P.ly_sh = y_sh;
+  P.inv_temp = inv_temp;
+  if (from_logits && ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) ||
+                      (x_sh % 4) || (x_sc % 4) || (x_sn % 4) || (y_sh % 4) || (y_sc % 4) || (y_sn % 4)))
+    return -1;
   CUtensorMap mx, my;
   if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, P.XP, P.XR, CB)) return -1;
   if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, P.XP, P.XR, CB)) return -1;
@@ -277,9 +354,10 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   }
 #define IIC_BWD_LAUNCH(KK)                                                              \
   switch (cfg) {                                                                        \
-    case 1: return launch_bwd_fast<KK, 1, 24, 3, 5>(mx, my, P, grid, smem, st);         \
-    default: return launch_bwd_fast<KK, 1, 16, 4, 5>(mx, my, P, grid, smem, st);        \
+    case 1: return launch_bwd_fast<KK, 1, 24, 3, 5, false>(mx, my, P, grid, smem, st);  \
+    default: return launch_bwd_fast<KK, 1, 16, 4, 5, false>(mx, my, P, grid, smem, st); \
   }
+  if (from_logits) return launch_bwd_fast<10, 1, 16, 2, 10, true>(mx, my, P, grid, smem, st);
   if (K == 10) { IIC_BWD_LAUNCH(10) }
   IIC_BWD_LAUNCH(20)
 #undef IIC_BWD_LAUNCH

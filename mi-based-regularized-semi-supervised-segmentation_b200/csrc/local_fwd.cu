@@ -371,7 +371,8 @@ int local_joint_tma_try(const float* x, long long x_sn, long long x_sc, long lon
                         float* partial, int max_ctas, int* ncta, cudaStream_t st);
 int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, cudaStream_t st);
+                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, int from_logits,
+                         float inv_temp, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -409,7 +410,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
     int ncta = 0, checked = 0;
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
-                                        (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, st);
+                                        (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, 0, 1.f, st);
     if (rc == 0 && checked) flags = nullptr;       // done inside the joint kernel
     if (rc < 0)
       rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
@@ -479,5 +480,36 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
                                                              (long long)E, J_out);
     IIC_CHECK_CUDA(cudaGetLastError());
   }
+  return 0;
+}
+
+// Fused cluster-head softmax + local joint: only the shapes the fast kernel covers
+extern "C" int iic_local_joint_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
+                                           const float* ly, long long y_sn, long long y_sc, long long y_sh,
+                                           int B, int K, int H, int W, int pad, float inv_temperature,
+                                           double* J_out, void* workspace, size_t workspace_bytes,
+                                           void* stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  IIC_REQUIRE(lx && ly && J_out && workspace, "iic_local_joint_from_logits: null pointer");
+  IIC_REQUIRE(B > 0 && K > 0 && H > 0 && W > 0, "iic_local_joint_from_logits: empty input");
+  const int device = current_device();
+  const int sms = sm_count_cached(device);
+  IIC_REQUIRE(sms > 0, "iic_local_joint_from_logits: no device");
+  const size_t E = (size_t)9 * K * K;
+  IIC_REQUIRE(workspace_bytes >= (size_t)sms * E * sizeof(float),
+              "iic_local_joint_from_logits: workspace too small (%zu < %zu)", workspace_bytes,
+              (size_t)sms * E * sizeof(float));
+  int ncta = 0, checked = 0;
+  const int rc = local_joint_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad,
+                                      (float*)workspace, sms, &ncta, nullptr, &checked, 1, inv_temperature, st);
+  if (rc < 0) {
+    set_error("iic_local_joint_from_logits: shape not covered by the fused kernel (needs padding 1, K == 10, "
+              "W %% 4 == 0, 16-byte aligned rows); apply the softmax and call iic_local_joint");
+    return IIC_UNSUPPORTED;
+  }
+  if (rc > 0) return rc;
+  dim3 rgrid((unsigned)((E + 31) / 32), 1);
+  reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+  IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -43,6 +43,7 @@ struct FwdFastParams {
   int B, K, H, W, tiles_h, tiles_w;
   float* partial;           // [gridDim.x][9][K][K]
   int* flags;               // non-null (and K == 10): also assert that x is a simplex over its channels
+  float inv_temp;           // FROM_LOGITS: softmax(logit * inv_temp)  (SoftmaxWithT, contrastyou/trainer/_utils.py:15-23)
 };
 
 // rows [0, NROWS) of a job; xa/xb point at (window row 0, dx 0) of the job's two x channels for this
@@ -89,6 +90,10 @@ __device__ __forceinline__ void sweep_rows(const float* __restrict__ xa, const f
   if constexpr (NROWS % 3 == 2) row(1, 0, xa, xb, y0);
 }
 
+// FROM_LOGITS: the maps hold the cluster head's logits; the channel softmax of LocalClusterHead
+// (contrastyou/trainer/_utils.py:137-168) is applied to every staged tile in shared memory, in place,
+// before the sweeps, so the probability maps never exist in HBM.  Needs all K channels in the tile (K == 10).
+template <bool FROM_LOGITS>
 __global__ void __launch_bounds__(fwdfast::NTHREADS, 1)
 local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                         const FwdFastParams P) {
@@ -156,6 +161,40 @@ local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_c
       }
       __syncwarp();
       mbar_wait(&full_bar[s], use & 1u);
+      if constexpr (FROM_LOGITS) {
+        // in-place channel softmax of the staged x tile (with halo) and y tile; positions outside the map
+        // must stay zero (they are the conv's padding), so they are masked rather than normalised
+        const int n = it / (P.tiles_h * P.tiles_w);
+        const int tt = it - n * (P.tiles_h * P.tiles_w);
+        const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
+        float* xt = reinterpret_cast<float*>(smem_raw + (size_t)s * STAGE_BYTES);
+        float* yt = reinterpret_cast<float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION);
+        const float sc = P.inv_temp * 1.4426950408889634f;
+        for (int pos = threadIdx.x; pos < XR * XP + TH * TW; pos += NTHREADS) {
+          float* base; int plane; bool valid;
+          if (pos < XR * XP) {
+            const int r = pos / XP, c = pos - r * XP;
+            base = xt + pos; plane = XPLANE;
+            valid = (unsigned)(th0 - PAD + r) < (unsigned)P.H && (unsigned)(tw0 - LP + c) < (unsigned)P.W;
+          } else {
+            const int q = pos - XR * XP;
+            const int r = q / TW, c = q - r * TW;
+            base = yt + q; plane = YPLANE;
+            valid = (th0 + r) < P.H && (tw0 + c) < P.W;
+          }
+          float v[KB];
+          float mx = -3.0e38f;
+#pragma unroll
+          for (int ch = 0; ch < KB; ++ch) { v[ch] = base[ch * plane]; mx = fmaxf(mx, v[ch]); }
+          float sum = 0.f;
+#pragma unroll
+          for (int ch = 0; ch < KB; ++ch) { v[ch] = exp2f((v[ch] - mx) * sc); sum += v[ch]; }
+          const float inv = valid ? 1.f / sum : 0.f;
+#pragma unroll
+          for (int ch = 0; ch < KB; ++ch) base[ch * plane] = v[ch] * inv;
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");      // every warp sweeps the whole tile
+      }
       const float* xs = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES) + xoff;
       const float* ys = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION) + yoff;
       if (split) sweep_rows<TH / 2>(xs, xs + XPLANE, ys, acc);
@@ -181,6 +220,7 @@ local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_c
         if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
       }
       __syncwarp();
+      if constexpr (FROM_LOGITS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our writes vs the next TMA fill
       if (lane == 0) mbar_arrive(&empty_bar[s]);
     }
 
@@ -219,16 +259,19 @@ local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_c
 // *checked = 1 when `flags` was given and the simplex assertion on x ran inside the kernel.
 int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, cudaStream_t st) {
+                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, int from_logits,
+                         float inv_temp, cudaStream_t st) {
   using namespace fwdfast;
   if (pad != PAD || K < KB || K % KB != 0 || K > 40) return -1;
+  if (from_logits && K != KB) return -1;
   if (W % 4 != 0) return -1;
   CUtensorMap mx, my;
   if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, XP, XR, KB)) return -1;
   if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, TW, TH, KB)) return -1;
   FwdFastParams P;
   P.B = B; P.K = K; P.H = H; P.W = W;
-  P.flags = (K == KB) ? flags : nullptr;
+  P.flags = (K == KB && !from_logits) ? flags : nullptr;
+  P.inv_temp = inv_temp;
   *checked = P.flags != nullptr;
   P.tiles_h = (H + TH - 1) / TH;
   P.tiles_w = (W + TW - 1) / TW;
@@ -241,11 +284,16 @@ int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long lo
   *ncta = gx;
   static bool attr_set = false;
   if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(STAGES * STAGE_BYTES)));
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(STAGES * STAGE_BYTES)));
     attr_set = true;
   }
-  local_joint_fast_kernel<<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
+  if (from_logits)
+    local_joint_fast_kernel<true><<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
+  else
+    local_joint_fast_kernel<false><<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

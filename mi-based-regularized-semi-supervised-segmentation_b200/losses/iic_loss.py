@@ -21,7 +21,8 @@ import torch
 from torch import Tensor, nn
 
 from .. import checks
-from ..ops import GlobalIICFunction, JointFunction, LocalIICFunction
+from ..ops import (FusedShapeUnsupported, GlobalIICFunction, JointFunction, LocalIICFunction,
+                   LocalIICLogitsFunction)
 
 
 def _pair(x):
@@ -118,3 +119,25 @@ class IIDSegmentationSmallPathLoss(IIDSegmentationLoss):
 
     def __repr__(self):
         return f"{self.__class__.__name__} with patch_size={self._patch_size} and padding={self.padding}."
+
+    def from_logits(self, logits_out: Tensor, logits_tf_out: Tensor, T: float = 1.0) -> Tensor:
+        """``self(softmax(logits_out / T, 1), softmax(logits_tf_out / T, 1))`` with both softmaxes -- the
+        ``SoftmaxWithT`` at the end of ``LocalClusterHead`` (contrastyou/trainer/_utils.py:15-23,137-168) --
+        fused into the joint kernel and their backward into the gradient kernel, so the probability maps are
+        never written to memory.  The gradient is returned with respect to the logits.
+
+        The fused kernels cover the udaiic decoder shapes (padding 1, 10 clusters, one patch, width a multiple
+        of 4 and at most 248); any other shape applies the softmax first and takes the probability path."""
+        assert logits_out.shape == logits_tf_out.shape, (logits_out.shape, logits_tf_out.shape)
+        assert logits_out.requires_grad and logits_tf_out.requires_grad        # :110
+        h, w = logits_out.shape[2], logits_out.shape[3]
+        one_patch = self._patch_size[0] >= h and self._patch_size[1] >= w
+        if one_patch and logits_out.is_cuda:
+            try:
+                loss = LocalIICLogitsFunction.apply(logits_out, logits_tf_out, int(self.padding), float(self.lamda),
+                                                    1.0 / float(T))
+                checks.finish(logits_out.device, loss)
+                return loss
+            except FusedShapeUnsupported:
+                pass
+        return self((logits_out / T).softmax(1), (logits_tf_out / T).softmax(1))

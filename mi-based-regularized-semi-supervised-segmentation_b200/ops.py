@@ -20,6 +20,9 @@ _LIBDEF.define("local_joint(Tensor x, Tensor y, Tensor? mask, int pad, int patch
 _LIBDEF.define("local_epilogue(Tensor J, int K, int pad, float lamda) -> (Tensor, Tensor, Tensor)")
 _LIBDEF.define("local_backward(Tensor x, Tensor y, Tensor? mask, Tensor Wx, Tensor Wy, Tensor grad, int pad, "
                "int patch_h, int patch_w, int step_h, int step_w) -> (Tensor, Tensor)")
+_LIBDEF.define("local_joint_logits(Tensor lx, Tensor ly, int pad, float inv_temperature) -> Tensor")
+_LIBDEF.define("local_backward_logits(Tensor lx, Tensor ly, Tensor Wx, Tensor Wy, Tensor grad, int pad, "
+               "float inv_temperature) -> (Tensor, Tensor)")
 _LIBDEF.define("global_joint(Tensor x, Tensor y, bool check_simplex=False) -> Tensor")
 _LIBDEF.define("global_epilogue(Tensor J, float lamb, bool symmetric, bool want_losses) -> (Tensor, Tensor)")
 _LIBDEF.define("global_backward(Tensor x, Tensor y, Tensor J, float lamb, bool symmetric, Tensor? g_loss, "
@@ -175,6 +178,54 @@ def _local_backward(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, ste
     return gx, gy
 
 
+class FusedShapeUnsupported(RuntimeError):
+    """The fused from-logits kernels do not cover this shape; apply the softmax and use the probability path."""
+
+
+def _logit_maps(lx, ly):
+    _require_cuda_f32("logits_out", lx)
+    _require_cuda_f32("logits_tf_out", ly)
+    if lx.dim() != 4 or lx.shape != ly.shape:
+        raise ValueError(f"iic_b200.local_joint_logits: shapes {tuple(lx.shape)} vs {tuple(ly.shape)}")
+    return _w_contig(lx), _w_contig(ly)
+
+
+def _local_joint_logits(lx, ly, pad, inv_temperature):
+    lib = _lib.load()
+    lx, ly = _logit_maps(lx, ly)
+    B, K, H, W = lx.shape
+    nbytes = lib.iic_b200_sm_count(lx.device.index or 0) * 9 * K * K * 4
+    ws = torch.empty(max(nbytes, 4), dtype=torch.uint8, device=lx.device)
+    J = torch.empty((1, 3, 3, K, K), dtype=torch.float64, device=lx.device)
+    with torch.cuda.device(lx.device):
+        rc = lib.iic_local_joint_from_logits(lx.data_ptr(), lx.stride(0), lx.stride(1), lx.stride(2),
+                                             ly.data_ptr(), ly.stride(0), ly.stride(1), ly.stride(2),
+                                             B, K, H, W, pad, float(inv_temperature), J.data_ptr(), ws.data_ptr(),
+                                             ws.numel(), _stream(lx.device))
+    if rc == _lib.UNSUPPORTED:
+        raise FusedShapeUnsupported(lib.iic_b200_last_error().decode())
+    _lib.check(rc, "iic_local_joint_from_logits")
+    return J
+
+
+def _local_backward_logits(lx, ly, Wx, Wy, grad, pad, inv_temperature):
+    lib = _lib.load()
+    lx, ly = _logit_maps(lx, ly)
+    B, K, H, W = lx.shape
+    gx = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
+    gy = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
+    grad = grad.to(torch.float32).reshape(())
+    with torch.cuda.device(lx.device):
+        rc = lib.iic_local_backward_from_logits(lx.data_ptr(), lx.stride(0), lx.stride(1), lx.stride(2),
+                                                ly.data_ptr(), ly.stride(0), ly.stride(1), ly.stride(2),
+                                                B, K, H, W, pad, float(inv_temperature), Wx.data_ptr(), Wy.data_ptr(),
+                                                grad.data_ptr(), gx.data_ptr(), gy.data_ptr(), _stream(lx.device))
+    if rc == _lib.UNSUPPORTED:
+        raise FusedShapeUnsupported(lib.iic_b200_last_error().decode())
+    _lib.check(rc, "iic_local_backward_from_logits")
+    return gx, gy
+
+
 def _global_joint(x, y, check_simplex=False):
     lib = _lib.load()
     _require_cuda_f32("x_out", x)
@@ -290,6 +341,8 @@ _LIBIMPL = torch.library.Library("iic_b200", "IMPL", "CUDA")
 _LIBIMPL.impl("local_joint", _local_joint)
 _LIBIMPL.impl("local_epilogue", _local_epilogue)
 _LIBIMPL.impl("local_backward", _local_backward)
+_LIBIMPL.impl("local_joint_logits", _local_joint_logits)
+_LIBIMPL.impl("local_backward_logits", _local_backward_logits)
 _LIBIMPL.impl("global_joint", _global_joint)
 _LIBIMPL.impl("global_epilogue", _global_epilogue)
 _LIBIMPL.impl("global_backward", _global_backward)
@@ -307,7 +360,7 @@ def _cpu_refusal(name):
 
 
 _LIBCPU = torch.library.Library("iic_b200", "IMPL", "CPU")
-for _n in ("local_joint", "local_epilogue", "local_backward", "global_joint", "global_epilogue",
+for _n in ("local_joint", "local_epilogue", "local_backward", "local_joint_logits", "local_backward_logits", "global_joint", "global_epilogue",
            "global_backward", "uda_forward", "uda_backward", "simplex_check"):
     _LIBCPU.impl(_n, _cpu_refusal(_n))
 
@@ -354,6 +407,27 @@ class LocalIICFunction(torch.autograd.Function):
         x, y, mask, Wx, Wy = ctx.saved_tensors
         gx, gy = ops.local_backward(x, y, mask, Wx, Wy, grad.contiguous(), *ctx.geom)
         return gx, gy, None, None, None, None, None, None, None, None
+
+
+class LocalIICLogitsFunction(torch.autograd.Function):
+    """LocalIICFunction applied to softmax(logits / T, dim=1) of both maps, with the softmax and its
+    backward fused into the joint and gradient kernels (contrastyou/trainer/_utils.py:15-23,137-168 feeding
+    iic_loss.py:107-149); one patch = the whole map.  Raises FusedShapeUnsupported for other shapes."""
+
+    @staticmethod
+    def forward(ctx, lx, ly, pad, lamda, inv_temperature):
+        J = ops.local_joint_logits(lx, ly, pad, inv_temperature)
+        J = _maybe_allreduce(J)
+        loss, Wx, Wy = ops.local_epilogue(J, lx.shape[1], pad, lamda)
+        ctx.save_for_backward(lx, ly, Wx, Wy)
+        ctx.cfg = (pad, inv_temperature)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        lx, ly, Wx, Wy = ctx.saved_tensors
+        gx, gy = ops.local_backward_logits(lx, ly, Wx, Wy, grad.contiguous(), *ctx.cfg)
+        return gx, gy, None, None, None
 
 
 class GlobalIICFunction(torch.autograd.Function):

@@ -155,6 +155,61 @@ def test_joint_kernel_vs_oracle(iic, cuda_device, B, K, H, W, pad):
     assert relmax(J[0].cpu().numpy(), ref) < 2e-6
 
 
+def _logit_views(rng, B, K, H, W):
+    base = rng.standard_normal((B, K, max(H // 4, 1), max(W // 4, 1))).repeat(4, axis=2).repeat(4, axis=3)[:, :, :H, :W] * 3
+    if base.shape[2] < H or base.shape[3] < W:
+        base = np.pad(base, ((0, 0), (0, 0), (0, H - base.shape[2]), (0, W - base.shape[3])), mode="edge")
+    l1 = (base + 0.5 * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    l2 = (base + 0.5 * rng.standard_normal((B, K, H, W))).astype(np.float32)
+    return l1, l2
+
+
+@pytest.mark.parametrize("B,K,H,W,pad,T", [
+    (2, 10, 64, 96, 1, 1.0),      # fused kernels (the udaiic decoder shape family)
+    (2, 10, 224, 224, 1, 1.0),    # ACDC Up_conv2 shape, reduced batch
+    (3, 10, 37, 44, 1, 0.7),      # ragged rows, temperature
+    (2, 10, 40, 42, 1, 1.0),      # W % 4 != 0 -> softmax + probability path
+    (2, 6, 32, 32, 2, 1.0),       # other K / padding -> softmax + probability path
+])
+def test_local_from_logits_vs_oracle(iic, cuda_device, B, K, H, W, pad, T):
+    """Cluster-head softmax (contrastyou/trainer/_utils.py:15-23) fused into the local loss: loss and the
+    gradients with respect to the LOGITS against the fp64 oracle chained through its own softmax."""
+    rng = np.random.default_rng(4321 + H + W + K)
+    l1, l2 = _logit_views(rng, B, K, H, W)
+    a = torch.from_numpy(l1).to(cuda_device).requires_grad_(True)
+    b = torch.from_numpy(l2).to(cuda_device).requires_grad_(True)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=pad, patch_size=512)
+    loss = crit.from_logits(a, b, T=T)
+    up = 0.37
+    (up * loss).backward()
+    p1, p2 = O.softmax(l1, 1, T), O.softmax(l2, 1, T)
+    ol, gp1, gp2 = O.iid_segmentation_small_path_loss(p1, p2, pad, 512, with_grads=True)
+    gl1 = up * O.softmax_backward(p1, gp1, 1, T)
+    gl2 = up * O.softmax_backward(p2, gp2, 1, T)
+    ex, ey = relmax(a.grad.cpu().numpy(), gl1), relmax(b.grad.cpu().numpy(), gl2)
+    print(f"loss err {abs(loss.item()-ol)/abs(ol):.2e}, grad err {max(ex, ey):.2e}")
+    assert _loss_close(loss.item(), ol), (loss.item(), ol)
+    assert ex <= GRAD_RTOL and ey <= GRAD_RTOL, (ex, ey)
+
+
+def test_local_from_logits_matches_probability_path(iic, cuda_device):
+    """Same inputs through softmax + the probability kernels and through the fused kernels."""
+    rng = np.random.default_rng(77)
+    l1, l2 = _logit_views(rng, 4, 10, 48, 64)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=512)
+    a = torch.from_numpy(l1).to(cuda_device).requires_grad_(True)
+    b = torch.from_numpy(l2).to(cuda_device).requires_grad_(True)
+    lf = crit.from_logits(a, b)
+    lf.backward()
+    c = torch.from_numpy(l1).to(cuda_device).requires_grad_(True)
+    d = torch.from_numpy(l2).to(cuda_device).requires_grad_(True)
+    lp = crit(c.softmax(1), d.softmax(1))
+    lp.backward()
+    assert abs(lf.item() - lp.item()) <= 2e-6 * abs(lp.item())
+    assert relmax(a.grad.cpu().numpy(), c.grad.cpu().numpy()) <= 2e-5
+    assert relmax(b.grad.cpu().numpy(), d.grad.cpu().numpy()) <= 2e-5
+
+
 def test_local_mask_and_lambda(iic, cuda_device):
     rng = np.random.default_rng(5)
     x, y = views(rng, 2, 6, 40, 44)
