@@ -323,6 +323,59 @@ def run_b200(args):
                                       "local_backward": round(t_bwd, 4)},
                 "whole_step_hbm_frac": round(24.0 * K * B * H * W / (ms_step * 1e-3) / 1e9 / hbm_peak, 4)}
 
+    # ---- secondary lines (not the headline): the softmax-fused variant and the UDA term ----
+    def timed_graph(fn, reps=20):
+        side2 = torch.cuda.Stream(device=dev)
+        side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side2):
+            for _ in range(2):
+                fn()
+        torch.cuda.current_stream().wait_stream(side2)
+        torch.cuda.synchronize()
+        g_ = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_, stream=side2):
+            fn()
+        for _ in range(3):
+            g_.replay()
+        torch.cuda.synchronize()
+        t0, t1 = ev(), ev()
+        t0.record()
+        for _ in range(reps):
+            g_.replay()
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / reps
+        del g_
+        return ms
+
+    extra = {}
+    try:
+        gl = torch.Generator(device=dev).manual_seed(99 + rank)
+        lbase = torch.nn.functional.interpolate(torch.randn(B, K, H // 8, W // 8, device=dev, generator=gl) * 3,
+                                                size=(H, W), mode="bilinear", align_corners=False)
+        l1 = (lbase + 0.5 * torch.randn(B, K, H, W, device=dev, generator=gl)).requires_grad_(True)
+        l2 = (lbase + 0.5 * torch.randn(B, K, H, W, device=dev, generator=gl)).requires_grad_(True)
+        ms_fused = timed_graph(lambda: torch.autograd.grad(local.from_logits(l1, l2), (l1, l2)))
+        ms_unfused = timed_graph(lambda: torch.autograd.grad(local(l1.softmax(1), l2.softmax(1)), (l1, l2)))
+        extra["local_from_logits"] = {
+            "what": "local IIC fwd+bwd from the cluster head's LOGITS (softmax fused into the kernels) vs "
+                    "torch softmax + the probability kernels + torch softmax backward, same shape",
+            "fused_ms": round(ms_fused, 4), "torch_softmax_plus_probs_ms": round(ms_unfused, 4),
+            "fused_mpx_s": round(B * H * W / (ms_fused * 1e-3) / 1e6, 1)}
+        # UDA (semi_seg/epocher.py:221-224): (B,4,H,W) logits both ways, MSE, fused softmax, fwd+bwd
+        C_ = 4
+        u1 = (torch.randn(B, C_, H, W, device=dev, generator=gl) * 2).requires_grad_(True)
+        u2 = torch.randn(B, C_, H, W, device=dev, generator=gl) * 2
+        ms_uda = timed_graph(lambda: torch.autograd.grad(iic_b200.uda_from_logits(u1, u2, "mse"), (u1,)))
+        uda_bytes = 20.0 * C_ * B * H * W
+        extra["uda_mse_from_logits"] = {
+            "what": "UDA consistency fwd+bwd, (B,4,H,W), softmax fused; algorithmic bytes 20*C per pixel",
+            "ms": round(ms_uda, 4), "gb_s": round(uda_bytes / (ms_uda * 1e-3) / 1e9, 1),
+            "hbm_frac": round(uda_bytes / (ms_uda * 1e-3) / 1e9 / hbm_peak, 4),
+            "note": "32 MB working set: L2-resident between replays, so this is an upper bound on HBM efficiency"}
+    except Exception as e:  # noqa: BLE001
+        extra["error"] = f"{type(e).__name__}: {e}"
+
     # ---- end to end through the public API with HOST buffers ----
     hx, hy, hgx, hgy = (t.detach().cpu().pin_memory() for t in sets[0])
     dx, dy = torch.empty_like(hx, device=dev), torch.empty_like(hy, device=dev)
@@ -397,6 +450,7 @@ def run_b200(args):
                              "sample": f"config-2 shape at batch {args.cpu_sample_batch} (of 32), fwd+bwd, best of 5, "
                                        f"oracle/torch_port.py"},
             "wall_s_timed_region": round(t_wall, 4),
+            "extra": extra,
         }
         print(json.dumps(line), flush=True)
     watchdog.cancel()

@@ -182,6 +182,142 @@ __global__ void __launch_bounds__(256) uda_bwd_kernel(const float* __restrict__ 
   }
 }
 
+
+// ---- vectorised UDA path: 4 consecutive pixels per thread, 16-byte loads/stores --------------------------
+// (inner % 4 == 0, 16-byte aligned bases, outer*inner/4 < 2^31).  The maps are streamed exactly once per
+// pass: forward reads 2*C floats per pixel, backward reads 2*C and writes C.
+template <bool FROM_LOGITS, int C>
+__device__ __forceinline__ void load_quad(const float* __restrict__ src, long long inner, float (&v)[C][4]) {
+#pragma unroll
+  for (int c = 0; c < C; ++c) {
+    const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)c * inner));
+    v[c][0] = t.x; v[c][1] = t.y; v[c][2] = t.z; v[c][3] = t.w;
+  }
+  if (FROM_LOGITS) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float mx = v[0][e];
+#pragma unroll
+      for (int c = 1; c < C; ++c) mx = fmaxf(mx, v[c][e]);
+      float s = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) { v[c][e] = __expf(v[c][e] - mx); s += v[c][e]; }
+      const float inv = 1.f / s;
+#pragma unroll
+      for (int c = 0; c < C; ++c) v[c][e] *= inv;
+    }
+  }
+}
+
+template <bool FROM_LOGITS, int C>
+__global__ void __launch_bounds__(256) uda_fwd_vec_kernel(const float* __restrict__ prob,
+                                                          const float* __restrict__ target, unsigned nquads,
+                                                          unsigned inner4, int kind, float eps,
+                                                          const float* __restrict__ weight, double denom,
+                                                          float* __restrict__ loss_out, int* __restrict__ flags,
+                                                          int check_simplex, UdaWorkspace* ws) {
+  __shared__ double scratch[40];
+  __shared__ bool is_last;
+  double* partial = reinterpret_cast<double*>(ws + 1);
+  const long long inner = 4ll * inner4;
+  float w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = weight ? __ldg(weight + c) : 1.f;
+  float local = 0.f;
+  bool bad = false;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nquads; idx += gridDim.x * blockDim.x) {
+    const unsigned o = idx / inner4, q = idx - o * inner4;
+    const long long base = (long long)o * C * inner + 4ll * q;
+    float p[C][4], t[C][4];
+    load_quad<FROM_LOGITS, C>(prob + base, inner, p);
+    load_quad<FROM_LOGITS, C>(target + base, inner, t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float sp = 0.f, st = 0.f, v = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        sp += p[c][e]; st += t[c][e];
+        if (kind == 0) { const float d = p[c][e] - t[c][e]; v = fmaf(d, d, v); }
+        else v += -t[c][e] * logf((p[c][e] + eps) / (t[c][e] + eps)) * w[c];
+      }
+      if (check_simplex && !FROM_LOGITS) {
+        if (!(fabsf(sp - 1.f) <= 2e-4f) || !(fabsf(st - 1.f) <= 2e-4f)) bad = true;
+      }
+      local += v;
+    }
+  }
+  if (check_simplex && __any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0)
+    atomicOr(flags, IIC_FLAG_NOT_SIMPLEX);
+  const double bsum = block_sum((double)local, scratch);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = bsum;
+    __threadfence();
+    is_last = (atomicAdd(&ws->ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (is_last) {
+    // the last CTA adds the per-CTA sums: thread t takes partial[t], partial[t+256], ... in order, then a
+    // fixed-shape block reduction -> deterministic
+    __threadfence();
+    const volatile double* pp = partial;
+    double tsum = 0.0;
+    for (unsigned int b = threadIdx.x; b < gridDim.x; b += blockDim.x) tsum += pp[b];
+    double tot = block_sum(tsum, scratch);
+    if (threadIdx.x == 0) {
+      tot /= denom;
+      loss_out[0] = (float)tot;
+      if (tot != tot) atomicOr(flags, IIC_FLAG_NAN_LOSS);
+      ws->ticket = 0;
+    }
+  }
+}
+
+template <bool FROM_LOGITS, int C>
+__global__ void __launch_bounds__(256) uda_bwd_vec_kernel(const float* __restrict__ prob,
+                                                          const float* __restrict__ target, unsigned nquads,
+                                                          unsigned inner4, int kind, float eps,
+                                                          const float* __restrict__ weight, float inv_denom,
+                                                          const float* __restrict__ grad_loss,
+                                                          float* __restrict__ grad_prob) {
+  const long long inner = 4ll * inner4;
+  const float g = (grad_loss ? __ldg(grad_loss) : 1.f) * inv_denom;
+  float w[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) w[c] = weight ? __ldg(weight + c) : 1.f;
+  for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < nquads; idx += gridDim.x * blockDim.x) {
+    const unsigned o = idx / inner4, q = idx - o * inner4;
+    const long long base = (long long)o * C * inner + 4ll * q;
+    float p[C][4], t[C][4];
+    load_quad<FROM_LOGITS, C>(prob + base, inner, p);
+    load_quad<FROM_LOGITS, C>(target + base, inner, t);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      float dot = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float gp = (kind == 0) ? 2.f * (p[c][e] - t[c][e]) * g : -t[c][e] / (p[c][e] + eps) * w[c] * g;
+        dot = fmaf(gp, p[c][e], dot);
+        t[c][e] = gp;                      // reuse as the gradient w.r.t. the probabilities
+      }
+      if (FROM_LOGITS) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) t[c][e] = p[c][e] * (t[c][e] - dot);   // softmax adjoint
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+      *reinterpret_cast<float4*>(grad_prob + base + (long long)c * inner) =
+          make_float4(t[c][0], t[c][1], t[c][2], t[c][3]);
+  }
+}
+
+static bool uda_vec_ok(const void* a, const void* b, const void* c, long long outer, int C, long long inner) {
+  if (C < 2 || C > 4) return false;
+  if (inner % 4 != 0) return false;
+  if ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) return false;
+  return outer * (inner / 4) < (1ll << 31);
+}
+
 static int uda_grid(long long total) {
   int sms = sm_count_cached(current_device());
   if (sms <= 0) sms = 148;
@@ -229,6 +365,18 @@ extern "C" int iic_uda_forward(const float* prob, const float* target, long long
   // MSELoss: mean over all elements; KL_div "mean": mean over outer*inner after the channel sum
   const double denom = kind == 0 ? (double)total * C : (double)total;
   cudaStream_t st = (cudaStream_t)stream;
+  if (uda_vec_ok(prob, target, prob, outer, C, inner)) {
+    const unsigned nquads = (unsigned)(total / 4), inner4 = (unsigned)(inner / 4);
+    const int vgrid = uda_grid(total / 4);
+#define IIC_UDA_FWD(FL, CC)                                                                                   \
+    uda_fwd_vec_kernel<FL, CC><<<vgrid, 256, 0, st>>>(prob, target, nquads, inner4, kind, (float)eps, weight, \
+                                                      denom, loss_out, flags, check_simplex, (UdaWorkspace*)workspace)
+    if (from_logits) { if (C == 2) IIC_UDA_FWD(true, 2); else if (C == 3) IIC_UDA_FWD(true, 3); else IIC_UDA_FWD(true, 4); }
+    else             { if (C == 2) IIC_UDA_FWD(false, 2); else if (C == 3) IIC_UDA_FWD(false, 3); else IIC_UDA_FWD(false, 4); }
+#undef IIC_UDA_FWD
+    IIC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (from_logits)
     uda_fwd_kernel<true><<<grid, 256, 0, st>>>(prob, target, outer, C, inner, kind, (float)eps, weight, denom,
                                                loss_out, flags, check_simplex, (UdaWorkspace*)workspace);
@@ -250,6 +398,18 @@ extern "C" int iic_uda_backward(const float* prob, const float* target, long lon
   const int grid = uda_grid(total);
   const float inv_denom = (float)(1.0 / (kind == 0 ? (double)total * C : (double)total));
   cudaStream_t st = (cudaStream_t)stream;
+  if (uda_vec_ok(prob, target, grad_prob, outer, C, inner)) {
+    const unsigned nquads = (unsigned)(total / 4), inner4 = (unsigned)(inner / 4);
+    const int vgrid = uda_grid(total / 4);
+#define IIC_UDA_BWD(FL, CC)                                                                                   \
+    uda_bwd_vec_kernel<FL, CC><<<vgrid, 256, 0, st>>>(prob, target, nquads, inner4, kind, (float)eps, weight, \
+                                                      inv_denom, grad_loss, grad_prob)
+    if (from_logits) { if (C == 2) IIC_UDA_BWD(true, 2); else if (C == 3) IIC_UDA_BWD(true, 3); else IIC_UDA_BWD(true, 4); }
+    else             { if (C == 2) IIC_UDA_BWD(false, 2); else if (C == 3) IIC_UDA_BWD(false, 3); else IIC_UDA_BWD(false, 4); }
+#undef IIC_UDA_BWD
+    IIC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
   if (from_logits)
     uda_bwd_kernel<true><<<grid, 256, 0, st>>>(prob, target, outer, C, inner, kind, (float)eps, weight,
                                                inv_denom, grad_loss, grad_prob);
