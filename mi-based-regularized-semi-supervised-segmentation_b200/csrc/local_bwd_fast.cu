@@ -1,21 +1,21 @@
 // Specialised local backward (the convolution_backward of contrastyou/losses/iic_loss.py:123) for the
-// 3 x 3 window, channel counts that are multiples of 10 and maps at most 248 pixels wide (one patch, no
-// mask) -- the shapes of the reference's udaiic configuration.  Both gradients come out of ONE launch:
+// reference's udaiic shapes: window 3 x 3 or 7 x 7 (padding 1 or 3, config/semi.yaml), 10 or 20 clusters,
+// maps at most 248 pixels wide (one patch, no mask).  Both gradients come from the same kernel:
 //   gx[i](px) = sum_{j,tap} Wx[j][tap][i] * y[j](px + tap)      gy[j](px) = sum_{i,tap} Wy[i][tap][j] * x[i](px + tap)
 // (Wx / Wy = dL/dJ re-laid by the epilogue kernel).
 //
 // Work decomposition.  The B*H image rows are dealt out in equal contiguous shares to the persistent
 // CTAs (one per SM), so no SM idles in a last partial wave; a CTA walks its share in chunks of CR whole
 // rows (CR * W/4 <= 512).  A thread owns one row x 4 pixels x 10 output channels = 20 float2
-// accumulators (pairs over adjacent output channels); 16 consumer warps = 4 per SM sub-partition.  Per input channel a thread loads its 3 x 6 window (three
-// LDS.128, the two halo columns come from the neighbouring lanes by shuffle).  The weights are warp-uniform,
-// so they never touch a vector register or the LSU: the host copies dL/dJ (Wx, Wy) device-to-device
-// into __constant__ memory in front of the launch and every update is one
+// accumulators (pairs over adjacent output channels); 16 consumer warps = 4 per SM sub-partition.
+// Per input channel and window row a thread loads its 4 + 2*pad window values (one LDS.128, the halo
+// columns come from the neighbouring lanes by shuffle).  The weights are warp-uniform, so they never touch
+// a vector register or the LSU: the host copies dL/dJ (Wx, Wy) device-to-device into __constant__ memory
+// in front of the launch and every update is one
 //   FFMA2 acc, window.F32 (scalar), UR.F32x2 (weight pair, LDCU.64 from the constant bank), acc
-// i.e. per input channel 180 FFMA2 + 45 uniform-datapath loads + ~15 shared-memory instructions.
-// (IIC_B200_BWD_CFG=1 selects 24 consumer warps with a 3-slot ring, for experiments.)
+// i.e. per input channel 20*T*T FFMA2 + 5*T*T uniform-datapath loads + a few shared-memory instructions.
 //
-// Input tiles (CR + 2 rows, full width + halo, 5 channels per stage) stream through a TMA ring with
+// Input tiles (CR + 2*pad rows, full width + halo, 5 channels per stage) stream through a TMA ring with
 // full/empty mbarriers per slot, refilled by a dedicated producer warp; the hardware zero-fills rows and
 // columns outside the map, which is the conv's padding.  (The producer must be its own warp: a
 // one-thread spin on an mbarrier inside the consumers' loop makes the compiler treat the loop counters
@@ -30,25 +30,26 @@ namespace iic {
 
 namespace bwdfast {
 constexpr int KB = 10;                 // output-channel block
+constexpr int WROW = 12;               // floats per (cin, tap) weight row in the constant bank (10 + 2 pad)
 constexpr int LP = 4;                  // halo columns staged left and right (keeps rows 16-byte aligned)
-constexpr int T2 = 9;
+constexpr int WC_FLOATS = 15360;       // 60 KB of the 64 KB constant bank
 }  // namespace bwdfast
 
-// dL/dJ for the two sweeps, [slot][sweep][cin][tap][Kp] (57.6 KB of the 64 KB bank).  Launches on one
-// stream are ordered, so one slot would do; the two slots, used round-robin, keep two interleaved
-// streams apart.  More than two streams running this backward concurrently are not supported.
-constexpr int WC_SLOT_FLOATS = 2 * 20 * 9 * 20;
-__constant__ float2 g_wc[2 * WC_SLOT_FLOATS / 2];
+// dL/dJ of this launch: [sweep][output block][cin][tap][WROW].  Launches on one stream are ordered, so the
+// copy in front of launch n+1 cannot overtake launch n; when a launch needs less than half of the array
+// two halves are used round-robin, which also keeps two interleaved streams apart.  More than two streams
+// running this backward concurrently are not supported.
+__constant__ float2 g_wc[bwdfast::WC_FLOATS / 2];
 
 struct BwdFastParams {
-  int wc_base;               // float2 index of this launch's slot in g_wc
-  int B, K, Kp, H, W;
+  int wc_base;               // float2 index of this launch's weights in g_wc
+  int sw0, nsw;              // sweeps done by this launch: [sw0, sw0 + nsw)   (0 = gx, 1 = gy)
+  int ob0;                   // first output-channel block of this launch (blockIdx.y counts from it)
+  int B, H, W;
   int QW, CR, XP, XR;        // thread tiles per row, rows per chunk, tile pitch (floats) and rows
   int plane;                 // floats per channel plane of a stage
   long long rows_total;      // B * H
   unsigned stage_bytes, box_bytes;
-  const float* Wx;           // [K][9][Kp]
-  const float* Wy;
   const float* grad_loss;
   float* gx;
   float* gy;
@@ -68,24 +69,25 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-// PXQ = pixel quads per thread (a thread owns one row x 4*PXQ pixels x 10 output channels); NWARPS consumer
-// warps + one producer warp.
-template <int K, int PXQ, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
+// K clusters, T x T window; NWARPS consumer warps + one producer warp; CB input channels per stage.
+template <int K, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 __global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
 local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                       const BwdFastParams P) {
   using namespace bwdfast;
-  constexpr int NPX = 4 * PXQ;
-  constexpr int Kp = (K + 3) & ~3;                        // row pitch of Wx / Wy
+  constexpr int PAD = T / 2, T2 = T * T;
+  constexpr int NPX = 4;
   constexpr int nchunk = K / CB;                            // stages per sweep
-  constexpr int per_chunk = 2 * nchunk;                     // stages per row chunk (two sweeps)
+  static_assert(PAD <= LP && PAD <= 3, "halo wider than the staged margin");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
   __shared__ __align__(8) uint64_t empty_bar[STAGES];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int oc0 = blockIdx.y * KB;                          // this CTA's output-channel block
+  const int ob_local = blockIdx.y;
+  const int oc0 = (P.ob0 + ob_local) * KB;                  // this CTA's output-channel block
   const long long R0 = (long long)blockIdx.x * P.rows_total / gridDim.x;
   const long long R1 = (long long)(blockIdx.x + 1) * P.rows_total / gridDim.x;
+  const int per_chunk = P.nsw * nchunk;                     // stages per row chunk
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -111,12 +113,13 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         if (nr > P.H - h0) nr = P.H - h0;
         if (nr > R1 - r) nr = (int)(R1 - r);
         for (int st = 0; st < per_chunk; ++st, ++k) {
-          const int sweep = st / nchunk, cb = st - sweep * nchunk;
+          const int sl = st / nchunk, cb = st - sl * nchunk;
+          const int sweep = P.sw0 + sl;
           const int s = k % STAGES;
           if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], P.box_bytes);
-          tma_load_4d(smem_raw + (size_t)s * P.stage_bytes, sweep == 0 ? &mapy : &mapx, &full_bar[s], -LP, h0 - 1,
-                      cb * CB, n);                          // gx reads y, gy reads x
+          tma_load_4d(smem_raw + (size_t)s * P.stage_bytes, sweep == 0 ? &mapy : &mapx, &full_bar[s], -LP,
+                      h0 - PAD, cb * CB, n);                // gx reads y, gy reads x
         }
         r += nr;
       }
@@ -131,7 +134,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   const int rr_c = in_tile ? rr : P.CR - 1;                 // idle threads read valid rows, store nothing
   const uint32_t toff = (uint32_t)(rr_c * P.XP + LP + NPX * q) * 4u;
   // the halo columns come from the neighbouring lanes, except at the warp's and the row's ends, where
-  // they are read from the tile (columns -1 and W hold the zero fill = the conv's padding)
+  // they are read from the tile (columns < 0 and >= W hold the zero fill = the conv's padding)
   const int ld_left = (lane == 0) | (q == 0), ld_right = (lane == 31) | (q == P.QW - 1);
   const uint32_t xp4 = (uint32_t)P.XP * 4u, plane4 = (uint32_t)P.plane * 4u;
   const uint32_t smem_base = smem_u32(smem_raw);
@@ -145,11 +148,14 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
     if (nr > R1 - r) nr = (int)(R1 - r);
     const bool active = in_tile && rr < nr;
     const bool warp_active = __any_sync(0xffffffffu, active);
-    for (int sweep = 0; sweep < 2; ++sweep) {
+    for (int sl = 0; sl < P.nsw; ++sl) {
+      const int sweep = P.sw0 + sl;
 #pragma unroll
       for (int c = 0; c < KB / 2; ++c)
 #pragma unroll
         for (int p = 0; p < NPX; ++p) acc[c][p] = make_float2(0.f, 0.f);
+      // weight pairs of this sweep and output block: g_wc[wbase + (cin * T2 + tap) * WROW / 2 + c]
+      const int wbase = P.wc_base + ((sl * (int)gridDim.y + ob_local) * K) * (T2 * WROW / 2);
       for (int cb = 0; cb < nchunk; ++cb, ++k) {
         const int s = k % STAGES;
         mbar_wait(&full_bar[s], (k / STAGES) & 1u);
@@ -162,7 +168,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           const int npos = P.XR * P.XP;
           for (int pos = threadIdx.x; pos < npos; pos += NWARPS * 32) {
             const int tr = pos / P.XP, tc = pos - tr * P.XP;
-            const bool valid = (unsigned)(h0 - 1 + tr) < (unsigned)P.H && (unsigned)(tc - LP) < (unsigned)P.W;
+            const bool valid = (unsigned)(h0 - PAD + tr) < (unsigned)P.H && (unsigned)(tc - LP) < (unsigned)P.W;
             float v[K];
             float mx = -3.0e38f;
 #pragma unroll
@@ -180,40 +186,37 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           uint32_t cp = smem_base + (uint32_t)s * P.stage_bytes + toff;
 #pragma unroll 1
           for (int ch = 0; ch < CB; ++ch, cp += plane4) {
-            // weight pairs of this sweep, input channel and output block: g_wc[wq + tap * Kp / 2 + c]
-            const int wq = P.wc_base + (sweep * K * T2 * Kp + oc0) / 2 + (cb * CB + ch) * (T2 * Kp / 2);
-            float win[3][NPX + 2];
+            const int wq = wbase + (cb * CB + ch) * (T2 * WROW / 2);
 #pragma unroll
-            for (int wr = 0; wr < 3; ++wr) {
-              const uint32_t rp = cp + wr * xp4;
+            for (int ry = 0; ry < T; ++ry) {
+              // window row ry: NPX own pixels + PAD halo columns on each side
+              const uint32_t rp = cp + ry * xp4;
+              float win[NPX + 2 * PAD];
+              const float4 v = lds128(rp);
+              win[PAD + 0] = v.x; win[PAD + 1] = v.y; win[PAD + 2] = v.z; win[PAD + 3] = v.w;
 #pragma unroll
-              for (int v4 = 0; v4 < PXQ; ++v4) {
-                const float4 v = lds128(rp + 16 * v4);
-                win[wr][1 + 4 * v4] = v.x; win[wr][2 + 4 * v4] = v.y;
-                win[wr][3 + 4 * v4] = v.z; win[wr][4 + 4 * v4] = v.w;
+              for (int h = 0; h < PAD; ++h) {
+                float l = __shfl_up_sync(0xffffffffu, win[PAD + NPX - PAD + h], 1);      // left neighbour's last PAD
+                float rt = __shfl_down_sync(0xffffffffu, win[PAD + h], 1);               // right neighbour's first PAD
+                lds_if(l, rp - 4 * (PAD - h), ld_left);
+                lds_if(rt, rp + 4 * (NPX + h), ld_right);
+                win[h] = l;
+                win[PAD + NPX + h] = rt;
               }
-              float l = __shfl_up_sync(0xffffffffu, win[wr][NPX], 1);
-              float rt = __shfl_down_sync(0xffffffffu, win[wr][1], 1);
-              lds_if(l, rp - 4, ld_left);
-              lds_if(rt, rp + 4 * NPX, ld_right);
-              win[wr][0] = l;
-              win[wr][NPX + 1] = rt;
-            }
 #pragma unroll
-            for (int ry = 0; ry < 3; ++ry)
-#pragma unroll
-              for (int rx = 0; rx < 3; ++rx) {
+              for (int rx = 0; rx < T; ++rx) {
                 float2 wp[KB / 2];
 #pragma unroll
-                for (int c = 0; c < KB / 2; ++c) wp[c] = g_wc[wq + (ry * 3 + rx) * (Kp / 2) + c];
+                for (int c = 0; c < KB / 2; ++c) wp[c] = g_wc[wq + (ry * T + rx) * (WROW / 2) + c];
 #pragma unroll
                 for (int p = 0; p < NPX; ++p) {
-                  const float a = win[ry][p + rx];
+                  const float a = win[p + rx];
                   const float2 a2 = make_float2(a, a);
 #pragma unroll
                   for (int c = 0; c < KB / 2; ++c) acc[c][p] = __ffma2_rn(a2, wp[c], acc[c][p]);
                 }
               }
+            }
           }
         }
         __syncwarp();
@@ -230,33 +233,30 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
                           sh = sweep == 0 ? P.lx_sh : P.ly_sh;
           const float* src = lg + (long long)n * sn + (long long)(h0 + rr) * sh + NPX * q;
           const float k2 = P.inv_temp * 1.4426950408889634f;
+          float4 l[K];
 #pragma unroll
-          for (int v4 = 0; v4 < PXQ; ++v4) {
-            float4 l[K];
+          for (int c = 0; c < K; ++c) l[c] = __ldg(reinterpret_cast<const float4*>(src + (long long)c * sc));
 #pragma unroll
-            for (int c = 0; c < K; ++c) l[c] = __ldg(reinterpret_cast<const float4*>(src + (long long)c * sc + 4 * v4));
+          for (int e = 0; e < 4; ++e) {
+            float pv[K];
+            float mx = -3.0e38f;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float pv[K];
-              float mx = -3.0e38f;
+            for (int c = 0; c < K; ++c) { pv[c] = (&l[c].x)[e]; mx = fmaxf(mx, pv[c]); }
+            float sum = 0.f;
 #pragma unroll
-              for (int c = 0; c < K; ++c) { pv[c] = (&l[c].x)[e]; mx = fmaxf(mx, pv[c]); }
-              float sum = 0.f;
+            for (int c = 0; c < K; ++c) { pv[c] = exp2f((pv[c] - mx) * k2); sum += pv[c]; }
+            const float inv = 1.f / sum;
+            float dot = 0.f;
 #pragma unroll
-              for (int c = 0; c < K; ++c) { pv[c] = exp2f((pv[c] - mx) * k2); sum += pv[c]; }
-              const float inv = 1.f / sum;
-              float dot = 0.f;
+            for (int c = 0; c < K; ++c) {
+              pv[c] *= inv;
+              const float gc = (c & 1) ? acc[c / 2][e].y : acc[c / 2][e].x;
+              dot = fmaf(gc, pv[c], dot);
+            }
 #pragma unroll
-              for (int c = 0; c < K; ++c) {
-                pv[c] *= inv;
-                const float gc = (c & 1) ? acc[c / 2][4 * v4 + e].y : acc[c / 2][4 * v4 + e].x;
-                dot = fmaf(gc, pv[c], dot);
-              }
-#pragma unroll
-              for (int c = 0; c < K; ++c) {
-                float& gc = (c & 1) ? acc[c / 2][4 * v4 + e].y : acc[c / 2][4 * v4 + e].x;
-                gc = pv[c] * (gc - dot) * P.inv_temp;
-              }
+            for (int c = 0; c < K; ++c) {
+              float& gc = (c & 1) ? acc[c / 2][e].y : acc[c / 2][e].x;
+              gc = pv[c] * (gc - dot) * P.inv_temp;
             }
           }
         }
@@ -265,24 +265,22 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + NPX * q;
         const size_t cs = (size_t)P.H * P.W;
 #pragma unroll
-        for (int c = 0; c < KB / 2; ++c)
-#pragma unroll
-          for (int v4 = 0; v4 < PXQ; ++v4) {
-            *reinterpret_cast<float4*>(out + (size_t)(2 * c) * cs + 4 * v4) =
-                make_float4(g * acc[c][4 * v4].x, g * acc[c][4 * v4 + 1].x, g * acc[c][4 * v4 + 2].x, g * acc[c][4 * v4 + 3].x);
-            *reinterpret_cast<float4*>(out + (size_t)(2 * c + 1) * cs + 4 * v4) =
-                make_float4(g * acc[c][4 * v4].y, g * acc[c][4 * v4 + 1].y, g * acc[c][4 * v4 + 2].y, g * acc[c][4 * v4 + 3].y);
-          }
+        for (int c = 0; c < KB / 2; ++c) {
+          *reinterpret_cast<float4*>(out + (size_t)(2 * c) * cs) =
+              make_float4(g * acc[c][0].x, g * acc[c][1].x, g * acc[c][2].x, g * acc[c][3].x);
+          *reinterpret_cast<float4*>(out + (size_t)(2 * c + 1) * cs) =
+              make_float4(g * acc[c][0].y, g * acc[c][1].y, g * acc[c][2].y, g * acc[c][3].y);
+        }
       }
     }
     r += nr;
   }
 }
 
-template <int K, int PXQ, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
+template <int K, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const BwdFastParams& P, dim3 grid,
                            size_t smem, cudaStream_t st) {
-  auto kern = local_bwd_fast_kernel<K, PXQ, NWARPS, STAGES, CB, FROM_LOGITS>;
+  auto kern = local_bwd_fast_kernel<K, T, NWARPS, STAGES, CB, FROM_LOGITS>;
   static bool attr_set = false;
   if (!attr_set) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -299,32 +297,28 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
                        int from_logits, float inv_temp, cudaStream_t st) {
   using namespace bwdfast;
-  if (pad != 1 || (K != 10 && K != 20)) return -1;
-  if (from_logits && K != 10) return -1;
+  if ((pad != 1 && pad != 3) || (K != 10 && K != 20)) return -1;
+  if (from_logits && (K != 10 || pad != 1)) return -1;
   if (W % 4 != 0 || W > 248 || W < 4) return -1;
   if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
-  // launch shape: 0 = 16 consumer warps x 4 stages, 1 = 24 consumer warps x 3 stages
-  int cfg = 0;
-  if (const char* e = getenv("IIC_B200_BWD_CFG")) cfg = atoi(e);
-  if (cfg < 0 || cfg > 1) cfg = 0;
-  if (from_logits) cfg = 0;
-  const int pxq = 1, CB = from_logits ? 10 : 5;    // the fused softmax needs all K channels in one stage
-  const int nthreads = cfg == 0 ? 512 : 768, stages = from_logits ? 2 : cfg == 0 ? 4 : 3;
+  const int T = 2 * pad + 1, T2 = T * T, Kp = (K + 3) & ~3;
+  const int CB = from_logits ? 10 : 5;               // the fused softmax needs all K channels in one stage
+  const int nthreads = 512, stages = from_logits ? 2 : (pad == 1 ? 4 : 3);
   BwdFastParams P;
-  P.B = B; P.K = K; P.Kp = (K + 3) & ~3; P.H = H; P.W = W;
-  P.QW = W / (4 * pxq);
+  P.B = B; P.H = H; P.W = W;
+  P.QW = W / 4;
   P.CR = nthreads / P.QW;
   if (P.CR > 62) P.CR = 62;
   if (P.CR > H) P.CR = H;
   P.XP = W + 2 * LP;
-  P.XR = P.CR + 2;
+  P.XR = P.CR + 2 * pad;
   P.plane = P.XR * P.XP;
   P.rows_total = (long long)B * H;
   P.box_bytes = (unsigned)((size_t)CB * P.plane * 4);
   P.stage_bytes = (P.box_bytes + 127u) & ~127u;
   const size_t smem = (size_t)P.stage_bytes * stages;
   if (smem > 226 * 1024) return -1;
-  P.Wx = Wx; P.Wy = Wy; P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
+  P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
   P.lx = x; P.lx_sn = x_sn; P.lx_sc = x_sc; P.lx_sh = x_sh;
   P.ly = y; P.ly_sn = y_sn; P.ly_sc = y_sc; P.ly_sh = y_sh;
   P.inv_temp = inv_temp;
@@ -335,32 +329,47 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, P.XP, P.XR, CB)) return -1;
   if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, P.XP, P.XR, CB)) return -1;
   const int nob = K / KB;
-  int gxd = sms / nob;
-  if (gxd < 1) gxd = 1;
-  if (gxd > P.rows_total) gxd = (int)P.rows_total;
-  const dim3 grid(gxd, nob);
-  // dL/dJ -> constant bank (device-to-device, stream ordered, capturable as a memcpy node)
+
+  // How many (sweep, output block) weight slabs fit in the constant bank at once decides the launches:
+  // everything in one launch (3 x 3 windows; 7 x 7 with 10 clusters) or one launch per slab (7 x 7, K = 20).
+  const int slab = K * T2 * WROW;                           // floats of one (sweep, output block) slab
+  const bool one_launch = 2 * nob * slab <= WC_FLOATS;
+  if (!one_launch && slab > WC_FLOATS) return -1;
+  float2* wc_dev = nullptr;
+  IIC_CHECK_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&wc_dev), g_wc));
   static unsigned slot_counter = 0;
-  const int slot = (int)(slot_counter++ & 1u);
-  const size_t wfloats = (size_t)K * T2 * P.Kp;
-  P.wc_base = slot * (WC_SLOT_FLOATS / 2);
-  const size_t off = (size_t)slot * WC_SLOT_FLOATS * sizeof(float);
-  if (Wy == Wx + wfloats) {
-    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wx, 2 * wfloats * sizeof(float), off, cudaMemcpyDeviceToDevice, st));
-  } else {
-    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wx, wfloats * sizeof(float), off, cudaMemcpyDeviceToDevice, st));
-    IIC_CHECK_CUDA(cudaMemcpyToSymbolAsync(g_wc, Wy, wfloats * sizeof(float), off + wfloats * sizeof(float),
-                                           cudaMemcpyDeviceToDevice, st));
-  }
-#define IIC_BWD_LAUNCH(KK)                                                              \
-  switch (cfg) {                                                                        \
-    case 1: return launch_bwd_fast<KK, 1, 24, 3, 5, false>(mx, my, P, grid, smem, st);  \
-    default: return launch_bwd_fast<KK, 1, 16, 4, 5, false>(mx, my, P, grid, smem, st); \
-  }
-  if (from_logits) return launch_bwd_fast<10, 1, 16, 2, 10, true>(mx, my, P, grid, smem, st);
-  if (K == 10) { IIC_BWD_LAUNCH(10) }
-  IIC_BWD_LAUNCH(20)
-#undef IIC_BWD_LAUNCH
+
+  auto run = [&](int sw0, int nsw, int ob0, int nobl) -> int {
+    const int need = nsw * nobl * slab;
+    int base = 0;                                           // floats
+    if (2 * need <= WC_FLOATS) base = (int)(slot_counter++ & 1u) * (WC_FLOATS / 2);
+    // dL/dJ -> constant bank: one strided device-to-device copy per slab (stream ordered, capturable);
+    // each (cin, tap) row keeps the 10 weights of the slab's output block in a 12-float row
+    for (int s = 0; s < nsw; ++s)
+      for (int o = 0; o < nobl; ++o) {
+        const float* src = ((sw0 + s) == 0 ? Wx : Wy) + (size_t)(ob0 + o) * KB;
+        float* dst = reinterpret_cast<float*>(wc_dev) + base + (size_t)(s * nobl + o) * slab;
+        IIC_CHECK_CUDA(cudaMemcpy2DAsync(dst, WROW * sizeof(float), src, (size_t)Kp * sizeof(float),
+                                         KB * sizeof(float), (size_t)K * T2, cudaMemcpyDeviceToDevice, st));
+      }
+    P.wc_base = base / 2;
+    P.sw0 = sw0; P.nsw = nsw; P.ob0 = ob0;
+    int gxd = sms / nobl;
+    if (gxd < 1) gxd = 1;
+    if (gxd > P.rows_total) gxd = (int)P.rows_total;
+    const dim3 grid(gxd, nobl);
+    if (from_logits) return launch_bwd_fast<10, 3, 16, 2, 10, true>(mx, my, P, grid, smem, st);
+    if (K == 10 && T == 3) return launch_bwd_fast<10, 3, 16, 4, 5, false>(mx, my, P, grid, smem, st);
+    if (K == 20 && T == 3) return launch_bwd_fast<20, 3, 16, 4, 5, false>(mx, my, P, grid, smem, st);
+    if (K == 10 && T == 7) return launch_bwd_fast<10, 7, 16, 3, 5, false>(mx, my, P, grid, smem, st);
+    return launch_bwd_fast<20, 7, 16, 3, 5, false>(mx, my, P, grid, smem, st);
+  };
+
+  if (one_launch) return run(0, 2, 0, nob);
+  for (int sw = 0; sw < 2; ++sw)
+    for (int ob = 0; ob < nob; ++ob)
+      if (int rc = run(sw, 1, ob, 1)) return rc;
+  return 0;
 }
 
 }  // namespace iic

@@ -373,6 +373,9 @@ int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long lo
                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                          float* partial, int max_ctas, int* ncta, int* flags, int* checked, int from_logits,
                          float inv_temp, cudaStream_t st);
+int local_joint_fast7_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                          long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                          float* partial, int max_ctas, int* ncta, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -412,6 +415,9 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                         (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, 0, 1.f, st);
     if (rc == 0 && checked) flags = nullptr;       // done inside the joint kernel
+    if (rc < 0 && !getenv("IIC_B200_NO_FAST"))
+      rc = local_joint_fast7_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
+                                 pl.slots_per_patch, &ncta, st);
     if (rc < 0)
       rc = local_joint_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                (float*)workspace, pl.slots_per_patch, &ncta, st);

@@ -115,7 +115,10 @@ LOCAL_CASES = [
     # B, K, H, W, pad, patch
     (4, 10, 64, 96, 1, 512),      # the headline variant (T=3, one job per warp)
     (2, 10, 224, 224, 1, 512),    # ACDC Up_conv2 shape, reduced batch
-    (2, 20, 40, 48, 3, 1024),     # yaml default K=20, p=3 (multi-round, T=7)
+    (2, 20, 40, 48, 3, 1024),     # yaml default K=20, p=3 (7 x 7 kernels, one backward launch per weight slab)
+    (2, 10, 56, 64, 3, 512),      # K=10, p=3 (7 x 7 kernels, single backward launch)
+    (1, 10, 224, 224, 3, 512),    # ACDC Up_conv2 shape with the yaml padding of 3
+    (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows
     (2, 20, 56, 56, 1, 1024),     # K=20, p=1
     (2, 4, 33, 45, 2, 512),       # T=5, odd sizes, W % 4 != 0
     (1, 3, 30, 70, 0, 512),       # T=1
