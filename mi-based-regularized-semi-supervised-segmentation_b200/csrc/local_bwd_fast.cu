@@ -1,6 +1,6 @@
 // Specialised local backward (the convolution_backward of contrastyou/losses/iic_loss.py:123) for the
 // reference's udaiic shapes: window 3 x 3 or 7 x 7 (padding 1 or 3, config/semi.yaml), 10 or 20 clusters,
-// maps at most 248 pixels wide (one patch, no mask).  Both gradients come from the same kernel:
+// one patch, no mask (maps wider than 248 pixels are cut into column panels).  Both gradients come from the same kernel:
 //   gx[i](px) = sum_{j,tap} Wx[j][tap][i] * y[j](px + tap)      gy[j](px) = sum_{i,tap} Wy[i][tap][j] * x[i](px + tap)
 // (Wx / Wy = dL/dJ re-laid by the epilogue kernel).
 //
@@ -46,9 +46,10 @@ struct BwdFastParams {
   int sw0, nsw;              // sweeps done by this launch: [sw0, sw0 + nsw)   (0 = gx, 1 = gy)
   int ob0;                   // first output-channel block of this launch (blockIdx.y counts from it)
   int B, H, W;
-  int QW, CR, XP, XR;        // thread tiles per row, rows per chunk, tile pitch (floats) and rows
+  int PW, NPW;               // column panels: width (multiple of 4, <= 248) and count; W <= 248 is one panel
+  int QW, CR, XP, XR;        // thread tiles per panel row, rows per chunk, tile pitch (floats) and rows
   int plane;                 // floats per channel plane of a stage
-  long long rows_total;      // B * H
+  long long rows_total;      // B * NPW * H: rows of all (image, panel) strips, dealt out to the CTAs
   unsigned stage_bytes, box_bytes;
   const float* grad_loss;
   float* gx;
@@ -108,7 +109,8 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
       tma_prefetch_desc(&mapy);
       unsigned k = 0;
       for (long long r = R0; r < R1;) {
-        const int n = (int)(r / P.H), h0 = (int)(r - (long long)n * P.H);
+        const int strip = (int)(r / P.H), h0 = (int)(r - (long long)strip * P.H);
+        const int n = strip / P.NPW, panel = strip - n * P.NPW;
         int nr = P.CR;
         if (nr > P.H - h0) nr = P.H - h0;
         if (nr > R1 - r) nr = (int)(R1 - r);
@@ -118,8 +120,8 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           const int s = k % STAGES;
           if (k >= STAGES) mbar_wait(&empty_bar[s], ((k / STAGES) & 1u) ^ 1u);
           mbar_arrive_expect_tx(&full_bar[s], P.box_bytes);
-          tma_load_4d(smem_raw + (size_t)s * P.stage_bytes, sweep == 0 ? &mapy : &mapx, &full_bar[s], -LP,
-                      h0 - PAD, cb * CB, n);                // gx reads y, gy reads x
+          tma_load_4d(smem_raw + (size_t)s * P.stage_bytes, sweep == 0 ? &mapy : &mapx, &full_bar[s],
+                      panel * P.PW - LP, h0 - PAD, cb * CB, n);       // gx reads y, gy reads x
         }
         r += nr;
       }
@@ -142,11 +144,13 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   float2 acc[KB / 2][NPX];
   unsigned k = 0;
   for (long long r = R0; r < R1;) {
-    const int n = (int)(r / P.H), h0 = (int)(r - (long long)n * P.H);
+    const int strip = (int)(r / P.H), h0 = (int)(r - (long long)strip * P.H);
+    const int n = strip / P.NPW, panel = strip - n * P.NPW;
+    const int col0 = panel * P.PW;                          // first image column of this panel
     int nr = P.CR;
     if (nr > P.H - h0) nr = P.H - h0;
     if (nr > R1 - r) nr = (int)(R1 - r);
-    const bool active = in_tile && rr < nr;
+    const bool active = in_tile && rr < nr && col0 + NPX * q < P.W;
     const bool warp_active = __any_sync(0xffffffffu, active);
     for (int sl = 0; sl < P.nsw; ++sl) {
       const int sweep = P.sw0 + sl;
@@ -168,7 +172,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           const int npos = P.XR * P.XP;
           for (int pos = threadIdx.x; pos < npos; pos += NWARPS * 32) {
             const int tr = pos / P.XP, tc = pos - tr * P.XP;
-            const bool valid = (unsigned)(h0 - PAD + tr) < (unsigned)P.H && (unsigned)(tc - LP) < (unsigned)P.W;
+            const bool valid = (unsigned)(h0 - PAD + tr) < (unsigned)P.H && (unsigned)(col0 + tc - LP) < (unsigned)P.W;
             float v[K];
             float mx = -3.0e38f;
 #pragma unroll
@@ -231,7 +235,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           const float* lg = sweep == 0 ? P.lx : P.ly;
           const long long sn = sweep == 0 ? P.lx_sn : P.ly_sn, sc = sweep == 0 ? P.lx_sc : P.ly_sc,
                           sh = sweep == 0 ? P.lx_sh : P.ly_sh;
-          const float* src = lg + (long long)n * sn + (long long)(h0 + rr) * sh + NPX * q;
+          const float* src = lg + (long long)n * sn + (long long)(h0 + rr) * sh + col0 + NPX * q;
           const float k2 = P.inv_temp * 1.4426950408889634f;
           float4 l[K];
 #pragma unroll
@@ -262,7 +266,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         }
       }
       if (active) {
-        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + NPX * q;
+        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + col0 + NPX * q;
         const size_t cs = (size_t)P.H * P.W;
 #pragma unroll
         for (int c = 0; c < KB / 2; ++c) {
@@ -299,21 +303,25 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   using namespace bwdfast;
   if ((pad != 1 && pad != 3) || (K != 10 && K != 20)) return -1;
   if (from_logits && (K != 10 || pad != 1)) return -1;
-  if (W % 4 != 0 || W > 248 || W < 4) return -1;
+  if (W % 4 != 0 || W < 4) return -1;
+  if (from_logits && W > 248) return -1;
   if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
   const int T = 2 * pad + 1, T2 = T * T, Kp = (K + 3) & ~3;
   const int CB = from_logits ? 10 : 5;               // the fused softmax needs all K channels in one stage
   const int nthreads = 512, stages = from_logits ? 2 : (pad == 1 ? 4 : 3);
   BwdFastParams P;
   P.B = B; P.H = H; P.W = W;
-  P.QW = W / 4;
+  // maps wider than one TMA box are cut into column panels of equal width (the last may be narrower)
+  P.NPW = (W + 247) / 248;
+  P.PW = (((W + P.NPW - 1) / P.NPW) + 3) & ~3;
+  P.QW = P.PW / 4;
   P.CR = nthreads / P.QW;
   if (P.CR > 62) P.CR = 62;
   if (P.CR > H) P.CR = H;
-  P.XP = W + 2 * LP;
+  P.XP = P.PW + 2 * LP;
   P.XR = P.CR + 2 * pad;
   P.plane = P.XR * P.XP;
-  P.rows_total = (long long)B * H;
+  P.rows_total = (long long)B * P.NPW * H;
   P.box_bytes = (unsigned)((size_t)CB * P.plane * 4);
   P.stage_bytes = (P.box_bytes + 127u) & ~127u;
   const size_t smem = (size_t)P.stage_bytes * stages;

@@ -119,6 +119,8 @@ LOCAL_CASES = [
     (2, 10, 56, 64, 3, 512),      # K=10, p=3 (7 x 7 kernels, single backward launch)
     (1, 10, 224, 224, 3, 512),    # ACDC Up_conv2 shape with the yaml padding of 3
     (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows
+    (1, 10, 20, 512, 1, 1024),    # wide map: the backward cuts it into column panels
+    (1, 20, 18, 300, 3, 1024),    # wide map, 7 x 7, last panel narrower
     (2, 20, 56, 56, 1, 1024),     # K=20, p=1
     (2, 4, 33, 45, 2, 512),       # T=5, odd sizes, W % 4 != 0
     (1, 3, 30, 70, 0, 512),       # T=1
