@@ -37,7 +37,8 @@ def _nvcc() -> str:
 
 
 def _newest_header() -> float:
-    hs = glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(INCLUDE, "*.h"))
+    hs = (glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.inc"))
+          + glob.glob(os.path.join(INCLUDE, "*.h")))
     return max(os.path.getmtime(h) for h in hs)
 
 

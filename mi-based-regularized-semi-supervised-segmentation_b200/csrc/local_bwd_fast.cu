@@ -1,5 +1,6 @@
 // Specialised local backward (the convolution_backward of contrastyou/losses/iic_loss.py:123) for the
-// reference's udaiic shapes: window 3 x 3 or 7 x 7 (padding 1 or 3, config/semi.yaml), 10 or 20 clusters,
+// reference's udaiic shapes: window 3 x 3 or 7 x 7 (padding 1 or 3, config/semi.yaml), 10 or 20 clusters (and
+// any multiple of 8 up to 256, in output blocks of 8),
 // one patch, no mask (maps wider than 248 pixels are cut into column panels).  Both gradients come from the same kernel:
 //   gx[i](px) = sum_{j,tap} Wx[j][tap][i] * y[j](px + tap)      gy[j](px) = sum_{i,tap} Wy[i][tap][j] * x[i](px + tap)
 // (Wx / Wy = dL/dJ re-laid by the epilogue kernel).
@@ -29,8 +30,6 @@
 namespace iic {
 
 namespace bwdfast {
-constexpr int KB = 10;                 // output-channel block
-constexpr int WROW = 12;               // floats per (cin, tap) weight row in the constant bank (10 + 2 pad)
 constexpr int LP = 4;                  // halo columns staged left and right (keeps rows 16-byte aligned)
 constexpr int WC_FLOATS = 15360;       // 60 KB of the 64 KB constant bank
 }  // namespace bwdfast
@@ -45,7 +44,7 @@ struct BwdFastParams {
   int wc_base;               // float2 index of this launch's weights in g_wc
   int sw0, nsw;              // sweeps done by this launch: [sw0, sw0 + nsw)   (0 = gx, 1 = gy)
   int ob0;                   // first output-channel block of this launch (blockIdx.y counts from it)
-  int B, H, W;
+  int B, K, H, W;
   int PW, NPW;               // column panels: width (multiple of 4, <= 248) and count; W <= 248 is one panel
   int QW, CR, XP, XR;        // thread tiles per panel row, rows per chunk, tile pitch (floats) and rows
   int plane;                 // floats per channel plane of a stage
@@ -70,15 +69,18 @@ __device__ __forceinline__ float4 lds128(uint32_t addr) {
   return v;
 }
 
-// K clusters, T x T window; NWARPS consumer warps + one producer warp; CB input channels per stage.
-template <int K, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
+// KB = output channels per CTA (10, or 8 for channel counts that are multiples of 8 but not of 10), T x T
+// window; NWARPS consumer warps + one producer warp; CB input channels per stage.  P.K = all channels.
+template <int KB, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 __global__ void __launch_bounds__((NWARPS + 1) * 32, 1)
 local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
                       const BwdFastParams P) {
   using namespace bwdfast;
   constexpr int PAD = T / 2, T2 = T * T;
   constexpr int NPX = 4;
-  constexpr int nchunk = K / CB;                            // stages per sweep
+  constexpr int WROW = (KB + 3) & ~3;                       // floats per (cin, tap) weight row in the constant bank
+  constexpr int K = KB;                                     // FROM_LOGITS only (P.K == KB there)
+  const int nchunk = P.K / CB;                              // stages per sweep
   static_assert(PAD <= LP && PAD <= 3, "halo wider than the staged margin");
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[STAGES];
@@ -159,7 +161,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
 #pragma unroll
         for (int p = 0; p < NPX; ++p) acc[c][p] = make_float2(0.f, 0.f);
       // weight pairs of this sweep and output block: g_wc[wbase + (cin * T2 + tap) * WROW / 2 + c]
-      const int wbase = P.wc_base + ((sl * (int)gridDim.y + ob_local) * K) * (T2 * WROW / 2);
+      const int wbase = P.wc_base + ((sl * (int)gridDim.y + ob_local) * P.K) * (T2 * WROW / 2);
       for (int cb = 0; cb < nchunk; ++cb, ++k) {
         const int s = k % STAGES;
         mbar_wait(&full_bar[s], (k / STAGES) & 1u);
@@ -266,7 +268,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         }
       }
       if (active) {
-        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * K + oc0) * P.H + (h0 + rr)) * P.W + col0 + NPX * q;
+        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * P.K + oc0) * P.H + (h0 + rr)) * P.W + col0 + NPX * q;
         const size_t cs = (size_t)P.H * P.W;
 #pragma unroll
         for (int c = 0; c < KB / 2; ++c) {
@@ -281,10 +283,10 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   }
 }
 
-template <int K, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
+template <int KB, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const BwdFastParams& P, dim3 grid,
                            size_t smem, cudaStream_t st) {
-  auto kern = local_bwd_fast_kernel<K, T, NWARPS, STAGES, CB, FROM_LOGITS>;
+  auto kern = local_bwd_fast_kernel<KB, T, NWARPS, STAGES, CB, FROM_LOGITS>;
   static bool attr_set = false;
   if (!attr_set) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
@@ -301,16 +303,20 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
                        int from_logits, float inv_temp, cudaStream_t st) {
   using namespace bwdfast;
-  if ((pad != 1 && pad != 3) || (K != 10 && K != 20)) return -1;
+  if (pad != 1 && pad != 3) return -1;
+  // output-channel block: 10 for the udaiic cluster counts (10, 20), 8 for other multiples of 8 (.., 128)
+  const int KB = (K % 10 == 0 && K <= 40) ? 10 : (K % 8 == 0 ? 8 : 0);
+  if (KB == 0 || K > 256) return -1;
   if (from_logits && (K != 10 || pad != 1)) return -1;
+  const int WROW = (KB + 3) & ~3;
   if (W % 4 != 0 || W < 4) return -1;
   if (from_logits && W > 248) return -1;
   if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
   const int T = 2 * pad + 1, T2 = T * T, Kp = (K + 3) & ~3;
-  const int CB = from_logits ? 10 : 5;               // the fused softmax needs all K channels in one stage
+  const int CB = from_logits ? 10 : (KB == 10 ? 5 : 4);   // the fused softmax needs all K channels in one stage
   const int nthreads = 512, stages = from_logits ? 2 : (pad == 1 ? 4 : 3);
   BwdFastParams P;
-  P.B = B; P.H = H; P.W = W;
+  P.B = B; P.K = K; P.H = H; P.W = W;
   // maps wider than one TMA box are cut into column panels of equal width (the last may be narrower)
   P.NPW = (W + 247) / 248;
   P.PW = (((W + P.NPW - 1) / P.NPW) + 3) & ~3;
@@ -367,10 +373,10 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
     if (gxd > P.rows_total) gxd = (int)P.rows_total;
     const dim3 grid(gxd, nobl);
     if (from_logits) return launch_bwd_fast<10, 3, 16, 2, 10, true>(mx, my, P, grid, smem, st);
-    if (K == 10 && T == 3) return launch_bwd_fast<10, 3, 16, 4, 5, false>(mx, my, P, grid, smem, st);
-    if (K == 20 && T == 3) return launch_bwd_fast<20, 3, 16, 4, 5, false>(mx, my, P, grid, smem, st);
-    if (K == 10 && T == 7) return launch_bwd_fast<10, 7, 16, 3, 5, false>(mx, my, P, grid, smem, st);
-    return launch_bwd_fast<20, 7, 16, 3, 5, false>(mx, my, P, grid, smem, st);
+    if (KB == 10 && T == 3) return launch_bwd_fast<10, 3, 16, 4, 5, false>(mx, my, P, grid, smem, st);
+    if (KB == 10 && T == 7) return launch_bwd_fast<10, 7, 16, 3, 5, false>(mx, my, P, grid, smem, st);
+    if (KB == 8 && T == 3) return launch_bwd_fast<8, 3, 16, 4, 4, false>(mx, my, P, grid, smem, st);
+    return launch_bwd_fast<8, 7, 16, 3, 4, false>(mx, my, P, grid, smem, st);
   };
 
   if (one_launch) return run(0, 2, 0, nob);

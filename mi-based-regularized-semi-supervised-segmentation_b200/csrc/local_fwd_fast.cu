@@ -22,23 +22,6 @@
 
 namespace iic {
 
-namespace fwdfast {
-constexpr int T = 3, PAD = 1, TH = 16, TW = 32, LP = 4, XP = LP + TW + 4, XR = TH + 2 * PAD;
-constexpr int KB = 10;                 // channel block
-constexpr int JT = 5;                  // y channels per job
-constexpr int NJOBS = (KB / 2) * (KB / JT);        // 10
-constexpr int NHELP = 2;               // helper warps (jobs 0 and 1 are split by rows)
-constexpr int NCONS = NJOBS + NHELP;   // 12 consumer warps
-constexpr int NTHREADS = NCONS * 32;
-constexpr int PRODUCER_WARP = NJOBS;   // helper warp 10
-constexpr int STAGES = 4;
-constexpr unsigned X_BYTES = KB * XR * XP * 4;
-constexpr unsigned Y_BYTES = KB * TH * TW * 4;
-constexpr unsigned X_REGION = (X_BYTES + 127u) & ~127u;
-constexpr unsigned STAGE_BYTES = X_REGION + ((Y_BYTES + 127u) & ~127u);
-constexpr int XPLANE = XR * XP, YPLANE = TH * TW;
-}  // namespace fwdfast
-
 struct FwdFastParams {
   int B, K, H, W, tiles_h, tiles_w;
   float* partial;           // [gridDim.x][9][K][K]
@@ -46,213 +29,36 @@ struct FwdFastParams {
   float inv_temp;           // FROM_LOGITS: softmax(logit * inv_temp)  (SoftmaxWithT, contrastyou/trainer/_utils.py:15-23)
 };
 
-// rows [0, NROWS) of a job; xa/xb point at (window row 0, dx 0) of the job's two x channels for this
-// lane, y0 at (row 0) of the job's first y channel for this lane.
-template <int NROWS>
-__device__ __forceinline__ void sweep_rows(const float* __restrict__ xa, const float* __restrict__ xb,
-                                           const float* __restrict__ y0, float2 (&acc)[fwdfast::JT][3][3]) {
-  using namespace fwdfast;
-  float2 xw[3][3];
-#pragma unroll
-  for (int r = 0; r < 2; ++r)
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx) xw[r][dx] = make_float2(xa[r * XP + dx], xb[r * XP + dx]);
+}  // namespace iic
 
-  auto row = [&](const int u, const int slot_new, const float* pa, const float* pb, const float* py) {
-    // pa/pb/py are the loop-carried bases; u is the static row offset inside the unrolled body
-#pragma unroll
-    for (int dx = 0; dx < 3; ++dx)
-      xw[slot_new][dx] = make_float2(pa[(u + 2) * XP + dx], pb[(u + 2) * XP + dx]);
-    float2 yv[JT];
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj) {
-      const float v = py[jj * YPLANE + u * TW];
-      yv[jj] = make_float2(v, v);
-    }
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj)
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
-          acc[jj][dy][dx] = __ffma2_rn(xw[(slot_new + 1 + dy) % 3][dx], yv[jj], acc[jj][dy][dx]);
-  };
+namespace iic {
 
-  constexpr int NLOOP = NROWS / 3;
-#pragma unroll 1
-  for (int it = 0; it < NLOOP; ++it) {
-    row(0, 2, xa, xb, y0);
-    row(1, 0, xa, xb, y0);
-    row(2, 1, xa, xb, y0);
-    xa += 3 * XP; xb += 3 * XP; y0 += 3 * TW;
-  }
-  if constexpr (NROWS % 3 >= 1) row(0, 2, xa, xb, y0);
-  if constexpr (NROWS % 3 == 2) row(1, 0, xa, xb, y0);
-}
+#define IIC_FWD_NS fwd3_kb10
+#define IIC_FWD_KB 10
+#include "local_fwd_fast3.inc"
+#undef IIC_FWD_NS
+#undef IIC_FWD_KB
+#define IIC_FWD_NS fwd3_kb8
+#define IIC_FWD_KB 8
+#include "local_fwd_fast3.inc"
+#undef IIC_FWD_NS
+#undef IIC_FWD_KB
 
-// FROM_LOGITS: the maps hold the cluster head's logits; the channel softmax of LocalClusterHead
-// (contrastyou/trainer/_utils.py:137-168) is applied to every staged tile in shared memory, in place,
-// before the sweeps, so the probability maps never exist in HBM.  Needs all K channels in the tile (K == 10).
-template <bool FROM_LOGITS>
-__global__ void __launch_bounds__(fwdfast::NTHREADS, 1)
-local_joint_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy,
-                        const FwdFastParams P) {
-  using namespace fwdfast;
-  extern __shared__ __align__(1024) unsigned char smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[STAGES];
-  __shared__ __align__(8) uint64_t empty_bar[STAGES];
-  __shared__ float red[NCONS][JT * 9 * 2];          // per-warp reduced sums
-  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int items = P.B * P.tiles_h * P.tiles_w;
-  const int nblk = P.K / KB;
-  const int i_off = ((int)blockIdx.y / nblk) * KB, j_off = ((int)blockIdx.y % nblk) * KB;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], NCONS);
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-
-  auto issue = [&](int k) {          // stage the k-th work item of this CTA (if there is one)
-    const int it = blockIdx.x + k * gridDim.x;
-    if (it >= items) return;
-    const int s = k % STAGES;
-    const int n = it / (P.tiles_h * P.tiles_w);
-    const int tt = it - n * (P.tiles_h * P.tiles_w);
-    const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
-    unsigned char* base = smem_raw + (size_t)s * STAGE_BYTES;
-    mbar_arrive_expect_tx(&full_bar[s], X_BYTES + Y_BYTES);
-    tma_load_4d(base, &mapx, &full_bar[s], tw0 - LP, th0 - PAD, i_off, n);
-    tma_load_4d(base + X_REGION, &mapy, &full_bar[s], tw0, th0, j_off, n);
-  };
-  const bool producer = (wid == PRODUCER_WARP && lane == 0);
-  if (producer) {
-    tma_prefetch_desc(&mapx);
-    tma_prefetch_desc(&mapy);
-    for (int k = 0; k < STAGES; ++k) issue(k);
-  }
-  {
-    const int job = wid < NJOBS ? wid : wid - NJOBS;
-    const bool split = job < NHELP;                    // this job's rows are shared with a helper warp
-    const int r0 = (wid >= NJOBS) ? TH / 2 : 0;
-    const int ip = job / (KB / JT), jg = job % (KB / JT);
-    const int xoff = (2 * ip) * XPLANE + r0 * XP + (LP - PAD) + lane;
-    const int yoff = (jg * JT) * YPLANE + r0 * TW + lane;
-
-    float2 acc[JT][3][3];
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj)
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) acc[jj][dy][dx] = make_float2(0.f, 0.f);
-
-    int k = 0;
-    for (int it = blockIdx.x; it < items; it += gridDim.x, ++k) {
-      const int s = k % STAGES;
-      const unsigned use = (unsigned)(k / STAGES);
-      if (producer && k >= 1) {
-        // item k-1 has been consumed by every warp -> its stage takes item k-1+STAGES
-        mbar_wait(&empty_bar[(k - 1) % STAGES], ((unsigned)((k - 1) / STAGES)) & 1u);
-        issue(k - 1 + STAGES);
-      }
-      __syncwarp();
-      mbar_wait(&full_bar[s], use & 1u);
-      if constexpr (FROM_LOGITS) {
-        // in-place channel softmax of the staged x tile (with halo) and y tile; positions outside the map
-        // must stay zero (they are the conv's padding), so they are masked rather than normalised
-        const int n = it / (P.tiles_h * P.tiles_w);
-        const int tt = it - n * (P.tiles_h * P.tiles_w);
-        const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
-        float* xt = reinterpret_cast<float*>(smem_raw + (size_t)s * STAGE_BYTES);
-        float* yt = reinterpret_cast<float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION);
-        const float sc = P.inv_temp * 1.4426950408889634f;
-        for (int pos = threadIdx.x; pos < XR * XP + TH * TW; pos += NTHREADS) {
-          float* base; int plane; bool valid;
-          if (pos < XR * XP) {
-            const int r = pos / XP, c = pos - r * XP;
-            base = xt + pos; plane = XPLANE;
-            valid = (unsigned)(th0 - PAD + r) < (unsigned)P.H && (unsigned)(tw0 - LP + c) < (unsigned)P.W;
-          } else {
-            const int q = pos - XR * XP;
-            const int r = q / TW, c = q - r * TW;
-            base = yt + q; plane = YPLANE;
-            valid = (th0 + r) < P.H && (tw0 + c) < P.W;
-          }
-          float v[KB];
-          float mx = -3.0e38f;
-#pragma unroll
-          for (int ch = 0; ch < KB; ++ch) { v[ch] = base[ch * plane]; mx = fmaxf(mx, v[ch]); }
-          float sum = 0.f;
-#pragma unroll
-          for (int ch = 0; ch < KB; ++ch) { v[ch] = exp2f((v[ch] - mx) * sc); sum += v[ch]; }
-          const float inv = valid ? 1.f / sum : 0.f;
-#pragma unroll
-          for (int ch = 0; ch < KB; ++ch) base[ch * plane] = v[ch] * inv;
-        }
-        asm volatile("bar.sync 1, %0;" ::"n"(NTHREADS) : "memory");      // every warp sweeps the whole tile
-      }
-      const float* xs = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES) + xoff;
-      const float* ys = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES + X_REGION) + yoff;
-      if (split) sweep_rows<TH / 2>(xs, xs + XPLANE, ys, acc);
-      else       sweep_rows<TH>(xs, xs + XPLANE, ys, acc);
-      if (P.flags != nullptr && wid >= NJOBS) {
-        // simplex assertion on x (dc2:utils/assertion.py:56-65 as called at iic_loss.py:113), fused: the
-        // two helper warps have half a job each, so they also add up the K channels of every pixel of
-        // the tile (8 rows each) while it is in shared memory -- no second pass over the map in HBM.
-        const int n = it / (P.tiles_h * P.tiles_w);
-        const int tt = it - n * (P.tiles_h * P.tiles_w);
-        const int th0 = (tt / P.tiles_w) * TH, tw0 = (tt % P.tiles_w) * TW;
-        const float* xc = reinterpret_cast<const float*>(smem_raw + (size_t)s * STAGE_BYTES) +
-                          (PAD + (wid - NJOBS) * (TH / 2)) * XP + LP + lane;
-        bool bad = false;
-#pragma unroll
-        for (int r = 0; r < TH / 2; ++r) {
-          float sum = 0.f;
-#pragma unroll
-          for (int c = 0; c < KB; ++c) sum += xc[c * XPLANE + r * XP];
-          const bool valid = (th0 + (wid - NJOBS) * (TH / 2) + r < P.H) && (tw0 + lane < P.W);
-          bad |= valid && !(fabsf(sum - 1.f) <= 1e-4f + 1e-4f * 1.f);     // allclose(sum, 1, 1e-4, 1e-4); NaN fails
-        }
-        if (__any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
-      }
-      __syncwarp();
-      if constexpr (FROM_LOGITS) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // our writes vs the next TMA fill
-      if (lane == 0) mbar_arrive(&empty_bar[s]);
-    }
-
-    // lanes -> one value per accumulator
-    int a = 0;
-#pragma unroll
-    for (int jj = 0; jj < JT; ++jj)
-#pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const float v0 = warp_sum(acc[jj][dy][dx].x);
-          const float v1 = warp_sum(acc[jj][dy][dx].y);
-          if (lane == (a & 31)) {
-            red[wid][2 * a] = v0;
-            red[wid][2 * a + 1] = v1;
-          }
-          ++a;
-        }
-  }
-  __syncthreads();
-  // this CTA's partial block: slot[d][i_off + i][j_off + j]
-  float* slot = P.partial + (size_t)blockIdx.x * (9 * P.K * P.K);
-  for (int e = threadIdx.x; e < NJOBS * JT * 9 * 2; e += blockDim.x) {
-    const int job = e / (JT * 9 * 2), r = e - job * (JT * 9 * 2);
-    const int a = r >> 1, half = r & 1;
-    const int jj = a / 9, d = a - jj * 9;
-    const int ip = job / (KB / JT), jg = job % (KB / JT);
-    float v = red[job][r];
-    if (job < NHELP) v += red[NJOBS + job][r];
-    slot[((size_t)d * P.K + (i_off + 2 * ip + half)) * P.K + (j_off + jg * JT + jj)] = v;
-  }
+// 0 = launched, 1 = error, -1 = not eligible.  *ncta = number of partial slots written.
+// *checked = 1 when `flags` was given and the simplex assertion on x ran inside the kernel.
+// Channel blocks of 10 for the udaiic cluster counts (10, 20, ..), of 8 for other multiples of 8 (.., 128).
+int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                         long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, int from_logits,
+                         float inv_temp, cudaStream_t st) {
+  *checked = 0;
+  if (K % 10 == 0 && K <= 40)
+    return fwd3_kb10::local_joint_fast_try_kb(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, partial,
+                                              max_ctas, ncta, flags, checked, from_logits, inv_temp, st);
+  if (K % 8 == 0 && K <= 256 && !from_logits)
+    return fwd3_kb8::local_joint_fast_try_kb(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, partial,
+                                             max_ctas, ncta, flags, checked, 0, 1.f, st);
+  return -1;
 }
 
 // ======================================================================================================
@@ -440,49 +246,6 @@ int local_joint_fast7_try(const float* x, long long x_sn, long long x_sc, long l
     attr_set = true;
   }
   local_joint_fast7_kernel<<<dim3(gx, ny), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
-  IIC_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-// 0 = launched, 1 = error, -1 = not eligible.  *ncta = number of partial slots written.
-// *checked = 1 when `flags` was given and the simplex assertion on x ran inside the kernel.
-int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
-                         long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                         float* partial, int max_ctas, int* ncta, int* flags, int* checked, int from_logits,
-                         float inv_temp, cudaStream_t st) {
-  using namespace fwdfast;
-  if (pad != PAD || K < KB || K % KB != 0 || K > 40) return -1;
-  if (from_logits && K != KB) return -1;
-  if (W % 4 != 0) return -1;
-  CUtensorMap mx, my;
-  if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, XP, XR, KB)) return -1;
-  if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, TW, TH, KB)) return -1;
-  FwdFastParams P;
-  P.B = B; P.K = K; P.H = H; P.W = W;
-  P.flags = (K == KB && !from_logits) ? flags : nullptr;
-  P.inv_temp = inv_temp;
-  *checked = P.flags != nullptr;
-  P.tiles_h = (H + TH - 1) / TH;
-  P.tiles_w = (W + TW - 1) / TW;
-  P.partial = partial;
-  const int nblk = K / KB, npairs = nblk * nblk;
-  long long items = (long long)B * P.tiles_h * P.tiles_w;
-  int gx = max_ctas / npairs;
-  if (gx < 1) gx = 1;
-  if (gx > items) gx = (int)items;
-  *ncta = gx;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(STAGES * STAGE_BYTES)));
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(STAGES * STAGE_BYTES)));
-    attr_set = true;
-  }
-  if (from_logits)
-    local_joint_fast_kernel<true><<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
-  else
-    local_joint_fast_kernel<false><<<dim3(gx, npairs), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

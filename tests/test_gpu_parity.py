@@ -119,6 +119,9 @@ LOCAL_CASES = [
     (2, 10, 56, 64, 3, 512),      # K=10, p=3 (7 x 7 kernels, single backward launch)
     (1, 10, 224, 224, 3, 512),    # ACDC Up_conv2 shape with the yaml padding of 3
     (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows
+    (2, 16, 40, 64, 1, 512),      # channel blocks of 8 (K a multiple of 8, not of 10)
+    (1, 128, 24, 32, 1, 512),     # config-5 cluster count (K = 128): 16 x 16 channel-block pairs
+    (1, 24, 20, 36, 3, 512),      # blocks of 8 with the 7 x 7 window (backward; the joint takes the generic kernel)
     (1, 10, 20, 512, 1, 1024),    # wide map: the backward cuts it into column panels
     (1, 20, 18, 300, 3, 1024),    # wide map, 7 x 7, last panel narrower
     (2, 20, 56, 56, 1, 1024),     # K=20, p=1
