@@ -1,0 +1,297 @@
+// Local IIC joint on the 5th-generation tensor cores (tcgen05 / UMMA) for wide cluster heads: K = 128 channels,
+// 3 x 3 window (padding 1) -- BASELINE config 5, "tensor cores only when K is large enough to be a real dense
+// contraction" (north_star).  Reference arithmetic: contrastyou/losses/iic_loss.py:120-123
+//   J[dy][dx][i][j] = sum_{n,u,v} x[n,i,u+dy-1,v+dx-1] * y[n,j,u,v]          (x zero outside the map)
+// = nine 128 x 128 x Npix contractions.  fp32-level accuracy with TF32 operands comes from the 3 x TF32 split:
+// the tensor core reads the top 19 bits of an fp32 word, so the raw value is its own "hi" part; lo = v - trunc19(v)
+// is exact in fp32, and hi*hi + hi*lo + lo*hi leaves a relative error of ~2^-21 per product.
+//
+// One CTA = one displacement row dy (blockIdx.y) and a contiguous share of the 16-pixel row segments ("k-blocks",
+// the reduction dimension of the MMA).  Per k-block:
+//   warp 0     TMA producer: x rows shifted by dy as an unswizzled [128 ch x 24 px] box (columns c0-4 .. c0+19; the
+//              hardware zero fill is the conv padding) and y as a 64-byte-swizzled [128 ch x 16 px] box -> raw ring.
+//              (A swizzled box cannot start at a column that is not a multiple of 4 floats -- the copy faults -- so
+//              the +-1 column shifts are made by the transform warps, not by TMA coordinates.)
+//   warps 4-7  transform: thread = channel row; writes the eight K-major SWIZZLE_64B operand tiles of the k-block
+//              (x hi/lo at the three column shifts, y hi/lo) into the operand ring, fences them for the async proxy.
+//   warp 1     one elected lane issues 3 (dx) x 2 (8-pixel slices) x 3 (split terms) tcgen05.mma.kind::tf32
+//              M = N = 128 into three 128-column TMEM accumulators; tcgen05.commit frees the operand slot.
+// Epilogue: warps 4-7 read the accumulators with tcgen05.ld (lane = x channel i, column = y channel j) and write
+// the CTA's partial-joint slot; reduce_partials_kernel (local_fwd.cu) adds the slots in fp64 in a fixed order.
+// To bound the fp32 accumulation run in TMEM the k-blocks are processed in segments: after each segment the
+// accumulators are drained into the slot (first segment stores, later ones add).
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "tma.cuh"
+
+namespace iic {
+namespace fwdtc {
+
+constexpr int KC = 128;                        // channels = UMMA M = UMMA N
+constexpr int PXB = 16;                        // pixels per k-block (64-byte operand rows)
+constexpr int XRW = 24;                        // staged x columns per k-block: c0-4 .. c0+19
+constexpr int TILE_BYTES = KC * PXB * 4;       // 8192
+constexpr int XRAW_BYTES = KC * XRW * 4;       // 12288
+constexpr int RAW_BYTES = XRAW_BYTES + TILE_BYTES;   // 20480
+constexpr int NRAW = 4;
+constexpr int OP_TILES = 8;                    // x hi (dx 0..2), y hi, x lo (dx 0..2), y lo
+constexpr int OP_BYTES = OP_TILES * TILE_BYTES;      // 65536
+constexpr int NOP = 2;
+constexpr int SMEM_BYTES = NRAW * RAW_BYTES + NOP * OP_BYTES + 1024;   // + alignment slack
+constexpr int NTHREADS = 256;
+
+__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+  // K-major, SWIZZLE_64B: 64-byte rows, 8-row groups 512 bytes apart
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                     // leading byte offset (unused for swizzled K-major)
+  d |= (uint64_t)(512 >> 4) << 32;            // stride byte offset
+  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
+  d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
+  return d;
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
+
+struct Params {
+  int B, H, W, segs_w;          // segs_w = W / 16
+  float* partial;               // [gridDim.x][9][128][128]
+  int seg_kb;                   // k-blocks per accumulation segment
+};
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, const Params P) {
+  extern __shared__ __align__(1024) unsigned char smem_dyn[];
+  __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], op_full[NOP], op_empty[NOP], accum_bar, drained_bar;
+  __shared__ uint32_t tmem_base_s;
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~(uintptr_t)1023);
+  unsigned char* raw_ring = smem + NOP * OP_BYTES;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int dy = blockIdx.y;
+  const int nkb_total = P.B * P.H * P.segs_w;
+  const int kb0 = (int)((long long)blockIdx.x * nkb_total / gridDim.x);
+  const int kb1 = (int)((long long)(blockIdx.x + 1) * nkb_total / gridDim.x);
+  const int nkb = kb1 - kb0;
+  const int SEG_KB = P.seg_kb;
+  const int nseg = (nkb + SEG_KB - 1) / SEG_KB;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
+    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], 4); mbar_init(&op_empty[s], 1); }
+    mbar_init(&accum_bar, 1);
+    mbar_init(&drained_bar, 4);
+    mbar_fence_init();
+  }
+  if (wid == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;");
+  const uint32_t tmem_base = tmem_base_s;
+
+  if (wid == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      tma_prefetch_desc(&mapx);
+      tma_prefetch_desc(&mapy);
+      const int per_img = P.H * P.segs_w;
+      for (int k = 0; k < nkb; ++k) {
+        const int s = k % NRAW;
+        if (k >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(k / NRAW) & 1u) ^ 1u, 1);
+        const int kb = kb0 + k;
+        const int n = kb / per_img;
+        const int rem = kb - n * per_img;
+        const int u = rem / P.segs_w, c0 = (rem - u * P.segs_w) * PXB;
+        unsigned char* st = raw_ring + (size_t)s * RAW_BYTES;
+        mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
+        tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, u + dy - 1, 0, n);
+        tma_load_4d(st + XRAW_BYTES, &mapy, &raw_full[s], c0, u, 0, n);
+      }
+    }
+  } else if (wid == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
+    for (int k = 0; k < nkb; ++k) {
+      const int o = k % NOP;
+      const int kin = k % SEG_KB;               // position inside the accumulation segment
+      if (kin == 0 && k > 0) {                  // the epilogue warps must have drained the previous segment
+        mbar_wait(&drained_bar, (unsigned)(k / SEG_KB - 1) & 1u, 6);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+      }
+      mbar_wait(&op_full[o], (unsigned)(k / NOP) & 1u, 5);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      if (lane == 0) {
+        const uint32_t sb = smem_u32(smem + (size_t)o * OP_BYTES);
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const uint32_t d_tmem = tmem_base + dx * KC;
+#pragma unroll
+          for (int ks = 0; ks < PXB / 8; ++ks) {
+            const uint64_t a_hi = make_desc_sw64(sb + dx * TILE_BYTES + ks * 32);
+            const uint64_t a_lo = make_desc_sw64(sb + (4 + dx) * TILE_BYTES + ks * 32);
+            const uint64_t b_hi = make_desc_sw64(sb + 3 * TILE_BYTES + ks * 32);
+            const uint64_t b_lo = make_desc_sw64(sb + 7 * TILE_BYTES + ks * 32);
+            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kin > 0 || ks > 0) ? 1u : 0u);   // small terms first
+            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
+            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+          }
+        }
+        umma_commit(&op_empty[o]);                              // frees the operand slot when these MMAs have read it
+        if (kin == SEG_KB - 1 || k == nkb - 1) umma_commit(&accum_bar);
+      }
+      __syncwarp();
+    }
+  } else if (wid >= 4) {
+    // ===== transform warps, and the epilogue =====
+    const int r = threadIdx.x - 128;                            // channel row
+    const int sw = (r >> 1) & 3;                                // SWIZZLE_64B: 16-byte chunk index ^= address bits 7..8
+    const int q4 = wid & 3;                                     // this warp reads TMEM lanes 32*q4 .. 32*q4+31
+    float* slot = P.partial + (size_t)blockIdx.x * (9 * KC * KC);
+    for (int k = 0; k < nkb; ++k) {
+      const int s = k % NRAW, o = k % NOP;
+      mbar_wait(&raw_full[s], (unsigned)(k / NRAW) & 1u, 3);
+      if (k >= NOP) mbar_wait(&op_empty[o], ((unsigned)(k / NOP) & 1u) ^ 1u, 2);
+      const unsigned char* raw = raw_ring + (size_t)s * RAW_BYTES;
+      unsigned char* op = smem + (size_t)o * OP_BYTES;
+      {
+        float v[XRW];
+        const float4* xr = reinterpret_cast<const float4*>(raw + r * (XRW * 4));
+#pragma unroll
+        for (int q = 0; q < XRW / 4; ++q) {
+          const float4 t = xr[q];
+          v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            // operand pixel e of chunk c is x column c0 + 4c + e + dx - 1 = staged column 4c + e + dx + 3
+            const float4 hi = make_float4(v[4 * c + dx + 3], v[4 * c + dx + 4], v[4 * c + dx + 5], v[4 * c + dx + 6]);
+            const int off = r * 64 + ((c ^ sw) << 4);
+            *reinterpret_cast<float4*>(op + dx * TILE_BYTES + off) = hi;
+            *reinterpret_cast<float4*>(op + (4 + dx) * TILE_BYTES + off) = tf32_lo4(hi);
+          }
+        // y arrives swizzled: the physical positions carry over unchanged
+        const float4* yr = reinterpret_cast<const float4*>(raw + XRAW_BYTES + r * 64);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float4 t = yr[c];
+          *reinterpret_cast<float4*>(op + 3 * TILE_BYTES + r * 64 + (c << 4)) = t;
+          *reinterpret_cast<float4*>(op + 7 * TILE_BYTES + r * 64 + (c << 4)) = tf32_lo4(t);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&op_full[o]);
+        mbar_arrive(&raw_empty[s]);
+      }
+      if ((k % SEG_KB) == SEG_KB - 1 || k == nkb - 1) {
+        // ---- drain the accumulators of this segment into the slot ----
+        const int seg = k / SEG_KB;
+        mbar_wait(&accum_bar, (unsigned)seg & 1u, 4);
+        asm volatile("tcgen05.fence::after_thread_sync;");
+        for (int dx = 0; dx < 3; ++dx)
+          for (int ch = 0; ch < KC / 32; ++ch) {
+            uint32_t a[32];
+            const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + dx * KC + ch * 32;
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+                : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                  "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15]),
+                  "=r"(a[16]), "=r"(a[17]), "=r"(a[18]), "=r"(a[19]), "=r"(a[20]), "=r"(a[21]), "=r"(a[22]), "=r"(a[23]),
+                  "=r"(a[24]), "=r"(a[25]), "=r"(a[26]), "=r"(a[27]), "=r"(a[28]), "=r"(a[29]), "=r"(a[30]), "=r"(a[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+            float4* dst = reinterpret_cast<float4*>(slot + ((size_t)(dy * 3 + dx) * KC + r) * KC + ch * 32);
+            if (seg == 0) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                dst[j] = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
+                                     __uint_as_float(a[4 * j + 3]));
+            } else {
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                float4 t = dst[j];
+                t.x += __uint_as_float(a[4 * j]); t.y += __uint_as_float(a[4 * j + 1]);
+                t.z += __uint_as_float(a[4 * j + 2]); t.w += __uint_as_float(a[4 * j + 3]);
+                dst[j] = t;
+              }
+            }
+          }
+        asm volatile("tcgen05.fence::before_thread_sync;");
+        __syncwarp();
+        if (lane == 0 && seg + 1 < nseg) mbar_arrive(&drained_bar);
+      }
+    }
+    if (nkb == 0) {
+      float4* dst = reinterpret_cast<float4*>(slot + (size_t)dy * 3 * KC * KC);
+      for (int e = r; e < 3 * KC * KC / 4; e += 128) dst[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;");
+  __syncthreads();
+  if (wid == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+}
+
+static bool make_map(CUtensorMap* map, const float* base, int B, int H, int W, long long sn, long long sc, long long sh,
+                     int box_w, CUtensorMapSwizzle swz) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return false;
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  if ((sh * 4) % 16 != 0 || (sc * 4) % 16 != 0 || (sn * 4) % 16 != 0) return false;
+  cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)KC, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)sh * 4, (cuuint64_t)sc * 4, (cuuint64_t)sn * 4};
+  cuuint32_t box[4] = {(cuuint32_t)box_w, 1, (cuuint32_t)KC, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
+             CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+}  // namespace fwdtc
+
+// Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
+int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial, int max_ctas,
+                       int* ncta, cudaStream_t st) {
+  using namespace fwdtc;
+  if (K != KC || pad != 1 || W % PXB != 0 || max_ctas < 1) return -1;
+  CUtensorMap mx, my;
+  if (!make_map(&mx, x, B, H, W, x_sn, x_sc, x_sh, XRW, CU_TENSOR_MAP_SWIZZLE_NONE)) return -1;
+  if (!make_map(&my, y, B, H, W, y_sn, y_sc, y_sh, PXB, CU_TENSOR_MAP_SWIZZLE_64B)) return -1;
+  const int sms = sm_count_cached(current_device());
+  if (sms <= 0) return -1;
+  const long long nkb = (long long)B * H * (W / PXB);
+  int gx = sms / 3;                                   // three displacement rows per share of the pixels
+  if (gx > max_ctas) gx = max_ctas;
+  if (gx > nkb) gx = (int)nkb;
+  if (gx < 1) gx = 1;
+  static bool attr_set = false;
+  if (!attr_set) {
+    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    attr_set = true;
+  }
+  Params P{B, H, W, W / PXB, partial, getenv("IIC_TC_SEG") ? atoi(getenv("IIC_TC_SEG")) : 256};
+  local_joint_tc_kernel<<<dim3(gx, 3), NTHREADS, SMEM_BYTES, st>>>(mx, my, P);
+  IIC_CHECK_CUDA(cudaGetLastError());
+  *ncta = gx;
+  return 0;
+}
+
+}  // namespace iic
