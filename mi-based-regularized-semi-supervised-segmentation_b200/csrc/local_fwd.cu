@@ -249,7 +249,10 @@ __global__ void __launch_bounds__(384, 1) local_joint_kernel(const LocalFwdParam
 // J[p][e] = sum over CTAs of partial[p][cta][e] in float64, in a fixed order: a block is 32 slot groups x
 // 32 consecutive elements (coalesced 128-byte reads); group g adds slots g, g+32, ... in order, then the 32
 // group sums are added in order.
+// TC_LAYOUT: the slots come from local_joint_tc_kernel (local_fwd_tc.cu) in its coalesced order
+// [d][32-column chunk][float4 of the chunk][row i][4] with K = 128; J is written in the standard [d][i][j] order.
 constexpr int RED_GROUPS = 32;
+template <bool TC_LAYOUT>
 __global__ void __launch_bounds__(RED_GROUPS * 32)
 reduce_partials_kernel(const float* __restrict__ partial, int ncta, long long E, double* __restrict__ J) {
   __shared__ double sm[RED_GROUPS][33];
@@ -272,7 +275,12 @@ reduce_partials_kernel(const float* __restrict__ partial, int ncta, long long E,
     double t = 0;
 #pragma unroll
     for (int g = 0; g < RED_GROUPS; ++g) t += sm[g][le];
-    J[(size_t)patch * E + e] = t;
+    long long dst = e;
+    if (TC_LAYOUT) {
+      const long long w = e & 3, i = (e >> 2) & 127, jv = (e >> 9) & 7, ch = (e >> 12) & 3, d = e >> 14;
+      dst = (d * 128 + i) * 128 + ch * 32 + jv * 4 + w;
+    }
+    J[(size_t)patch * E + dst] = t;
   }
 }
 
@@ -376,6 +384,9 @@ int local_joint_fast_try(const float* x, long long x_sn, long long x_sc, long lo
 int local_joint_fast7_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                           long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                           float* partial, int max_ctas, int* ncta, cudaStream_t st);
+int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
+                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
+                       float* partial, int max_ctas, int* ncta, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -411,6 +422,19 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
   if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
     int ncta = 0, checked = 0;
+    // wide cluster heads (K = 128): tcgen05 3xTF32 contraction (local_fwd_tc.cu)
+    if (!getenv("IIC_B200_NO_TC")) {
+      const int rc_tc = local_joint_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
+                                           pl.slots_per_patch, &ncta, st);
+      if (rc_tc > 0) return rc_tc;
+      if (rc_tc == 0) {
+        if (int e = simplex_pass()) return e;
+        dim3 rgrid((unsigned)((E + 31) / 32), 1);
+        reduce_partials_kernel<true><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+        IIC_CHECK_CUDA(cudaGetLastError());
+        return 0;
+      }
+    }
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                         (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, 0, 1.f, st);
@@ -425,7 +449,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
     if (rc == 0) {
       if (int e = simplex_pass()) return e;
       dim3 rgrid((unsigned)((E + 31) / 32), 1);
-      reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+      reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
       IIC_CHECK_CUDA(cudaGetLastError());
       return 0;
     }
@@ -482,7 +506,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   }
   {
     dim3 rgrid((unsigned)((E + 31) / 32), pl.n_patches);
-    reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, pl.ctas_per_patch,
+    reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, pl.ctas_per_patch,
                                                              (long long)E, J_out);
     IIC_CHECK_CUDA(cudaGetLastError());
   }
@@ -515,7 +539,7 @@ extern "C" int iic_local_joint_from_logits(const float* lx, long long x_sn, long
   }
   if (rc > 0) return rc;
   dim3 rgrid((unsigned)((E + 31) / 32), 1);
-  reduce_partials_kernel<<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
+  reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -120,7 +120,9 @@ LOCAL_CASES = [
     (1, 10, 224, 224, 3, 512),    # ACDC Up_conv2 shape with the yaml padding of 3
     (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows
     (2, 16, 40, 64, 1, 512),      # channel blocks of 8 (K a multiple of 8, not of 10)
-    (1, 128, 24, 32, 1, 512),     # config-5 cluster count (K = 128): 16 x 16 channel-block pairs
+    (1, 128, 24, 32, 1, 512),     # config-5 cluster count (K = 128): tcgen05 joint (W % 16 == 0)
+    (3, 128, 112, 112, 1, 512),   # K = 128, long enough for two TMEM accumulation segments per CTA
+    (1, 128, 20, 40, 1, 512),     # K = 128 with W % 16 != 0: FFMA2 blocks of 8
     (1, 24, 20, 36, 3, 512),      # blocks of 8 with the 7 x 7 window (backward; the joint takes the generic kernel)
     (1, 10, 20, 512, 1, 1024),    # wide map: the backward cuts it into column panels
     (1, 20, 18, 300, 3, 1024),    # wide map, 7 x 7, last panel narrower
@@ -161,6 +163,23 @@ def test_joint_kernel_vs_oracle(iic, cuda_device, B, K, H, W, pad):
     ref = O.local_joint(x, y, pad)
     assert J.shape == (1, 2 * pad + 1, 2 * pad + 1, K, K)
     assert relmax(J[0].cpu().numpy(), ref) < 2e-6
+
+
+def test_joint_tensor_core_vs_oracle(iic, cuda_device):
+    """K = 128: the tcgen05 3xTF32 joint.  The tensor core accumulates in fp32 with truncation, which scales
+    all of J by (1 - b) with b <= 1e-5 for the 512-pixel accumulation runs used (csrc/local_fwd_tc.cu); the
+    normalisation of iic_loss.py:129 removes a uniform factor, so the entries are compared after dividing by
+    the respective totals (2e-6) and the factor itself is bounded separately."""
+    B, K, H, W, pad = 4, 128, 96, 112, 1
+    rng = np.random.default_rng(4242)
+    x, y = views(rng, B, K, H, W)
+    J = torch.ops.iic_b200.local_joint(torch.from_numpy(x).to(cuda_device), torch.from_numpy(y).to(cuda_device),
+                                       None, pad, H, W, H, W)[0].cpu().numpy()
+    ref = O.local_joint(x, y, pad)
+    scale = J.sum() / ref.sum()
+    print(f"uniform factor 1 - {1 - scale:.2e}; normalised max-norm err {relmax(J / J.sum(), ref / ref.sum()):.2e}")
+    assert abs(1 - scale) < 1.5e-5
+    assert relmax(J / J.sum(), ref / ref.sum()) < 2e-6
 
 
 def _logit_views(rng, B, K, H, W):

@@ -74,7 +74,8 @@ int main(int argc, char** argv) {
             }
           }
         double got = 0.0;
-        for (int c = 0; c < ncta; ++c) got += (double)ho[((size_t)c * 9 + d) * KC * KC + (size_t)i * KC + j];
+        const size_t e_tc = ((((size_t)d * 4 + j / 32) * 8 + (j % 32) / 4) * KC + i) * 4 + (j % 4);   // slot order of the kernel
+        for (int c = 0; c < ncta; ++c) got += (double)ho[(size_t)c * 9 * KC * KC + e_tc];
         const double ae = fabs(got - ref), re = ae / fmax(fabs(ref), 1e-30);
         sum_rel += (got - ref) / ref; sum_rel2 += (got - ref) / ref * (got - ref) / ref; ++cnt;
         if (re > max_rel) max_rel = re;
