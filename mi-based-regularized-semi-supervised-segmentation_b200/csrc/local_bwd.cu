@@ -207,6 +207,9 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
                        int from_logits, float inv_temp, cudaStream_t st);
+int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                     long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                     const float* grad_loss, float* gx, float* gy, cudaStream_t st);
 }
 using namespace iic;
 
@@ -231,6 +234,12 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
 
   // fast path: one patch, no mask, TMA-describable rows, small window (local_bwd_tma.cu)
   if (n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
+    // wide cluster heads (K = 128): tcgen05 3xTF32 sweeps (local_bwd_tc.cu)
+    if (!getenv("IIC_B200_NO_TC")) {
+      const int rc_tc = local_bwd_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                         gx, gy, st);
+      if (rc_tc >= 0) return rc_tc;
+    }
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
                                       grad_loss, gx, gy, sms, 0, 1.f, st);

@@ -1,6 +1,6 @@
 """Time the local IIC loss (fwd+bwd, probability inputs) over the BASELINE.json shapes on one GPU.
 
-    python tools/shape_sweep.py
+    python tools/shape_sweep.py [substring of the shape name]
 
 Prints one JSON line per shape: Mpx/s, fraction of the HBM roofline (24*K bytes per pixel over the
 measured copy bandwidth) and fraction of the FP32 FMA peak (6*K^2*T^2 flop per pixel).
@@ -21,6 +21,7 @@ SHAPES = [  # name, B, K, H, W, pad
     ("cfg3  Up_conv2 K=20 p=3 (8/GPU)", 8, 20, 224, 224, 3),
     ("cfg4  512^2 K=20 p=3 (16/GPU)", 16, 20, 512, 512, 3),
     ("cfg5  K=128 p=1 (4/GPU sample)", 4, 128, 224, 224, 1),
+    ("cfg5  K=128 p=1 (32/GPU, full)", 32, 128, 224, 224, 1),
 ]
 dev = torch.device("cuda:0")
 iic_b200.set_check_mode("deferred")
@@ -29,7 +30,10 @@ try:
     hbm = float(peaks["hbm_gbs"])
 except Exception:  # noqa: BLE001
     hbm = 6650.0
+only = sys.argv[1] if len(sys.argv) > 1 else ""
 for name, B, K, H, W, pad in SHAPES:
+    if only not in name:
+        continue
     g = torch.Generator(device=dev).manual_seed(1)
     base = torch.nn.functional.interpolate(torch.randn(B, K, H // 8, W // 8, device=dev, generator=g) * 3, size=(H, W), mode="bilinear")
     x = (base + 0.5 * torch.randn(B, K, H, W, device=dev, generator=g)).softmax(1).requires_grad_(True)
