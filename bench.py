@@ -56,6 +56,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+def bf16_peak():
+    """Measured dense bf16 TFLOP/s (burst figure: the kernel is timed alone), else the profiling guide's fallback."""
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p)).get("bf16_tflops", 1590.0))
+    return 1590.0
+
+
 # ---------------------------------------------------------------------------------------------------
 # clocks sampler (nvidia-smi during the timed region)
 # ---------------------------------------------------------------------------------------------------
@@ -367,6 +375,26 @@ def run_b200(args):
             "ms": round(ms_uda, 4), "gb_s": round(uda_bytes / (ms_uda * 1e-3) / 1e9, 1),
             "hbm_frac": round(uda_bytes / (ms_uda * 1e-3) / 1e9 / hbm_peak, 4),
             "note": "32 MB working set: L2-resident between replays, so this is an upper bound on HBM efficiency"}
+        del l1, l2, lbase, u1, u2
+        # config 5 (wide cluster head, K = 128): the tcgen05 3xTF32 joint and backward sweeps, per-GPU batch 32
+        B5, K5 = 32, 128
+        b5 = torch.nn.functional.interpolate(torch.randn(B5, K5, H // 8, W // 8, device=dev, generator=gl) * 3,
+                                             size=(H, W), mode="bilinear", align_corners=False)
+        x5 = (b5 + 0.5 * torch.randn(B5, K5, H, W, device=dev, generator=gl)).softmax(1).requires_grad_(True)
+        y5 = (b5 + 0.5 * torch.randn(B5, K5, H, W, device=dev, generator=gl)).softmax(1).requires_grad_(True)
+        del b5
+        ms5 = timed_graph(lambda: torch.autograd.grad(local(x5, y5), (x5, y5)), reps=10)
+        px5 = B5 * H * W
+        tf32_peak = bf16_peak() / 2.0
+        extra["config5_k128_tensor_core"] = {
+            "what": "local IIC fwd+bwd at K=128, padding 1, (32,128,224,224) per GPU: tcgen05.mma kind::tf32 with the "
+                    "3xTF32 split (fp32-level accuracy), TMEM accumulators",
+            "ms": round(ms5, 4), "mpx_s": round(px5 / (ms5 * 1e-3) / 1e6, 1),
+            "hbm_frac": round(24.0 * K5 * px5 / (ms5 * 1e-3) / 1e9 / hbm_peak, 4),
+            "fp32_equiv_tflops": round(6.0 * K5 * K5 * 9 * px5 / (ms5 * 1e-3) / 1e12, 1),
+            "tf32_issued_tflops": round(3 * 6.0 * K5 * K5 * 9 * px5 / (ms5 * 1e-3) / 1e12, 1),
+            "tensor_frac_of_half_measured_bf16": round(3 * 6.0 * K5 * K5 * 9 * px5 / (ms5 * 1e-3) / 1e12 / tf32_peak, 4)}
+        del x5, y5
     except Exception as e:  # noqa: BLE001
         extra["error"] = f"{type(e).__name__}: {e}"
 

@@ -75,6 +75,7 @@ struct Params {
   const float* wimg;            // [16 slices][9 taps][hi, lo][2 chunks][128 out][4 in]
   const float* grad_loss;       // device scalar or null
   float* out;                   // (B, 128, H, W) dense
+  int dbg;                      // bring-up switches (IIC_TC_DBG): 1 no source loads, 2 no weight loads, 4 no transform, 8 no stores
 };
 
 // Wc[cin][tap][128] (iic_local_epilogue) -> operand image, split into tf32 hi / lo
@@ -144,6 +145,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             if (t >= 1) mbar_wait(&raw_empty[h], ((unsigned)t & 1u) ^ 1u, 1);
+            if (P.dbg & 1) { mbar_arrive(&raw_full[h]); continue; }
             mbar_arrive_expect_tx(&raw_full[h], raw_half_bytes);
             tma_load_4d(raw_ring + h * RAW_HALF_MAX, &maps, &raw_full[h], -4, r - 1 + 2 * h, js * SL, n);
           }
@@ -157,6 +159,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
       for (int w = 0; w < total; ++w) {
         const int s = w % NW;
         if (w >= NW) mbar_wait(&w_empty[s], ((unsigned)(w / NW) & 1u) ^ 1u, 2);
+        if (P.dbg & 2) { mbar_arrive(&w_full[s]); continue; }
         mbar_arrive_expect_tx(&w_full[s], W_TILE);
         bulk_load(w_ring + s * W_TILE, P.wimg + (size_t)(w % (NSL * 9)) * (W_TILE / 4), W_TILE, &w_full[s]);
       }
@@ -220,7 +223,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
       for (int h = 0; h < 2; ++h) {
         mbar_wait(&raw_full[h], (unsigned)t & 1u, 4);
         const float* raw = reinterpret_cast<const float*>(raw_ring + h * RAW_HALF_MAX);
-        for (int e = tid; e < 2 * SW; e += 128) {
+        for (int e = tid; e < ((P.dbg & 4) ? 0 : 2 * SW); e += 128) {
           const int row = e >= SW ? 1 : 0;
           const int px = e - row * SW;
           float v[SL];
@@ -272,7 +275,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
                   "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                 : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < P.W) {
+            if (c < P.W && !(P.dbg & 8)) {
 #pragma unroll
               for (int o = 0; o < 32; ++o) dst[(size_t)(ch * 32 + o) * plane] = g * __uint_as_float(v[o]);
             }
@@ -344,9 +347,10 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y);
   IIC_CHECK_CUDA(cudaGetLastError());
-  Params Pgx{B, H, W, n_items, img_x, grad_loss, gx};     // dL/dx from y
+  const int dbg = getenv("IIC_TC_DBG") ? atoi(getenv("IIC_TC_DBG")) : 0;
+  Params Pgx{B, H, W, n_items, img_x, grad_loss, gx, dbg};     // dL/dx from y
   local_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(my, Pgx);
-  Params Pgy{B, H, W, n_items, img_y, grad_loss, gy};     // dL/dy from x
+  Params Pgy{B, H, W, n_items, img_y, grad_loss, gy, dbg};     // dL/dy from x
   local_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, Pgy);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
