@@ -5,7 +5,11 @@
 // Wc = the coefficient tensors iic_local_epilogue writes (Wx with src = y gives dL/dx, Wy with src = x gives dL/dy).
 //
 // GEMM view: M = pixels (128 per MMA, TMEM lanes), N = 128 output channels (TMEM columns), reduction = input channels
-// (8 per tcgen05.mma.kind::tf32) x 9 taps.  fp32-level accuracy from the 3 x TF32 split (see local_fwd_tc.cu).
+// (8 per step) x 9 taps.  fp32-level accuracy from a split product: with ah = the top 19 bits of a (what kind::tf32
+// reads of an fp32 word) and al = a - ah (exact), a*w = ah*wh + (al*wh + ah*wl) + al*wl.  The main term is one
+// tcgen05.mma.kind::tf32 (K = 8 channels); the two correction terms, 2^-11 of it, only need ~8 bits and share ONE
+// tcgen05.mma.kind::f16 on bf16 copies with K = 16 = [al | ah] x [wh | wl]; al*wl (2^-22) is dropped.  Two MMAs per
+// step instead of the three of a plain 3xTF32 scheme.
 //
 // The +-1 column shifts of the taps are start-address shifts of the A descriptor: the transform warps re-lay every
 // staged row pixel-major, as a K-major operand WITHOUT swizzle whose rows (pixels) are 16 bytes = 4 channels and whose
@@ -16,10 +20,12 @@
 // One CTA per SM walks a contiguous share of the (image, row pair) work items.  Per item the accumulators are the four
 // 128-column TMEM blocks [output row 0/1][pixel tile 0/1]; the 128 input channels stream through in 16 slices of 8:
 //   warp 0     TMA: the slice's four source rows r-1 .. r+2 as two [8 ch x 2 rows x (W+8) px] boxes (zero fill = padding)
-//   warp 3     bulk copies of the slice's nine 8 KB weight tiles (hi and lo, already in operand order) into a ring of 6
-//   warps 4-7  transform: [ch][row][px] fp32 -> [row][4-channel chunk][px][4] hi and lo operand images
-//   warp 1     one lane issues 9 taps x 2 rows x 2 tiles x 3 split terms MMAs per slice
+//   warp 3     bulk copies of the slice's nine 8 KB weight tiles (fp32 + bf16 parts, already in operand order), ring of 6
+//   warps 4-7  transform: [ch][row][px] fp32 -> [row][chunk][px][16 B] operand images (fp32: 4 channels per
+//              chunk; bf16: chunk 0 = al, chunk 1 = ah of the 8 channels)
+//   warp 1     one lane issues 9 taps x 2 rows x 2 tiles x 2 MMAs per slice
 //   warps 8-11 epilogue after the 16th slice: tcgen05.ld (lane = pixel, columns = channels), scale by g, coalesced stores
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -34,10 +40,10 @@ constexpr int NSL = KC / SL;             // 16 slices
 constexpr int APX = 272;                 // pixels per row buffer; buffer pixel b holds column b - 8, so that the window of the
                                          // centre tap starts on a 128-byte boundary (rows up to b = 264 are read)
 constexpr int MAXW = 248;                // widest map: W + 8 staged columns <= 256 (TMA box limit)
-constexpr int A_PART = 4 * 2 * APX * 16; // one of hi / lo: 4 rows x 2 chunks x APX pixels x 16 B = 34816
+constexpr int A_PART = 4 * 2 * APX * 16; // fp32 part / bf16 correction part: 4 rows x 2 chunks x APX pixels x 16 B = 34816
 constexpr int A_SLOT = 2 * A_PART;       // 69632
 constexpr int NA = 2;
-constexpr int W_TILE = 2 * 2 * KC * 16;  // hi, lo x 2 chunks x 128 channels x 16 B = 8192
+constexpr int W_TILE = 2 * 2 * KC * 16;  // fp32 part, bf16 part x 2 chunks x 128 channels x 16 B = 8192
 constexpr int NW = 6;
 constexpr int RAW_HALF_MAX = SL * 2 * 256 * 4;   // 16384 (8 ch x 2 rows x up to 256 px)
 constexpr int SMEM_BYTES = NA * A_SLOT + NW * W_TILE + 2 * RAW_HALF_MAX + 1024;
@@ -67,35 +73,56 @@ __device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint3
                ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
 }
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__host__ __device__ __forceinline__ float tf32_hi(float v) {
+#ifdef __CUDA_ARCH__
+  return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+#else
+  uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; memcpy(&v, &u, 4); return v;
+#endif
+}
+__device__ __forceinline__ float tf32_lo(float v) { return v - tf32_hi(v); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a at the lower address
+  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+// eight fp32 values -> 16 bytes of bf16; LO selects the tf32 remainder instead of the value
+template <bool LO>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  float t[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
+  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
+}
 
 struct Params {
   int B, H, W;
   int n_items;                  // B * ceil(H / 2)
-  const float* wimg;            // [16 slices][9 taps][hi, lo][2 chunks][128 out][4 in]
+  const float* wimg;            // [16 slices][9 taps]{fp32 [2 chunks][128 out][4 in], bf16 [wh, wl][128 out][8 in]}
   const float* grad_loss;       // device scalar or null
   float* out;                   // (B, 128, H, W) dense
   int dbg;                      // bring-up switches (IIC_TC_DBG): 1 no source loads, 2 no weight loads, 4 no transform, 8 no stores
 };
 
-// Wc[cin][tap][128] (iic_local_epilogue) -> operand image, split into tf32 hi / lo
+// Wc[cin][tap][128] (iic_local_epilogue) -> operand image: the fp32 tile and the bf16 correction tile [wh | wl]
 __global__ void weight_image_kernel(const float* __restrict__ Wc, float* __restrict__ img) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // one (slice, tap, chunk, out) per thread: 4 input channels
-  if (e >= NSL * 9 * 2 * KC) return;
-  const int o = e % KC, chunk = (e / KC) % 2, tap = (e / (2 * KC)) % 9, js = e / (2 * KC * 9);
-  float4 hi, lo;
-  float* h = &hi.x;
-  float* l = &lo.x;
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;      // one (slice, tap, out) per thread: 8 input channels
+  if (e >= NSL * 9 * KC) return;
+  const int o = e % KC, tap = (e / KC) % 9, js = e / (KC * 9);
+  float v[SL];
 #pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    const int cin = js * SL + chunk * 4 + q;
-    const float v = Wc[((size_t)cin * 9 + tap) * KC + o];
-    h[q] = v;
-    l[q] = tf32_lo(v);
-  }
-  float4* dst = reinterpret_cast<float4*>(img) + ((size_t)(js * 9 + tap) * 2) * (2 * KC);
-  dst[chunk * KC + o] = hi;
-  dst[2 * KC + chunk * KC + o] = lo;
+  for (int q = 0; q < SL; ++q) v[q] = Wc[((size_t)(js * SL + q) * 9 + tap) * KC + o];
+  float4* dst = reinterpret_cast<float4*>(img) + (size_t)(js * 9 + tap) * (W_TILE / 16);
+  dst[o] = make_float4(v[0], v[1], v[2], v[3]);
+  dst[KC + o] = make_float4(v[4], v[5], v[6], v[7]);
+  reinterpret_cast<uint4*>(dst)[2 * KC + o] = pack8<false>(v);     // wh (pairs with al)
+  reinterpret_cast<uint4*>(dst)[3 * KC + o] = pack8<true>(v);      // wl (pairs with ah)
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -167,6 +194,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
   } else if (wid == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
+    const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
     for (int i = 0; i < nit; ++i) {
       const int item = it0 + i;
       const int n = item / pairs, r = (item - n * pairs) * 2;
@@ -179,28 +207,41 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
         const int t = i * NSL + js;
         const int a = t % NA;
         mbar_wait(&a_full[a], (unsigned)(t / NA) & 1u, 5);
-        const uint32_t ab = smem_u32(a_ring + (size_t)a * A_SLOT);
+        // The issuing lane is latency-bound on its own instruction stream, so every descriptor is a 64-bit base plus a
+        // compile-time constant (in 16-byte units): the tap / row / tile loops are fully unrolled.
+        const uint64_t a_base = make_desc_kmajor_noswz(smem_u32(a_ring + (size_t)a * A_SLOT), APX * 16);
+        const int w0 = t * 9;
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const int w = t * 9 + tap;
+          const int w = w0 + tap;
           const int s = w % NW;
           mbar_wait(&w_full[s], (unsigned)(w / NW) & 1u, 7);
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
+            constexpr int A_CR = A_PART / 16, B_CR = 2 * KC;          // offsets of the bf16 parts, 16-byte units
             const int ty = tap / 3, tx = tap - ty * 3;
-            const uint32_t wb = smem_u32(w_ring + (size_t)s * W_TILE);
-            const uint64_t b_hi = make_desc_kmajor_noswz(wb, KC * 16);
-            const uint64_t b_lo = make_desc_kmajor_noswz(wb + 2 * KC * 16, KC * 16);
-            for (int orow = 0; orow < nrow; ++orow)
-              for (int mt = 0; mt < ntile; ++mt) {
-                // output pixel c of row r+orow reads source row r+orow+ty-1 (buffer row orow+ty), column c+tx-1 (buffer pixel c+tx+7)
-                const uint32_t aoff = (uint32_t)(((orow + ty) * 2) * APX + mt * 128 + tx + 7) * 16u;
-                const uint64_t a_hi = make_desc_kmajor_noswz(ab + aoff, APX * 16);
-                const uint64_t a_lo = make_desc_kmajor_noswz(ab + A_PART + aoff, APX * 16);
-                const uint32_t d_tmem = tmem_base + (uint32_t)(orow * 2 + mt) * KC;
-                umma_tf32(d_tmem, a_lo, b_hi, idesc, (js > 0 || tap > 0) ? 1u : 0u);
-                umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-                umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
-              }
+            const uint64_t b_hi = make_desc_kmajor_noswz(smem_u32(w_ring + (size_t)s * W_TILE), KC * 16);
+            const uint32_t acc0 = (tap > 0 || js > 0) ? 1u : 0u;
+            // output pixel c of row r+orow reads source row r+orow+ty-1 (buffer row orow+ty), column c+tx-1 (buffer pixel c+tx+7)
+            if (nrow == 2 && ntile == 2) {
+#pragma unroll
+              for (int orow = 0; orow < 2; ++orow)
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                  const int off = ((orow + ty) * 2) * APX + mt * 128 + tx + 7;
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(orow * 2 + mt) * KC;
+                  umma_bf16(d_tmem, a_base + (uint64_t)(A_CR + off), b_hi + B_CR, idesc_bf16, acc0);   // al*wh + ah*wl
+                  umma_tf32(d_tmem, a_base + (uint64_t)off, b_hi, idesc, 1u);
+                }
+            } else {
+              for (int orow = 0; orow < nrow; ++orow)
+                for (int mt = 0; mt < ntile; ++mt) {
+                  const int off = ((orow + ty) * 2) * APX + mt * 128 + tx + 7;
+                  const uint32_t d_tmem = tmem_base + (uint32_t)(orow * 2 + mt) * KC;
+                  umma_bf16(d_tmem, a_base + (uint64_t)(A_CR + off), b_hi + B_CR, idesc_bf16, acc0);
+                  umma_tf32(d_tmem, a_base + (uint64_t)off, b_hi, idesc, 1u);
+                }
+            }
             umma_commit(&w_empty[s]);
             if (tap == 8) {
               umma_commit(&a_empty[a]);
@@ -230,14 +271,11 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
 #pragma unroll
           for (int c = 0; c < SL; ++c) v[c] = raw[(c * 2 + row) * SW + px];
           const int q = 2 * h + row;
-#pragma unroll
-          for (int ch = 0; ch < 2; ++ch) {
-            const float4 hi = make_float4(v[4 * ch], v[4 * ch + 1], v[4 * ch + 2], v[4 * ch + 3]);
-            const float4 lo = make_float4(tf32_lo(hi.x), tf32_lo(hi.y), tf32_lo(hi.z), tf32_lo(hi.w));
-            const int off = ((q * 2 + ch) * APX + px + 4) * 16;          // staged pixel px is column px - 4
-            *reinterpret_cast<float4*>(ahi + off) = hi;
-            *reinterpret_cast<float4*>(ahi + A_PART + off) = lo;
-          }
+          const int off = ((q * 2) * APX + px + 4) * 16;                 // staged pixel px is column px - 4
+          *reinterpret_cast<float4*>(ahi + off) = make_float4(v[0], v[1], v[2], v[3]);
+          *reinterpret_cast<float4*>(ahi + off + APX * 16) = make_float4(v[4], v[5], v[6], v[7]);
+          *reinterpret_cast<uint4*>(ahi + A_PART + off) = pack8<true>(v);              // al (pairs with wh)
+          *reinterpret_cast<uint4*>(ahi + A_PART + off + APX * 16) = pack8<false>(v);  // ah (pairs with wl)
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[h]);
@@ -341,7 +379,7 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
   }
   const int n_items = B * ((H + 1) / 2);
   const int grid = n_items < sms ? n_items : sms;
-  const int wthreads = NSL * 9 * 2 * KC;
+  const int wthreads = NSL * 9 * KC;
   float* img_x = img;
   float* img_y = img + (size_t)NSL * 9 * (W_TILE / 4);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x);

@@ -2,9 +2,12 @@
 // 3 x 3 window (padding 1) -- BASELINE config 5, "tensor cores only when K is large enough to be a real dense
 // contraction" (north_star).  Reference arithmetic: contrastyou/losses/iic_loss.py:120-123
 //   J[dy][dx][i][j] = sum_{n,u,v} x[n,i,u+dy-1,v+dx-1] * y[n,j,u,v]          (x zero outside the map)
-// = nine 128 x 128 x Npix contractions.  fp32-level accuracy with TF32 operands comes from the 3 x TF32 split:
-// the tensor core reads the top 19 bits of an fp32 word, so the raw value is its own "hi" part; lo = v - trunc19(v)
-// is exact in fp32, and hi*hi + hi*lo + lo*hi leaves a relative error of ~2^-21 per product.
+// = nine 128 x 128 x Npix contractions.  fp32-level accuracy from a split product: kind::tf32 reads the top 19 bits
+// of an fp32 word, so with xh = trunc19(x) and xl = x - xh (exact in fp32)  x*y = xh*yh + (xl*yh + xh*yl) + xl*yl.
+// The main term is one tcgen05.mma.kind::tf32 on the raw fp32 tiles (K = 8 pixels); the two correction terms are
+// 2^-11 of it and only need ~8 bits, so they share ONE tcgen05.mma.kind::f16 on bf16 copies with K = 16 =
+// [xl(8 px) | xh(8 px)] x [yh(8 px) | yl(8 px)]; xl*yl (2^-22) is dropped.  Two MMAs per 8 pixels and displacement
+// instead of the three of a plain 3xTF32 scheme; relative error ~2^-20 per product.
 //
 // One CTA = one displacement row dy (blockIdx.y) and a contiguous share of the 16-pixel row segments ("k-blocks",
 // the reduction dimension of the MMA).  Per k-block:
@@ -13,14 +16,16 @@
 //              (A box cannot start at a column that is not a multiple of 4 floats -- the copy faults -- so
 //              the +-1 column shifts are made by the transform warps, not by TMA coordinates.)
 //   warps 4-7  transform: thread = channel row; writes the eight K-major SWIZZLE_64B operand tiles of the k-block
-//              (x hi/lo at the three column shifts, y hi/lo) into the operand ring, fences them for the async proxy.
-//   warp 1     one elected lane issues 3 (dx) x 2 (8-pixel slices) x 3 (split terms) tcgen05.mma.kind::tf32
-//              M = N = 128 into three 128-column TMEM accumulators; tcgen05.commit frees the operand slot.
+//              (x fp32 + bf16 correction tile at the three column shifts, y fp32 + bf16) into the operand ring and
+//              fences them for the async proxy.
+//   warp 1     one elected lane issues 3 (dx) x 2 (8-pixel slices) x 2 MMAs, M = N = 128, into three 128-column
+//              TMEM accumulators; tcgen05.commit frees the operand slot.
 // Epilogue: warps 4-7 read the accumulators with tcgen05.ld (lane = x channel i, column = y channel j) and write
 // the CTA's partial-joint slot in the permuted order tc_slot_index() describes (coalesced 512-byte warp accesses);
 // reduce_partials_kernel (local_fwd.cu) adds the slots in fp64 in a fixed order and undoes the permutation.
 // To bound the fp32 accumulation run in TMEM the k-blocks are processed in segments: after each segment the
 // accumulators are drained into the slot (first segment stores, later ones add).
+#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -38,11 +43,11 @@ constexpr int TILE_BYTES = KC * PXB * 4;       // 8192
 constexpr int XRAW_BYTES = KC * XRW * 4;       // 14336
 constexpr int RAW_BYTES = XRAW_BYTES + TILE_BYTES;   // 22528
 constexpr int NRAW = 4;
-constexpr int OP_TILES = 8;                    // x hi (dx 0..2), y hi, x lo (dx 0..2), y lo
+constexpr int OP_TILES = 8;                    // x fp32 (dx 0..2), y fp32, x bf16 [xl|xh] (dx 0..2), y bf16 [yh|yl]
 constexpr int OP_BYTES = OP_TILES * TILE_BYTES;      // 65536
 constexpr int NOP = 2;
 constexpr int SMEM_BYTES = NRAW * RAW_BYTES + NOP * OP_BYTES + 1024;   // + alignment slack
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;                   // 4 control warps + two transform / drain groups of 4 warps
 // k-blocks per TMEM accumulation run.  The tensor core adds into the fp32 accumulator with truncation, a relative
 // bias of about -1.4e-7 per 8-pixel slice that is (measured) uniform over the entries of J to 0.4 % of itself -- the
 // normalisation of iic_loss.py:129 removes a uniform factor.  32 k-blocks = 512 pixels bound it at 1e-5.
@@ -68,13 +73,32 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-__device__ __forceinline__ float4 tf32_lo4(float4 v) { return make_float4(tf32_lo(v.x), tf32_lo(v.y), tf32_lo(v.z), tf32_lo(v.w)); }
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a at the lower address
+  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+// eight fp32 values -> 16 bytes of bf16; LO selects the tf32 remainder instead of the value
+template <bool LO>
+__device__ __forceinline__ uint4 pack8(const float* v) {
+  float t[8];
+#pragma unroll
+  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
+  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
+}
 
 struct Params {
   int B, H, W, segs_w;          // segs_w = W / 16
   float* partial;               // [gridDim.x][9][128][128]
   int seg_kb;                   // k-blocks per accumulation segment
+  int dbg;                      // bring-up switches (IIC_TC_DBG): 1 no loads, 4 no transform
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -95,10 +119,10 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   const int nseg = (nkb + SEG_KB - 1) / SEG_KB;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
-    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], 4); mbar_init(&op_empty[s], 1); }
+    for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
+    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], 8); mbar_init(&op_empty[s], 1); }
     mbar_init(&accum_bar, 1);
-    mbar_init(&drained_bar, 4);
+    mbar_init(&drained_bar, 8);
     mbar_fence_init();
   }
   if (wid == 2) {
@@ -124,6 +148,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         const int rem = kb - n * per_img;
         const int u = rem / P.segs_w, c0 = (rem - u * P.segs_w) * PXB;
         unsigned char* st = raw_ring + (size_t)s * RAW_BYTES;
+        if (P.dbg & 1) { mbar_arrive(&raw_full[s]); continue; }
         mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
         tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, u + dy - 1, 0, n);
         tma_load_4d(st + XRAW_BYTES, &mapy, &raw_full[s], c0, u, 0, n);
@@ -132,6 +157,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
   } else if (wid == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
+    const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
     for (int k = 0; k < nkb; ++k) {
       const int o = k % NOP;
       const int kin = k % SEG_KB;               // position inside the accumulation segment
@@ -142,19 +168,17 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
       mbar_wait(&op_full[o], (unsigned)(k / NOP) & 1u, 5);
       asm volatile("tcgen05.fence::after_thread_sync;");
       if (lane == 0) {
-        const uint32_t sb = smem_u32(smem + (size_t)o * OP_BYTES);
+        // one base descriptor per operand slot; every tile / slice is a compile-time offset in 16-byte units
+        const uint64_t base = make_desc_sw64(smem_u32(smem + (size_t)o * OP_BYTES));
+        constexpr int TL = TILE_BYTES / 16;
 #pragma unroll
         for (int dx = 0; dx < 3; ++dx) {
           const uint32_t d_tmem = tmem_base + dx * KC;
 #pragma unroll
           for (int ks = 0; ks < PXB / 8; ++ks) {
-            const uint64_t a_hi = make_desc_sw64(sb + dx * TILE_BYTES + ks * 32);
-            const uint64_t a_lo = make_desc_sw64(sb + (4 + dx) * TILE_BYTES + ks * 32);
-            const uint64_t b_hi = make_desc_sw64(sb + 3 * TILE_BYTES + ks * 32);
-            const uint64_t b_lo = make_desc_sw64(sb + 7 * TILE_BYTES + ks * 32);
-            umma_tf32(d_tmem, a_lo, b_hi, idesc, (kin > 0 || ks > 0) ? 1u : 0u);   // small terms first
-            umma_tf32(d_tmem, a_hi, b_lo, idesc, 1u);
-            umma_tf32(d_tmem, a_hi, b_hi, idesc, 1u);
+            umma_bf16(d_tmem, base + (uint64_t)((4 + dx) * TL + ks * 2), base + (uint64_t)(7 * TL + ks * 2), idesc_bf16,
+                      (kin > 0 || ks > 0) ? 1u : 0u);                                              // xl*yh + xh*yl
+            umma_tf32(d_tmem, base + (uint64_t)(dx * TL + ks * 2), base + (uint64_t)(3 * TL + ks * 2), idesc, 1u);
           }
         }
         umma_commit(&op_empty[o]);                              // frees the operand slot when these MMAs have read it
@@ -163,8 +187,11 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
       __syncwarp();
     }
   } else if (wid >= 4) {
-    // ===== transform warps, and the epilogue =====
-    const int r = threadIdx.x - 128;                            // channel row
+    // ===== transform warps, and the epilogue: two groups of four warps, a thread of each per channel row.
+    // group 0 writes the x tiles of column shifts 0 and 1 and drains accumulator chunks 0-5, group 1 the x tiles of
+    // shift 2, the y tiles and chunks 6-11 =====
+    const int grp = wid >= 8 ? 1 : 0;
+    const int r = (threadIdx.x - 128) & 127;                    // channel row
     const int sw = (r >> 1) & 3;                                // SWIZZLE_64B: 16-byte chunk index ^= address bits 7..8
     const int q4 = wid & 3;                                     // this warp reads TMEM lanes 32*q4 .. 32*q4+31
     float* slot = P.partial + (size_t)blockIdx.x * (9 * KC * KC);
@@ -174,7 +201,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
       if (k >= NOP) mbar_wait(&op_empty[o], ((unsigned)(k / NOP) & 1u) ^ 1u, 2);
       const unsigned char* raw = raw_ring + (size_t)s * RAW_BYTES;
       unsigned char* op = smem + (size_t)o * OP_BYTES;
-      {
+      if (!(P.dbg & 4)) {
         float v[XRU];
         const float4* xr = reinterpret_cast<const float4*>(raw + r * (XRW * 4));
 #pragma unroll
@@ -183,22 +210,36 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
           v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
         }
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx)
+        for (int dx = 0; dx < 3; ++dx) {
+          if ((dx == 2) != (grp == 1)) continue;
+          // operand pixel p of the k-block is x column c0 + p + dx - 1 = staged column p + dx + 3
+          const float* xv = v + dx + 3;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            // operand pixel e of chunk c is x column c0 + 4c + e + dx - 1 = staged column 4c + e + dx + 3
-            const float4 hi = make_float4(v[4 * c + dx + 3], v[4 * c + dx + 4], v[4 * c + dx + 5], v[4 * c + dx + 6]);
-            const int off = r * 64 + ((c ^ sw) << 4);
-            *reinterpret_cast<float4*>(op + dx * TILE_BYTES + off) = hi;
-            *reinterpret_cast<float4*>(op + (4 + dx) * TILE_BYTES + off) = tf32_lo4(hi);
-          }
-        // y arrives swizzled: the physical positions carry over unchanged (walked in swizzle order: no bank conflicts)
+          for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<float4*>(op + dx * TILE_BYTES + r * 64 + ((c ^ sw) << 4)) =
+                make_float4(xv[4 * c], xv[4 * c + 1], xv[4 * c + 2], xv[4 * c + 3]);
+          // bf16 correction tile: per 8-pixel slice [xl | xh]
+          unsigned char* cr = op + (4 + dx) * TILE_BYTES + r * 64;
+          *reinterpret_cast<uint4*>(cr + ((0 ^ sw) << 4)) = pack8<true>(xv);
+          *reinterpret_cast<uint4*>(cr + ((1 ^ sw) << 4)) = pack8<false>(xv);
+          *reinterpret_cast<uint4*>(cr + ((2 ^ sw) << 4)) = pack8<true>(xv + 8);
+          *reinterpret_cast<uint4*>(cr + ((3 ^ sw) << 4)) = pack8<false>(xv + 8);
+        }
+        if (grp == 1) {
+        // y arrives swizzled (physical chunk c ^ sw holds pixels 4c .. 4c+3); walked in swizzle order: no bank conflicts
+        float yv[PXB];
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
           const int off = r * 64 + ((c ^ sw) << 4);
           const float4 t = *reinterpret_cast<const float4*>(raw + XRAW_BYTES + off);
           *reinterpret_cast<float4*>(op + 3 * TILE_BYTES + off) = t;
-          *reinterpret_cast<float4*>(op + 7 * TILE_BYTES + off) = tf32_lo4(t);
+          yv[4 * c] = t.x; yv[4 * c + 1] = t.y; yv[4 * c + 2] = t.z; yv[4 * c + 3] = t.w;
+        }
+        unsigned char* cr = op + 7 * TILE_BYTES + r * 64;          // per 8-pixel slice [yh | yl]
+        *reinterpret_cast<uint4*>(cr + ((0 ^ sw) << 4)) = pack8<false>(yv);
+        *reinterpret_cast<uint4*>(cr + ((1 ^ sw) << 4)) = pack8<true>(yv);
+        *reinterpret_cast<uint4*>(cr + ((2 ^ sw) << 4)) = pack8<false>(yv + 8);
+        *reinterpret_cast<uint4*>(cr + ((3 ^ sw) << 4)) = pack8<true>(yv + 8);
         }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> tensor-core reads
@@ -212,20 +253,21 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         const int seg = k / SEG_KB;
         mbar_wait(&accum_bar, (unsigned)seg & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;");
-        // 12 chunks of 32 columns; the slot values a later segment adds to are prefetched two chunks ahead
+        // 12 chunks of 32 columns, 6 per group; the slot values a later segment adds to are prefetched two chunks ahead
         float4 g[2][8];
         // slot layout [dy*3+dx][32-column chunk][float4 j of the chunk][row][4]: every warp access is 512 contiguous bytes
         auto chunk_ptr = [&](int c) { return reinterpret_cast<float4*>(slot) + ((size_t)((dy * 3 + (c >> 2)) * 4 + (c & 3)) * 8) * KC + r; };
         if (seg > 0) {
 #pragma unroll
           for (int p = 0; p < 2; ++p) {
-            const float4* src = chunk_ptr(p);
+            const float4* src = chunk_ptr(grp * 6 + p);
 #pragma unroll
             for (int j = 0; j < 8; ++j) g[p][j] = src[j * KC];
           }
         }
 #pragma unroll
-        for (int c = 0; c < 12; ++c) {
+        for (int cc = 0; cc < 6; ++cc) {
+          const int c = grp * 6 + cc;
           uint32_t a[32];
           const uint32_t taddr = tmem_base + ((uint32_t)(q4 * 32) << 16) + (c >> 2) * KC + (c & 3) * 32;
           asm volatile(
@@ -245,13 +287,13 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
             out[j] = make_float4(__uint_as_float(a[4 * j]), __uint_as_float(a[4 * j + 1]), __uint_as_float(a[4 * j + 2]),
                                  __uint_as_float(a[4 * j + 3]));
             if (seg > 0) {
-              out[j].x += g[c & 1][j].x; out[j].y += g[c & 1][j].y; out[j].z += g[c & 1][j].z; out[j].w += g[c & 1][j].w;
+              out[j].x += g[cc & 1][j].x; out[j].y += g[cc & 1][j].y; out[j].z += g[cc & 1][j].z; out[j].w += g[cc & 1][j].w;
             }
           }
-          if (seg > 0 && c + 2 < 12) {
+          if (seg > 0 && cc + 2 < 6) {
             const float4* src = chunk_ptr(c + 2);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) g[c & 1][j] = src[j * KC];
+            for (int j = 0; j < 8; ++j) g[cc & 1][j] = src[j * KC];
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) dst[j * KC] = out[j];
@@ -309,7 +351,8 @@ int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long
     IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  Params P{B, H, W, W / PXB, partial, getenv("IIC_TC_SEG") ? atoi(getenv("IIC_TC_SEG")) : SEG_KB_DEFAULT};
+  Params P{B, H, W, W / PXB, partial, getenv("IIC_TC_SEG") ? atoi(getenv("IIC_TC_SEG")) : SEG_KB_DEFAULT,
+           getenv("IIC_TC_DBG") ? atoi(getenv("IIC_TC_DBG")) : 0};
   local_joint_tc_kernel<<<dim3(gx, 3), NTHREADS, SMEM_BYTES, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   *ncta = gx;
