@@ -463,7 +463,8 @@ def run_b200(args):
                        "launch": "cuda_graph_replay" if use_graph else "eager",
                        "l2": f"inputs rotate over {NSETS} sets ({NSETS * 128} MB of maps) > 126 MB L2",
                        "checks": "deferred (device-side simplex + NaN flags, read after the timed region)",
-                       "multi_gpu": "batch sharded; one NCCL all-reduce of the fp64 joints per loss call" if world > 1
+                       "multi_gpu": ("batch sharded; one exchange of the fp64 joints per loss call, transport = " + iic_b200.data_parallel_transport()
+                                     + (" (NVLink peer-memory kernel, csrc/xchg.cu)" if iic_b200.data_parallel_transport() == "peer_memory" else "")) if world > 1
                        else "single GPU"},
             "e2e": {"value": round(e2e_val, 2), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": round(e2e_ms, 4), "steps": e2e_steps},

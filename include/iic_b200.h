@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IIC_B200_ABI_VERSION 2
+#define IIC_B200_ABI_VERSION 3
 
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
@@ -162,6 +162,28 @@ int iic_uda_forward(const float* prob, const float* target, long long outer, int
 int iic_uda_backward(const float* prob, const float* target, long long outer, int C, long long inner,
                      int kind, double eps, const float* weight, int from_logits,
                      const float* grad_loss, float* grad_prob, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Joint exchange over NVLink peer memory (multi-GPU, one process per GPU).  The path's only collective
+ * (J is a plain sum over the batch index, iic_loss.py:89,123) without NCCL: each
+ * rank stores its fp64 partial joints into its slot of every peer's buffer, publishes a sequence number,
+ * waits for all peers and adds the slots in rank order (bit-identical result on every rank).  The sequence
+ * counter lives in the buffer, so the call can be captured in a CUDA graph.  All ranks must issue the same
+ * exchanges in the same order.
+ *   iic_xchg_create      cudaMalloc + zero a buffer for `world` ranks of `capacity` doubles each
+ *   iic_xchg_export      its 64-byte CUDA IPC handle (host memory), to be sent to the peers
+ *   iic_xchg_import      map a peer's buffer from its handle
+ *   iic_xchg_release     cudaFree (imported = 0) or cudaIpcCloseMemHandle (imported = 1)
+ *   iic_xchg_allreduce   J[0..E) <- sum over ranks, in place; bufs_host[r] = this process's pointer to rank
+ *                        r's buffer (host array of `world` device pointers)
+ * ---------------------------------------------------------------------------------------------- */
+size_t iic_xchg_buffer_bytes(int world, long long capacity);
+int iic_xchg_create(int world, long long capacity, void** buf_out);
+int iic_xchg_export(void* buf, void* handle64_host);
+int iic_xchg_import(const void* handle64_host, void** peer_out);
+int iic_xchg_release(void* buf, int imported);
+int iic_xchg_allreduce(double* J, long long E, long long capacity, void* const* bufs_host, int rank,
+                       int world, void* stream);
 
 #ifdef __cplusplus
 }

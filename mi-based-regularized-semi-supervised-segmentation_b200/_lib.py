@@ -10,7 +10,7 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libiic_b200.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 FLAG_NAN_LOSS = 1
 FLAG_NOT_SIMPLEX = 2
 UNSUPPORTED = 3
@@ -47,6 +47,12 @@ PROTOTYPES = {
     "iic_uda_workspace_bytes": (_sz, [_i]),
     "iic_uda_forward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _i, _p, _p]),
     "iic_uda_backward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _p]),
+    "iic_xchg_buffer_bytes": (_sz, [_i, _ll]),
+    "iic_xchg_create": (_i, [_i, _ll, _p]),
+    "iic_xchg_export": (_i, [_p, _p]),
+    "iic_xchg_import": (_i, [_p, _p]),
+    "iic_xchg_release": (_i, [_p, _i]),
+    "iic_xchg_allreduce": (_i, [_p, _ll, _ll, _p, _i, _i, _p]),
 }
 
 _lib = None

@@ -367,24 +367,100 @@ for _n in ("local_joint", "local_epilogue", "local_backward", "local_joint_logit
 ops = torch.ops.iic_b200
 
 
-# ---- data-parallel hook: one all-reduce of the partial joints ---------------------------------------
+# ---- data-parallel hook: one exchange of the partial joints ------------------------------------------
 _process_group = None
 _dist_enabled = False
+_xchg = None          # PeerExchange, when the NVLink peer-memory exchange is set up
+XCHG_CAPACITY = 9 * 128 * 128     # doubles per rank slot: the local joint at K = 128, padding 1 (config 5)
 
 
-def set_data_parallel(enabled: bool, group=None):
-    """When enabled, every joint (local and global) is summed over `group` with ONE all-reduce before
+class PeerExchange:
+    """Exchange buffers of all ranks mapped into this process with CUDA IPC (csrc/xchg.cu).  Built collectively."""
+
+    def __init__(self, group, device: torch.device, capacity: int = XCHG_CAPACITY):
+        import ctypes as C
+        import torch.distributed as dist
+        lib = _lib.load()
+        self.group, self.device, self.capacity = group, device, int(capacity)
+        self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        with torch.cuda.device(device):
+            buf = C.c_void_p()
+            _lib.check(lib.iic_xchg_create(self.world, self.capacity, C.byref(buf)), "iic_xchg_create")
+            handle = C.create_string_buffer(64)
+            _lib.check(lib.iic_xchg_export(buf, handle), "iic_xchg_export")
+            handles = [None] * self.world
+            dist.all_gather_object(handles, bytes(handle.raw), group=group)
+            self.ptrs = (C.c_void_p * self.world)()
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.ptrs[r] = buf.value
+                else:
+                    peer = C.c_void_p()
+                    _lib.check(lib.iic_xchg_import(C.create_string_buffer(h, 64), C.byref(peer)), f"iic_xchg_import(rank {r})")
+                    self.ptrs[r] = peer.value
+        dist.barrier(group=group)     # every rank has mapped every buffer before the first exchange
+
+    def allreduce_(self, J: torch.Tensor) -> torch.Tensor:
+        assert J.dtype == torch.float64 and J.is_contiguous() and J.device == self.device
+        lib = _lib.load()
+        _lib.check(lib.iic_xchg_allreduce(J.data_ptr(), J.numel(), self.capacity, self.ptrs, self.rank, self.world,
+                                          torch.cuda.current_stream(self.device).cuda_stream), "iic_xchg_allreduce")
+        return J
+
+
+def set_data_parallel(enabled: bool, group=None, peer_memory=None):
+    """When enabled, every joint (local and global) is summed over `group` with ONE exchange before
     the epilogue: each rank then holds the loss of the GLOBAL batch and the gradient of that loss with
-    respect to its own shard."""
-    global _process_group, _dist_enabled
+    respect to its own shard.
+
+    peer_memory: True  = the NVLink peer-memory exchange of csrc/xchg.cu (all ranks on one node, one GPU each;
+                         collective call: every rank of `group` must make it), raising if it cannot be set up;
+                 False = torch.distributed.all_reduce (NCCL);
+                 None  = peer memory when the group is a single-node CUDA group of <= 16 ranks and the environment
+                         variable IIC_B200_NO_P2P is unset, else NCCL."""
+    global _process_group, _dist_enabled, _xchg
     _dist_enabled = bool(enabled)
     _process_group = group
+    _xchg = None
+    if not _dist_enabled or peer_memory is False:
+        return
+    import os
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1):
+        return
+    auto = peer_memory is None
+    if auto and (os.environ.get("IIC_B200_NO_P2P") or not torch.cuda.is_available() or dist.get_backend(group) != "nccl"
+                 or dist.get_world_size(group) > 16
+                 or int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size(group))) != dist.get_world_size(group)):
+        return
+    try:
+        _xchg = PeerExchange(group, torch.device("cuda", torch.cuda.current_device()))
+    except Exception:
+        _xchg = None
+        if not auto:
+            raise
+    # all ranks must agree, or some would wait in the exchange kernel while others sit in NCCL
+    ok = torch.tensor([1 if _xchg is not None else 0], device="cuda")
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+    if int(ok.item()) == 0:
+        if not auto:
+            raise RuntimeError("iic_b200: the peer-memory exchange could not be set up on every rank")
+        _xchg = None
+
+
+def data_parallel_transport() -> str:
+    """'peer_memory', 'nccl' or 'off' -- what _maybe_allreduce will use."""
+    if not _dist_enabled:
+        return "off"
+    return "peer_memory" if _xchg is not None else "nccl"
 
 
 def _maybe_allreduce(J: torch.Tensor) -> torch.Tensor:
     if _dist_enabled:
         import torch.distributed as dist
         if dist.is_available() and dist.is_initialized() and dist.get_world_size(_process_group) > 1:
+            if _xchg is not None and J.is_cuda and J.numel() <= _xchg.capacity:
+                return _xchg.allreduce_(J if J.is_contiguous() else J.contiguous())
             dist.all_reduce(J, op=dist.ReduceOp.SUM, group=_process_group)
     return J
 

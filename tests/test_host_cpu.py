@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"libiic_b200.so does not export {name}"
     assert declared == set(built._lib.PROTOTYPES), declared ^ set(built._lib.PROTOTYPES)
-    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 2
+    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 3
 
 
 def test_patch_count_matches_reference_windows(built):
