@@ -343,11 +343,17 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int H, int W, l
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// per-device scratch for the two weight images (2 x 1.18 MB), allocated on first use
-static float* weight_scratch(int device) {
+// per-device scratch for the two weight images (2 x 1.18 MB), allocated on first use -- but never while the stream
+// is being captured into a CUDA graph (cudaMalloc would invalidate the capture): the caller then takes the FFMA2 path
+static float* weight_scratch(int device, cudaStream_t st) {
   static float* buf[64] = {nullptr};
   if (device < 0 || device >= 64) return nullptr;
   if (!buf[device]) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
+      cudaGetLastError();
+      return nullptr;
+    }
     if (cudaMalloc(&buf[device], 2 * (size_t)NSL * 9 * W_TILE) != cudaSuccess) {
       cudaGetLastError();
       buf[device] = nullptr;
@@ -370,7 +376,7 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
   const int device = current_device();
   const int sms = sm_count_cached(device);
   if (sms <= 0) return -1;
-  float* img = weight_scratch(device);
+  float* img = weight_scratch(device, st);
   if (!img) return -1;
   static bool attr_set = false;
   if (!attr_set) {
