@@ -20,10 +20,10 @@
 // One CTA per SM walks a contiguous share of the (image, row pair) work items.  Per item the accumulators are the four
 // 128-column TMEM blocks [output row 0/1][pixel tile 0/1]; the 128 input channels stream through in 16 slices of 8:
 //   warp 0     TMA: the slice's four source rows r-1 .. r+2 as two [8 ch x 2 rows x (W+8) px] boxes (zero fill = padding)
-//   warp 3     bulk copies of the slice's nine 8 KB weight tiles (fp32 + bf16 parts, already in operand order), ring of 6
+//   warp 3     TMEM allocation; bulk copies of the slice's nine 8 KB weight tiles (fp32 + bf16 parts, already in operand order), ring of 6
 //   warps 4-7  transform: [ch][row][px] fp32 -> [row][chunk][px][16 B] operand images (fp32: 4 channels per
 //              chunk; bf16: chunk 0 = al, chunk 1 = ah of the 8 channels)
-//   warp 1     one lane issues 9 taps x 2 rows x 2 tiles x 2 MMAs per slice
+//   warps 1-2  MMA issuers (one lane each, one output row each): 9 taps x 2 tiles x 2 MMAs per slice and row
 //   warps 8-11 epilogue after the 16th slice: tcgen05.ld (lane = pixel, columns = channels), scale by g, coalesced stores
 #include <cuda_bf16.h>
 #include <stdlib.h>
@@ -145,13 +145,13 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < 2; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
-    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 1); }
-    for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 1); }
-    mbar_init(&accum_full, 1);
+    for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
+    for (int s = 0; s < NW; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
+    mbar_init(&accum_full, 2);
     mbar_init(&tmem_empty, 4);
     mbar_fence_init();
   }
-  if (wid == 2) {
+  if (wid == 3) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -191,8 +191,12 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
         bulk_load(w_ring + s * W_TILE, P.wimg + (size_t)(w % (NSL * 9)) * (W_TILE / 4), W_TILE, &w_full[s]);
       }
     }
-  } else if (wid == 1) {
-    // ===== MMA issuer =====
+  } else if (wid == 1 || wid == 2) {
+    // ===== MMA issuers: warp 1 owns the accumulators of output row 0, warp 2 those of output row 1.  With one issuing
+    // lane an MMA went out every ~104 clk, with two every ~88 clk (both measured with everything else ablated, and both
+    // independent of N down to N = 8: the limit is per instruction, not tensor math).  Each warp commits to the ring
+    // barriers. =====
+    const int orow = wid - 1;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
     const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
     for (int i = 0; i < nit; ++i) {
@@ -209,7 +213,8 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
         mbar_wait(&a_full[a], (unsigned)(t / NA) & 1u, 5);
         // The issuing lane is latency-bound on its own instruction stream, so every descriptor is a 64-bit base plus a
         // compile-time constant (in 16-byte units): the tap / row / tile loops are fully unrolled.
-        const uint64_t a_base = make_desc_kmajor_noswz(smem_u32(a_ring + (size_t)a * A_SLOT), APX * 16);
+        const uint64_t a_base = make_desc_kmajor_noswz(smem_u32(a_ring + (size_t)a * A_SLOT), APX * 16) + (uint64_t)(orow * 2 * APX);
+        const uint32_t d_row = tmem_base + (uint32_t)(orow * 2) * KC;
         const int w0 = t * 9;
 #pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
@@ -223,24 +228,21 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
             const uint64_t b_hi = make_desc_kmajor_noswz(smem_u32(w_ring + (size_t)s * W_TILE), KC * 16);
             const uint32_t acc0 = (tap > 0 || js > 0) ? 1u : 0u;
             // output pixel c of row r+orow reads source row r+orow+ty-1 (buffer row orow+ty), column c+tx-1 (buffer pixel c+tx+7)
-            if (nrow == 2 && ntile == 2) {
-#pragma unroll
-              for (int orow = 0; orow < 2; ++orow)
+            if (orow < nrow) {
+              if (ntile == 2) {
 #pragma unroll
                 for (int mt = 0; mt < 2; ++mt) {
-                  const int off = ((orow + ty) * 2) * APX + mt * 128 + tx + 7;
-                  const uint32_t d_tmem = tmem_base + (uint32_t)(orow * 2 + mt) * KC;
+                  const int off = (ty * 2) * APX + mt * 128 + tx + 7;
+                  const uint32_t d_tmem = d_row + (uint32_t)mt * KC;
                   umma_bf16(d_tmem, a_base + (uint64_t)(A_CR + off), b_hi + B_CR, idesc_bf16, acc0);   // al*wh + ah*wl
                   umma_tf32(d_tmem, a_base + (uint64_t)off, b_hi, idesc, 1u);
                 }
-            } else {
-              for (int orow = 0; orow < nrow; ++orow)
-                for (int mt = 0; mt < ntile; ++mt) {
-                  const int off = ((orow + ty) * 2) * APX + mt * 128 + tx + 7;
-                  const uint32_t d_tmem = tmem_base + (uint32_t)(orow * 2 + mt) * KC;
-                  umma_bf16(d_tmem, a_base + (uint64_t)(A_CR + off), b_hi + B_CR, idesc_bf16, acc0);
-                  umma_tf32(d_tmem, a_base + (uint64_t)off, b_hi, idesc, 1u);
-                }
+              } else {
+                const int off = (ty * 2) * APX + tx + 7;
+                const uint32_t d_tmem = d_row;
+                umma_bf16(d_tmem, a_base + (uint64_t)(A_CR + off), b_hi + B_CR, idesc_bf16, acc0);
+                umma_tf32(d_tmem, a_base + (uint64_t)off, b_hi, idesc, 1u);
+              }
             }
             umma_commit(&w_empty[s]);
             if (tap == 8) {
@@ -326,7 +328,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (wid == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  if (wid == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 static bool make_map(CUtensorMap* map, const float* base, int B, int H, int W, long long sn, long long sc, long long sh) {
