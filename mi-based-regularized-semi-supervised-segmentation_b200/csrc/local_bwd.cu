@@ -210,6 +210,9 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
 int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                      long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
                      const float* grad_loss, float* gx, float* gy, cudaStream_t st);
+int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                       const float* grad_loss, float* gx, float* gy, cudaStream_t st);
 }
 using namespace iic;
 
@@ -239,6 +242,13 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
       const int rc_tc = local_bwd_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                          gx, gy, st);
       if (rc_tc >= 0) return rc_tc;
+      // the reference's default cluster count (16 <= K <= 24), padding 1 or 3: row-block tensor-core sweeps
+      // (local_bwd_tcrb.cu); padding 1 only pays on maps with enough rows to fill the SMs
+      if (pad == 3 || getenv("IIC_B200_TCRB_P1")) {
+        const int rc_rb = local_bwd_tcrb_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                             gx, gy, st);
+        if (rc_rb >= 0) return rc_rb;
+      }
     }
     int rc = getenv("IIC_B200_NO_FAST") ? -1
                  : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
