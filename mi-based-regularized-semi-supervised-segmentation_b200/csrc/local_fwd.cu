@@ -364,13 +364,19 @@ extern "C" int iic_local_num_patches(int H, int W, int patch_h, int patch_w, int
   return g.nh * g.nw;
 }
 
+namespace iic { size_t local_joint_tcp_slot_floats(int K, int pad); }
+
 extern "C" size_t iic_local_joint_workspace_bytes(int device, int B, int K, int H, int W, int pad,
                                                   int patch_h, int patch_w, int step_h, int step_w) {
   PatchGrid g;
   FwdPlan pl;
   if (!make_patch_grid(H, W, patch_h, patch_w, step_h, step_w, &g)) return 0;
   if (!make_fwd_plan(device, B, K, g, pad, &pl)) return 0;
-  return (size_t)pl.n_patches * pl.slots_per_patch * pl.T * pl.T * K * K * sizeof(float);
+  size_t bytes = (size_t)pl.n_patches * pl.slots_per_patch * pl.T * pl.T * K * K * sizeof(float);
+  // the packed tensor-core joint (local_fwd_tcp.cu) keeps whole accumulator tiles per CTA slot
+  const size_t tcp = local_joint_tcp_slot_floats(K, pad) * (size_t)pl.slots_per_patch * sizeof(float);
+  if (pl.n_patches == 1 && tcp > bytes) bytes = tcp;
+  return bytes;
 }
 
 namespace iic {
@@ -387,6 +393,10 @@ int local_joint_fast7_try(const float* x, long long x_sn, long long x_sc, long l
 int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                        float* partial, int max_ctas, int* ncta, cudaStream_t st);
+size_t local_joint_tcp_slot_floats(int K, int pad);
+int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                        long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial,
+                        size_t partial_floats, double* J_out, cudaStream_t st);
 }
 
 extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
@@ -422,6 +432,14 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
   if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
     int ncta = 0, checked = 0;
+    // the reference's default cluster count (16 <= K <= 24), padding 3: packed tensor-core joint (local_fwd_tcp.cu);
+    // padding 1 stays on the FFMA2 kernel unless IIC_B200_TCP_P1 is set
+    if (!getenv("IIC_B200_NO_TC") && (pad == 3 || getenv("IIC_B200_TCP_P1"))) {
+      const int rc_p = local_joint_tcp_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
+                                           workspace_bytes / sizeof(float), J_out, st);
+      if (rc_p > 0) return rc_p;
+      if (rc_p == 0) return simplex_pass();
+    }
     // wide cluster heads (K = 128): tcgen05 3xTF32 contraction (local_fwd_tc.cu)
     if (!getenv("IIC_B200_NO_TC")) {
       const int rc_tc = local_joint_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,

@@ -118,7 +118,11 @@ LOCAL_CASES = [
     (2, 20, 40, 48, 3, 1024),     # yaml default K=20, p=3 (7 x 7 kernels, one backward launch per weight slab)
     (2, 10, 56, 64, 3, 512),      # K=10, p=3 (7 x 7 kernels, single backward launch)
     (1, 10, 224, 224, 3, 512),    # ACDC Up_conv2 shape with the yaml padding of 3
-    (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows
+    (3, 20, 33, 36, 3, 512),      # 7 x 7, ragged tile rows (tensor-core row-block backward; the joint stays on FFMA2: W % 16 != 0)
+    (2, 20, 40, 64, 3, 512),      # K = 20, padding 3: packed tensor-core joint + row-block tensor-core backward
+    (1, 24, 21, 48, 3, 512),      # K = 24 (no channel padding), odd height
+    (1, 16, 26, 112, 3, 512),     # K = 16, one 128-pixel tile
+    (4, 20, 224, 224, 3, 512),    # the yaml default at full map size: two TMEM accumulation runs per CTA, two pixel tiles
     (2, 16, 40, 64, 1, 512),      # channel blocks of 8 (K a multiple of 8, not of 10)
     (1, 128, 24, 32, 1, 512),     # config-5 cluster count (K = 128): tcgen05 joint (W % 16 == 0)
     (3, 128, 112, 112, 1, 512),   # K = 128, long enough for two TMEM accumulation segments per CTA
