@@ -81,7 +81,8 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
 struct Params {
   int B, H, W, K;
   int KP, NS, R;                // channels padded to 8, channel slices, output rows per item
-  int nblk, n_items;            // row blocks per image, B * nblk
+  int nblk, n_items;            // row blocks per image, B * nblk * npanel
+  int PW, npanel;               // column panels (maps wider than one TMA box): width and count
   int wslice_bytes;             // bytes of one slice's weight image = T tiles of 64*T*KP bytes
   int na, nraw;                 // operand-ring and raw-ring depths
   const float* wimg;
@@ -126,9 +127,9 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
   const int it0 = (int)((long long)blockIdx.x * P.n_items / gridDim.x);
   const int it1 = (int)((long long)(blockIdx.x + 1) * P.n_items / gridDim.x);
   const int nit = it1 - it0;
-  const int SW = P.W + 8;
+  const int SW = P.PW + 8;                                 // staged columns of a panel: col0 - 4 .. col0 + PW + 3
   const int raw_bytes = SL * SW * 4;
-  const int ntile = P.W > 128 ? 2 : 1;
+  const int ntile = P.PW > 128 ? 2 : 1;
   const int NQ = P.R + T - 1;                              // source rows per item
   const int KP = P.KP, NS = P.NS, R = P.R, NA = P.na, NRAW = P.nraw;
 
@@ -156,13 +157,14 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
       int t = 0;
       for (int i = 0; i < nit; ++i) {
         const int item = it0 + i;
-        const int n = item / P.nblk, r0 = (item - n * P.nblk) * R;
+        const int panel = item % P.npanel, ib = item / P.npanel;
+        const int n = ib / P.nblk, r0 = (ib - n * P.nblk) * R;
         for (int js = 0; js < NS; ++js)
           for (int q = 0; q < NQ; ++q, ++t) {
             const int s = t % NRAW;
             if (t >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(t / NRAW) & 1u) ^ 1u, 1);
             mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
-            tma_load_4d(raw_ring + s * RAW_MAX, &maps, &raw_full[s], -4, r0 - PAD + q, js * SL, n);
+            tma_load_4d(raw_ring + s * RAW_MAX, &maps, &raw_full[s], panel * P.PW - 4, r0 - PAD + q, js * SL, n);
           }
       }
     }
@@ -267,11 +269,14 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     zero_accumulators();
     for (int i = 0; i < nit; ++i) {
       const int item = it0 + i;
-      const int n = item / P.nblk, r0 = (item - n * P.nblk) * R;
+      const int panel = item % P.npanel, ib = item / P.npanel;
+      const int n = ib / P.nblk, r0 = (ib - n * P.nblk) * R;
+      const int col0 = panel * P.PW;
       mbar_wait(&accum_full, (unsigned)i & 1u, 8);
       asm volatile("tcgen05.fence::after_thread_sync;");
       for (int mt = 0; mt < ntile; ++mt) {
-        const int c = mt * 128 + q4 * 32 + lane;
+        const int cp = mt * 128 + q4 * 32 + lane;            // column inside the panel
+        const int c = col0 + cp;
         for (int orow = 0; orow < R && r0 + orow < P.H; ++orow) {
           float* dst = P.out + (size_t)n * P.K * plane + (size_t)(r0 + orow) * P.W + c;
           for (int ch = 0; ch < KP; ch += 8) {
@@ -281,7 +286,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
                          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                          : "r"(taddr));
             asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < P.W) {
+            if (c < P.W && cp < P.PW) {
 #pragma unroll
               for (int o = 0; o < 8; ++o)
                 if (ch + o < P.K) dst[(size_t)(ch + o) * plane] = g * __uint_as_float(v[o]);
@@ -297,14 +302,14 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
   if (wid == 3) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
-static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, int W, long long sn, long long sc, long long sh) {
+static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, int W, long long sn, long long sc, long long sh, int box_w) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return false;
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
   if ((sh * 4) % 16 != 0 || (sc * 4) % 16 != 0 || (sn * 4) % 16 != 0) return false;
   cuuint64_t dims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)K, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)sh * 4, (cuuint64_t)sc * 4, (cuuint64_t)sn * 4};
-  cuuint32_t box[4] = {(cuuint32_t)(W + 8), 1, (cuuint32_t)SL, 1};
+  cuuint32_t box[4] = {(cuuint32_t)box_w, 1, (cuuint32_t)SL, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(base), dims, strides, box, estr,
              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -348,9 +353,16 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
                        long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
                        const float* grad_loss, float* gx, float* gy, cudaStream_t st) {
   using namespace bwdrb;
-  if (K < 16 || K > 24 || (pad != 1 && pad != 3) || W % 4 != 0 || W > MAXW || W < 8) return -1;
+  if (K < 16 || K > 24 || (pad != 1 && pad != 3) || W % 4 != 0 || W < 8) return -1;
+  // maps wider than one TMA box are cut into column panels: 128 columns (one pixel tile, no padding) when that divides
+  // the width, else equal panels of at most 248 columns
+  int npanel = 1, PW = W;
+  if (W > MAXW) {
+    if (W % 128 == 0) { PW = 128; npanel = W / 128; }
+    else { npanel = (W + MAXW - 1) / MAXW; PW = (((W + npanel - 1) / npanel) + 3) & ~3; }
+  }
   const int T = 2 * pad + 1, KP = (K + 7) & ~7, NS = KP / SL, Kp4 = (K + 3) & ~3;
-  const int ntile = W > 128 ? 2 : 1;
+  const int ntile = PW > 128 ? 2 : 1;
   int R = 512 / (ntile * KP);
   if (R > H) R = H;
   const int wslice = 64 * T * T * KP;
@@ -363,15 +375,15 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
   const size_t smem = (size_t)2 * ((wslice + 127) & ~127) + (size_t)na * A_ROW + (size_t)nraw * RAW_MAX + 1024;
   if ((size_t)2 * NS * wslice + 4096 > SCRATCH_BYTES) return -1;
   CUtensorMap mx, my;
-  if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh)) return -1;
-  if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh)) return -1;
+  if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, PW + 8)) return -1;
+  if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh, PW + 8)) return -1;
   const int device = current_device();
   const int sms = sm_count_cached(device);
   if (sms <= 0) return -1;
   float* img = weight_scratch(device, st);
   if (!img) return -1;
   const int nblk = (H + R - 1) / R;
-  const int n_items = B * nblk;
+  const int n_items = B * nblk * npanel;
   const int grid = n_items < sms ? n_items : sms;
   float* img_x = img;
   float* img_y = img + ((size_t)NS * wslice + 1023) / 1024 * 256;      // 1 KB aligned second image
@@ -379,8 +391,8 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x, K, Kp4, KP, NS, T);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y, K, Kp4, KP, NS, T);
   IIC_CHECK_CUDA(cudaGetLastError());
-  Params Pgx{B, H, W, K, KP, NS, R, nblk, n_items, wslice, na, nraw, img_x, grad_loss, gx};     // dL/dx from y
-  Params Pgy{B, H, W, K, KP, NS, R, nblk, n_items, wslice, na, nraw, img_y, grad_loss, gy};     // dL/dy from x
+  Params Pgx{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_x, grad_loss, gx};     // dL/dx from y
+  Params Pgy{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_y, grad_loss, gy};     // dL/dy from x
   if (T == 3) {
     if (int rc = launch<3>(my, Pgx, grid, smem, st)) return rc;
     return launch<3>(mx, Pgy, grid, smem, st);
