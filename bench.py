@@ -397,6 +397,23 @@ def run_b200(args):
             "fp32_equiv_tflops": round(6.0 * K5 * K5 * 9 * px5 / (ms5 * 1e-3) / 1e12, 1),
             "tensor_frac_of_measured_peak": round(2 * 6.0 * K5 * K5 * 9 * px5 / (ms5 * 1e-3) / 1e12 / tf32_peak, 4)}
         del x5, y5
+        # configs 3 and 4 (the yaml default head: K = 20, padding 3): packed tensor-core joint + row-block backward
+        for tag, (Bc, Hc, Wc) in {"config3_up_conv2_k20_p3": (8, 224, 224), "config4_512_k20_p3": (16, 512, 512)}.items():
+            bc = torch.nn.functional.interpolate(torch.randn(Bc, 20, Hc // 8, Wc // 8, device=dev, generator=gl) * 3,
+                                                 size=(Hc, Wc), mode="bilinear", align_corners=False)
+            xc = (bc + 0.5 * torch.randn(Bc, 20, Hc, Wc, device=dev, generator=gl)).softmax(1).requires_grad_(True)
+            yc = (bc + 0.5 * torch.randn(Bc, 20, Hc, Wc, device=dev, generator=gl)).softmax(1).requires_grad_(True)
+            del bc
+            with contextlib.redirect_stdout(sys.stderr):
+                crit3 = iic_b200.IIDSegmentationSmallPathLoss(padding=3, patch_size=1024)
+            msc = timed_graph(lambda: torch.autograd.grad(crit3(xc, yc), (xc, yc)), reps=10)
+            pxc = Bc * Hc * Wc
+            extra[tag] = {"what": f"local IIC fwd+bwd, ({Bc},20,{Hc},{Wc}) per GPU, padding 3 (49 displacements), tensor-core kernels",
+                          "ms": round(msc, 4), "mpx_s": round(pxc / (msc * 1e-3) / 1e6, 1),
+                          "hbm_frac": round(24.0 * 20 * pxc / (msc * 1e-3) / 1e9 / hbm_peak, 4),
+                          "fp32_equiv_tflops": round(6.0 * 400 * 49 * pxc / (msc * 1e-3) / 1e12, 1),
+                          "fp32_simt_peak_tflops": round(2 * 148 * 128 * 1.965e9 / 1e12, 1)}
+            del xc, yc
     except Exception as e:  # noqa: BLE001
         extra["error"] = f"{type(e).__name__}: {e}"
 

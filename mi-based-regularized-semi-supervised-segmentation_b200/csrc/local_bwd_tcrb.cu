@@ -154,17 +154,18 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     // ===== TMA producer: one source row of one channel slice per stage =====
     if (lane == 0) {
       tma_prefetch_desc(&maps);
-      int t = 0;
+      int t = 0, s = 0;                                 // ring slot and phase as running counters: no divisions per stage
+      unsigned sph = 0;
       for (int i = 0; i < nit; ++i) {
         const int item = it0 + i;
         const int panel = item % P.npanel, ib = item / P.npanel;
         const int n = ib / P.nblk, r0 = (ib - n * P.nblk) * R;
         for (int js = 0; js < NS; ++js)
           for (int q = 0; q < NQ; ++q, ++t) {
-            const int s = t % NRAW;
-            if (t >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(t / NRAW) & 1u) ^ 1u, 1);
+            if (t >= NRAW) mbar_wait(&raw_empty[s], sph ^ 1u, 1);
             mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
             tma_load_4d(raw_ring + s * RAW_MAX, &maps, &raw_full[s], panel * P.PW - 4, r0 - PAD + q, js * SL, n);
+            if (++s == NRAW) { s = 0; sph ^= 1u; }
           }
       }
     }
@@ -185,7 +186,8 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     const int mt = wid - 1;
     const bool mine = mt < ntile;
     const uint32_t rows = (uint32_t)(T * KP);              // rows of one weight part chunk
-    int t = 0;
+    int a = 0;
+    unsigned aph = 0;
     for (int i = 0; i < nit; ++i) {
       mbar_wait(&tmem_ready, (unsigned)i & 1u, 6);          // accumulators zeroed
       asm volatile("tcgen05.fence::after_thread_sync;");
@@ -193,9 +195,8 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
         const int w = i * NS + js, ws = w & 1;
         mbar_wait(&w_full[ws], (unsigned)(w >> 1) & 1u, 7);
         const uint64_t w_base = make_desc_kmajor_noswz(smem_u32(w_ring + ws * wslot_bytes), rows * 16);
-        for (int q = 0; q < NQ; ++q, ++t) {
-          const int a = t % NA;
-          mbar_wait(&a_full[a], (unsigned)(t / NA) & 1u, 5);
+        for (int q = 0; q < NQ; ++q) {
+          mbar_wait(&a_full[a], aph, 5);
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
             if (mine) {
@@ -222,6 +223,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
             }
           }
           __syncwarp();
+          if (++a == NA) { a = 0; aph ^= 1u; }
         }
       }
     }
@@ -229,10 +231,11 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     // ===== transform: [ch][px] fp32 -> [chunk][px][16 B] operand images (fp32 and bf16 [al | ah]) =====
     const int tid = threadIdx.x - 128;
     const int total = nit * NS * NQ;
+    int a = 0, s = 0;
+    unsigned aph = 0, sph = 0;
     for (int t = 0; t < total; ++t) {
-      const int a = t % NA, s = t % NRAW;
-      if (t >= NA) mbar_wait(&a_empty[a], ((unsigned)(t / NA) & 1u) ^ 1u, 3);
-      mbar_wait(&raw_full[s], (unsigned)(t / NRAW) & 1u, 4);
+      if (t >= NA) mbar_wait(&a_empty[a], aph ^ 1u, 3);
+      mbar_wait(&raw_full[s], sph, 4);
       unsigned char* abuf = a_ring + a * A_ROW;
       const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_MAX);
       for (int px = tid; px < SW; px += 128) {
@@ -250,6 +253,8 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[a]);
+      if (++a == NA) { a = 0; aph ^= 1u; }
+      if (++s == NRAW) { s = 0; sph ^= 1u; }
     }
   } else if (wid >= 8) {
     // ===== epilogue: drain the R x tiles x KP accumulator columns, store, zero them for the next item =====

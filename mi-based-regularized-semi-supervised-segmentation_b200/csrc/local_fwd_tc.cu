@@ -139,30 +139,34 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
     if (lane == 0) {
       tma_prefetch_desc(&mapx);
       tma_prefetch_desc(&mapy);
+      // (image, row, segment) of the first k-block by division, then running counters: a division by a runtime value
+      // costs this single-lane loop ~100 clk per k-block
       const int per_img = P.H * P.segs_w;
+      int n = kb0 / per_img;
+      int u = (kb0 - n * per_img) / P.segs_w;
+      int sg = kb0 - n * per_img - u * P.segs_w;
       for (int k = 0; k < nkb; ++k) {
         const int s = k % NRAW;
         if (k >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(k / NRAW) & 1u) ^ 1u, 1);
-        const int kb = kb0 + k;
-        const int n = kb / per_img;
-        const int rem = kb - n * per_img;
-        const int u = rem / P.segs_w, c0 = (rem - u * P.segs_w) * PXB;
+        const int c0 = sg * PXB, uc = u, nc = n;
+        if (++sg == P.segs_w) { sg = 0; if (++u == P.H) { u = 0; ++n; } }
         unsigned char* st = raw_ring + (size_t)s * RAW_BYTES;
         if (P.dbg & 1) { mbar_arrive(&raw_full[s]); continue; }
         mbar_arrive_expect_tx(&raw_full[s], RAW_BYTES);
-        tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, u + dy - 1, 0, n);
-        tma_load_4d(st + XRAW_BYTES, &mapy, &raw_full[s], c0, u, 0, n);
+        tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, uc + dy - 1, 0, nc);
+        tma_load_4d(st + XRAW_BYTES, &mapy, &raw_full[s], c0, uc, 0, nc);
       }
     }
   } else if (wid == 1) {
     // ===== MMA issuer =====
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
     const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(KC >> 3) << 17) | ((uint32_t)(KC >> 4) << 24);
+    int kin = 0;                                // position inside the accumulation segment (running: no divisions)
+    unsigned seg = 0;
     for (int k = 0; k < nkb; ++k) {
       const int o = k % NOP;
-      const int kin = k % SEG_KB;               // position inside the accumulation segment
       if (kin == 0 && k > 0) {                  // the epilogue warps must have drained the previous segment
-        mbar_wait(&drained_bar, (unsigned)(k / SEG_KB - 1) & 1u, 6);
+        mbar_wait(&drained_bar, (seg - 1) & 1u, 6);
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
       mbar_wait(&op_full[o], (unsigned)(k / NOP) & 1u, 5);
@@ -185,6 +189,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         if (kin == SEG_KB - 1 || k == nkb - 1) umma_commit(&accum_bar);
       }
       __syncwarp();
+      if (++kin == SEG_KB) { kin = 0; ++seg; }
     }
   } else if (wid >= 4) {
     // ===== transform warps, and the epilogue: two groups of four warps, a thread of each per channel row.
@@ -195,6 +200,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
     const int sw = (r >> 1) & 3;                                // SWIZZLE_64B: 16-byte chunk index ^= address bits 7..8
     const int q4 = wid & 3;                                     // this warp reads TMEM lanes 32*q4 .. 32*q4+31
     float* slot = P.partial + (size_t)blockIdx.x * (9 * KC * KC);
+    int kin = 0, seg = 0;                                       // running segment counters (no divisions in the loop)
     for (int k = 0; k < nkb; ++k) {
       const int s = k % NRAW, o = k % NOP;
       mbar_wait(&raw_full[s], (unsigned)(k / NRAW) & 1u, 3);
@@ -248,9 +254,8 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         mbar_arrive(&op_full[o]);
         mbar_arrive(&raw_empty[s]);
       }
-      if ((k % SEG_KB) == SEG_KB - 1 || k == nkb - 1) {
+      if (kin == SEG_KB - 1 || k == nkb - 1) {
         // ---- drain the accumulators of this segment into the slot ----
-        const int seg = k / SEG_KB;
         mbar_wait(&accum_bar, (unsigned)seg & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;");
         // 12 chunks of 32 columns, 6 per group; the slot values a later segment adds to are prefetched two chunks ahead
@@ -302,6 +307,7 @@ local_joint_tc_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         __syncwarp();
         if (lane == 0 && seg + 1 < nseg) mbar_arrive(&drained_bar);
       }
+      if (++kin == SEG_KB) { kin = 0; ++seg; }
     }
     if (nkb == 0) {
       float4* dst = reinterpret_cast<float4*>(slot + (size_t)dy * 3 * KC * KC);

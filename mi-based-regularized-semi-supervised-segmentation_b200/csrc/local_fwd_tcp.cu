@@ -95,7 +95,7 @@ template <int T>
 __global__ void __launch_bounds__(NTHREADS, 1)
 local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, const Params P) {
   constexpr int PAD = T / 2;
-  constexpr int NOP_MAX = 4;
+  constexpr int NOP_MAX = 8;
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], op_full[NOP_MAX], op_empty[NOP_MAX], accum_bar, drained_bar;
   __shared__ uint32_t tmem_base_s;
@@ -134,19 +134,22 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
     if (lane == 0) {
       tma_prefetch_desc(&mapx);
       tma_prefetch_desc(&mapy);
+      // (image, row, segment) of the first k-block by division, then running counters: no divisions in the loops
       const int per_img = P.H * P.segs_w;
+      int n = kb0 / per_img;
+      int q = (kb0 - n * per_img) / P.segs_w;
+      int sg = kb0 - n * per_img - q * P.segs_w;
       for (int k = 0; k < nkb; ++k) {
         const int s = k % NRAW;
         if (k >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(k / NRAW) & 1u) ^ 1u, 1);
-        const int kb = kb0 + k;
-        const int n = kb / per_img;
-        const int rem = kb - n * per_img;
-        const int q = rem / P.segs_w, c0 = (rem - q * P.segs_w) * PXB;
+        const int c0 = sg * PXB;
+        const int qc = q, nc = n;
+        if (++sg == P.segs_w) { sg = 0; if (++q == P.H) { q = 0; ++n; } }
         unsigned char* st = raw_ring + (size_t)s * P.raw_bytes;
         if (P.dbg & 1) { mbar_arrive(&raw_full[s]); continue; }
         mbar_arrive_expect_tx(&raw_full[s], xraw_bytes + KPC * T * 64);
-        tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, q, 0, n);
-        tma_load_4d(st + 3072, &mapy, &raw_full[s], c0, q + PAD - (T - 1), 0, n);
+        tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, qc, 0, nc);
+        tma_load_4d(st + 3072, &mapy, &raw_full[s], c0, qc + PAD - (T - 1), 0, nc);
       }
     }
   } else if (wid == 1) {
@@ -154,14 +157,14 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
     const uint32_t nn = (uint32_t)NB;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((nn >> 3) << 17) | (8u << 24);
     const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((nn >> 3) << 17) | (8u << 24);
+    int o = 0, kin = 0;
+    unsigned oph = 0, seg = 0;
     for (int k = 0; k < nkb; ++k) {
-      const int o = k % NOP;
-      const int kin = k % SEG_KB;
       if (kin == 0 && k > 0) {
-        mbar_wait(&drained_bar, (unsigned)(k / SEG_KB - 1) & 1u, 6);
+        mbar_wait(&drained_bar, (seg - 1) & 1u, 6);
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
-      mbar_wait(&op_full[o], (unsigned)(k / NOP) & 1u, 5);
+      mbar_wait(&op_full[o], oph, 5);
       asm volatile("tcgen05.fence::after_thread_sync;");
       if (lane == 0) {
         const uint64_t base = make_desc_sw64(smem_u32(smem + (size_t)o * P.op_bytes));
@@ -176,10 +179,12 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
             umma_tf32(d_tmem, ab + (uint64_t)(ks * 2), bb + (uint64_t)(ks * 2), idesc, 1u);
           }
         }
-        umma_commit(&op_empty[o]);
+        if (P.dbg & 8) mbar_arrive(&op_empty[o]); else umma_commit(&op_empty[o]);      // dbg 8: plain arrive (timing experiment)
         if (kin == SEG_KB - 1 || k == nkb - 1) umma_commit(&accum_bar);
       }
       __syncwarp();
+      if (++o == NOP) { o = 0; oph ^= 1u; }
+      if (++kin == SEG_KB) { kin = 0; ++seg; }
     }
   } else if (wid >= 4) {
     // ===== transform warps, and the drains =====
@@ -190,10 +195,12 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
     const int slot_floats = NMT * 128 * NB;
     float* slot = P.partial + (size_t)blockIdx.x * slot_floats;
     const int nrows_a = T * P.K;
+    int o = 0, kin = 0, seg = 0;
+    unsigned oph = 0;
     for (int k = 0; k < nkb; ++k) {
-      const int s = k % NRAW, o = k % NOP;
+      const int s = k % NRAW;
       mbar_wait(&raw_full[s], (unsigned)(k / NRAW) & 1u, 3);
-      if (k >= NOP) mbar_wait(&op_empty[o], ((unsigned)(k / NOP) & 1u) ^ 1u, 2);
+      if (k >= NOP) mbar_wait(&op_empty[o], oph ^ 1u, 2);
       const unsigned char* raw = raw_ring + (size_t)s * P.raw_bytes;
       unsigned char* op = smem + (size_t)o * P.op_bytes;
       if (tid < nrows_a && !(P.dbg & 4)) {
@@ -241,9 +248,9 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         mbar_arrive(&op_full[o]);
         mbar_arrive(&raw_empty[s]);
       }
-      if ((k % SEG_KB) == SEG_KB - 1 || k == nkb - 1) {
+      const bool run_end = kin == SEG_KB - 1 || k == nkb - 1;
+      if (run_end) {
         // ---- drain this run's accumulators into the slot (first run stores, later runs add) ----
-        const int seg = k / SEG_KB;
         mbar_wait(&accum_bar, (unsigned)seg & 1u, 4);
         asm volatile("tcgen05.fence::after_thread_sync;");
         if (grp < NMT) {
@@ -272,6 +279,8 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         __syncwarp();
         if (lane == 0 && seg + 1 < nseg) mbar_arrive(&drained_bar);
       }
+      if (++o == NOP) { o = 0; oph ^= 1u; }
+      if (++kin == SEG_KB) { kin = 0; ++seg; }
     }
     if (nkb == 0)
       for (int e = tid; e < slot_floats; e += 384) slot[e] = 0.f;
@@ -364,7 +373,8 @@ int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long lon
   const int op_bytes = (nmt * 2 * ATILE + 2 * nb * 64 + 1023) & ~1023;
   const int raw_bytes = (3072 + KPC * T * 64 + 1023) & ~1023;
   int nop = (SMEM_LIMIT - 1024 - NRAW * raw_bytes) / op_bytes;
-  if (nop > 4) nop = 4;
+  if (nop > 8) nop = 8;
+  if (getenv("IIC_TC_NOP") && atoi(getenv("IIC_TC_NOP")) < nop) nop = atoi(getenv("IIC_TC_NOP"));   // experiments
   if (nop < 2) return -1;
   const size_t smem = (size_t)nop * op_bytes + (size_t)NRAW * raw_bytes + 1024;
   Params P{B, H, W, K, W / PXB, nmt, nb, op_bytes, raw_bytes, nop,
