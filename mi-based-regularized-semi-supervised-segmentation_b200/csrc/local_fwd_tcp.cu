@@ -75,6 +75,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
 }
 
+#ifdef IIC_TC_TRACE
+__device__ long long g_trace[3][64][6];
+#define TRACE(role, slot) do { if (blockIdx.x == 0 && k >= 64 && k < 128) g_trace[role][k - 64][slot] = clock64(); } while (0)
+#else
+#define TRACE(role, slot) do { } while (0)
+#endif
+
 struct Params {
   int B, H, W, K, segs_w;       // segs_w = W / 16
   int nmt;                      // 128-row A tiles: ceil(T*K / 128)
@@ -141,7 +148,9 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
       int sg = kb0 - n * per_img - q * P.segs_w;
       for (int k = 0; k < nkb; ++k) {
         const int s = k % NRAW;
+        TRACE(0, 0);
         if (k >= NRAW) mbar_wait(&raw_empty[s], ((unsigned)(k / NRAW) & 1u) ^ 1u, 1);
+        TRACE(0, 1);
         const int c0 = sg * PXB;
         const int qc = q, nc = n;
         if (++sg == P.segs_w) { sg = 0; if (++q == P.H) { q = 0; ++n; } }
@@ -150,6 +159,7 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         mbar_arrive_expect_tx(&raw_full[s], xraw_bytes + KPC * T * 64);
         tma_load_4d(st, &mapx, &raw_full[s], c0 - 4, qc, 0, nc);
         tma_load_4d(st + 3072, &mapy, &raw_full[s], c0, qc + PAD - (T - 1), 0, nc);
+        TRACE(0, 2);
       }
     }
   } else if (wid == 1) {
@@ -164,9 +174,11 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         mbar_wait(&drained_bar, (seg - 1) & 1u, 6);
         asm volatile("tcgen05.fence::after_thread_sync;");
       }
+      if (lane == 0) TRACE(1, 0);
       mbar_wait(&op_full[o], oph, 5);
       asm volatile("tcgen05.fence::after_thread_sync;");
       if (lane == 0) {
+        TRACE(1, 1);
         const uint64_t base = make_desc_sw64(smem_u32(smem + (size_t)o * P.op_bytes));
         const uint64_t bb = base + (uint64_t)(b_off / 16);
         for (int mt = 0; mt < ((P.dbg & 2) ? 0 : NMT); ++mt) {
@@ -181,6 +193,7 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         }
         if (P.dbg & 8) mbar_arrive(&op_empty[o]); else umma_commit(&op_empty[o]);      // dbg 8: plain arrive (timing experiment)
         if (kin == SEG_KB - 1 || k == nkb - 1) umma_commit(&accum_bar);
+        TRACE(1, 2);
       }
       __syncwarp();
       if (++o == NOP) { o = 0; oph ^= 1u; }
@@ -199,8 +212,11 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
     unsigned oph = 0;
     for (int k = 0; k < nkb; ++k) {
       const int s = k % NRAW;
+      if (threadIdx.x == 128) TRACE(2, 0);
       mbar_wait(&raw_full[s], (unsigned)(k / NRAW) & 1u, 3);
+      if (threadIdx.x == 128) TRACE(2, 1);
       if (k >= NOP) mbar_wait(&op_empty[o], oph ^ 1u, 2);
+      if (threadIdx.x == 128) TRACE(2, 2);
       const unsigned char* raw = raw_ring + (size_t)s * P.raw_bytes;
       unsigned char* op = smem + (size_t)o * P.op_bytes;
       if (tid < nrows_a && !(P.dbg & 4)) {
@@ -242,12 +258,14 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         *reinterpret_cast<uint4*>(b16 + ((2 ^ sw) << 4)) = pack8<false>(yv + 8);
         *reinterpret_cast<uint4*>(b16 + ((3 ^ sw) << 4)) = pack8<true>(yv + 8);
       }
+      if (threadIdx.x == 128) TRACE(2, 3);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&op_full[o]);
         mbar_arrive(&raw_empty[s]);
       }
+      if (threadIdx.x == 128) TRACE(2, 4);
       const bool run_end = kin == SEG_KB - 1 || k == nkb - 1;
       if (run_end) {
         // ---- drain this run's accumulators into the slot (first run stores, later runs add) ----

@@ -55,6 +55,17 @@ int main(int argc, char** argv) {
   err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("timed launches: %s\n", cudaGetErrorString(err)); return 1; }
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+#ifdef IIC_TC_TRACE
+  {
+    long long tr[3][64][6];
+    cudaMemcpyFromSymbol(tr, iic::fwdtcp::g_trace, sizeof(tr));
+    const long long t0 = tr[0][0][0];
+    printf("k | producer: enter waited issued | mma: enter op_full_ok issued | transform(w4): enter raw_ok op_empty_ok done arrived   (clk rel.)\n");
+    for (int k = 0; k < 24; ++k)
+      printf("%2d | %7lld %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld %7lld %7lld\n", k + 64, tr[0][k][0] - t0, tr[0][k][1] - t0, tr[0][k][2] - t0,
+             tr[1][k][0] - t0, tr[1][k][1] - t0, tr[1][k][2] - t0, tr[2][k][0] - t0, tr[2][k][1] - t0, tr[2][k][2] - t0, tr[2][k][3] - t0, tr[2][k][4] - t0);
+  }
+#endif
   std::vector<double> hJ(E);
   cudaMemcpy(hJ.data(), dJ, E * 8, cudaMemcpyDeviceToHost);
   double max_rel = 0.0, sum_rel = 0.0, sum_rel2 = 0.0; int cnt = 0;
