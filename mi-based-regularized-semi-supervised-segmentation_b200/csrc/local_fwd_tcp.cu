@@ -14,7 +14,7 @@
 //              [24 ch x T rows x 16 px] box (rows outside the map are zero-filled: no contribution)
 //   warps 4-15 transform: one thread per A row (its channel's staged row shifted by dx; fp32 + bf16 [xl|xh]) and one
 //              per B row (copy + bf16 [yh|yl]); the drains: warps 4-7 own row tile 0, warps 8-11 row tile 1
-//   warp 1     MMA issuer
+//   warps 1, 3 MMA issuers (one row tile each)
 // The slot holds D in a coalesced permuted order; reduce_packed_kernel adds the slots in fp64 in a fixed order and
 // writes J in its [dy][dx][i][j] layout.
 #include <cuda_bf16.h>
@@ -122,8 +122,8 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 12); }
-    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], 12); mbar_init(&op_empty[s], 1); }
-    mbar_init(&accum_bar, 1);
+    for (int s = 0; s < NOP; ++s) { mbar_init(&op_full[s], 12); mbar_init(&op_empty[s], 2); }
+    mbar_init(&accum_bar, 2);
     mbar_init(&drained_bar, 12);
     mbar_fence_init();
   }
@@ -162,8 +162,11 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         TRACE(0, 2);
       }
     }
-  } else if (wid == 1) {
-    // ===== MMA issuer =====
+  } else if (wid == 1 || wid == 3) {
+    // ===== MMA issuers: warp 1 owns row tile 0, warp 3 row tile 1 (independent accumulators).  tcgen05.mma issue
+    // blocks at the tensor pipe's rate, so the second warp overlaps the first one's barrier waits and loop overhead;
+    // both commit to the ring barriers =====
+    const int my_mt = wid == 1 ? 0 : 1;
     const uint32_t nn = (uint32_t)NB;
     const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((nn >> 3) << 17) | (8u << 24);
     const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((nn >> 3) << 17) | (8u << 24);
@@ -181,7 +184,7 @@ local_joint_tcp_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_co
         TRACE(1, 1);
         const uint64_t base = make_desc_sw64(smem_u32(smem + (size_t)o * P.op_bytes));
         const uint64_t bb = base + (uint64_t)(b_off / 16);
-        for (int mt = 0; mt < ((P.dbg & 2) ? 0 : NMT); ++mt) {
+        for (int mt = my_mt; mt < ((P.dbg & 2) ? 0 : NMT); mt += 2) {
           const uint64_t ab = base + (uint64_t)(mt * 2 * (ATILE / 16));
           const uint32_t d_tmem = tmem_base + (uint32_t)(mt * NB);
 #pragma unroll
