@@ -243,8 +243,8 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
                                          gx, gy, st);
       if (rc_tc >= 0) return rc_tc;
       // the reference's default cluster count (16 <= K <= 24), padding 1 or 3: row-block tensor-core sweeps
-      // (local_bwd_tcrb.cu); padding 1 only pays on maps with enough rows to fill the SMs
-      if (pad == 3 || getenv("IIC_B200_TCRB_P1")) {
+      // (local_bwd_tcrb.cu; at padding 1 only when the map has enough row blocks to fill the SMs, decided inside)
+      {
         const int rc_rb = local_bwd_tcrb_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                              gx, gy, st);
         if (rc_rb >= 0) return rc_rb;

@@ -78,6 +78,13 @@ __device__ __forceinline__ uint4 pack8(const float* v) {
   return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
 }
 
+#ifdef IIC_TC_TRACE
+__device__ long long g_trace[4][64][6];
+#define TRACE(role, slot) do { if (blockIdx.x == 0 && tt >= 40 && tt < 104) g_trace[role][tt - 40][slot] = clock64(); } while (0)
+#else
+#define TRACE(role, slot) do { } while (0)
+#endif
+
 struct Params {
   int B, H, W, K;
   int KP, NS, R;                // channels padded to 8, channel slices, output rows per item
@@ -162,7 +169,9 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
         const int n = ib / P.nblk, r0 = (ib - n * P.nblk) * R;
         for (int js = 0; js < NS; ++js)
           for (int q = 0; q < NQ; ++q, ++t) {
+            { const int tt = t; (void)tt; TRACE(0, 0); }
             if (t >= NRAW) mbar_wait(&raw_empty[s], sph ^ 1u, 1);
+            { const int tt = t; (void)tt; TRACE(0, 1); }
             mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
             tma_load_4d(raw_ring + s * RAW_MAX, &maps, &raw_full[s], panel * P.PW - 4, r0 - PAD + q, js * SL, n);
             if (++s == NRAW) { s = 0; sph ^= 1u; }
@@ -186,7 +195,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     const int mt = wid - 1;
     const bool mine = mt < ntile;
     const uint32_t rows = (uint32_t)(T * KP);              // rows of one weight part chunk
-    int a = 0;
+    int a = 0, tt = 0;
     unsigned aph = 0;
     for (int i = 0; i < nit; ++i) {
       mbar_wait(&tmem_ready, (unsigned)i & 1u, 6);          // accumulators zeroed
@@ -195,10 +204,12 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
         const int w = i * NS + js, ws = w & 1;
         mbar_wait(&w_full[ws], (unsigned)(w >> 1) & 1u, 7);
         const uint64_t w_base = make_desc_kmajor_noswz(smem_u32(w_ring + ws * wslot_bytes), rows * 16);
-        for (int q = 0; q < NQ; ++q) {
+        for (int q = 0; q < NQ; ++q, ++tt) {
+          if (lane == 0) TRACE(1 + mt, 0);
           mbar_wait(&a_full[a], aph, 5);
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
+            TRACE(1 + mt, 1);
             if (mine) {
               // source row q feeds output rows q - ty, 0 <= q - ty < R
               const int ty_max = q < T - 1 ? q : T - 1;
@@ -216,6 +227,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
                 umma_tf32(d_tmem, a_base + (uint64_t)tx, bt, idesc);
               }
             }
+            TRACE(1 + mt, 2);
             umma_commit(&a_empty[a]);
             if (q == NQ - 1) {
               umma_commit(&w_empty[ws]);
@@ -234,8 +246,13 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
     int a = 0, s = 0;
     unsigned aph = 0, sph = 0;
     for (int t = 0; t < total; ++t) {
+      const int tt = t;
+      (void)tt;
+      if (threadIdx.x == 128) TRACE(3, 0);
       if (t >= NA) mbar_wait(&a_empty[a], aph ^ 1u, 3);
+      if (threadIdx.x == 128) TRACE(3, 1);
       mbar_wait(&raw_full[s], sph, 4);
+      if (threadIdx.x == 128) TRACE(3, 2);
       unsigned char* abuf = a_ring + a * A_ROW;
       const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_MAX);
       for (int px = tid; px < SW; px += 128) {
@@ -253,6 +270,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncwarp();
       if (lane == 0) mbar_arrive(&a_full[a]);
+      if (threadIdx.x == 128) TRACE(3, 3);
       if (++a == NA) { a = 0; aph ^= 1u; }
       if (++s == NRAW) { s = 0; sph ^= 1u; }
     }
@@ -279,22 +297,39 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
       const int col0 = panel * P.PW;
       mbar_wait(&accum_full, (unsigned)i & 1u, 8);
       asm volatile("tcgen05.fence::after_thread_sync;");
+      // The MMAs of the next item wait for this drain (all TMEM columns are in use), so it is kept short: the 2 x 24
+      // accumulator columns of two output rows are fetched with six back-to-back tcgen05.ld and ONE wait, then stored.
+      const int rv = (P.H - r0 < R) ? P.H - r0 : R;            // output rows of this item
       for (int mt = 0; mt < ntile; ++mt) {
         const int cp = mt * 128 + q4 * 32 + lane;            // column inside the panel
         const int c = col0 + cp;
-        for (int orow = 0; orow < R && r0 + orow < P.H; ++orow) {
-          float* dst = P.out + (size_t)n * P.K * plane + (size_t)(r0 + orow) * P.W + c;
-          for (int ch = 0; ch < KP; ch += 8) {
-            uint32_t v[8];
-            const uint32_t taddr = lane_base + (uint32_t)((mt * R + orow) * KP + ch);
-            asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                         : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
-                         : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (c < P.W && cp < P.PW) {
+        const bool live = c < P.W && cp < P.PW;
+        for (int orow = 0; orow < rv; orow += 2) {
+          uint32_t v[2][24];
 #pragma unroll
-              for (int o = 0; o < 8; ++o)
-                if (ch + o < P.K) dst[(size_t)(ch + o) * plane] = g * __uint_as_float(v[o]);
+          for (int h = 0; h < 2; ++h) {
+            const int orh = orow + h < R ? orow + h : orow;     // the pair's second row may not exist: re-read the first
+#pragma unroll
+            for (int ch = 0; ch < 24; ch += 8) {
+              if (ch < KP) {
+                const uint32_t taddr = lane_base + (uint32_t)((mt * R + orh) * KP + ch);
+                asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                             : "=r"(v[h][ch]), "=r"(v[h][ch + 1]), "=r"(v[h][ch + 2]), "=r"(v[h][ch + 3]), "=r"(v[h][ch + 4]),
+                               "=r"(v[h][ch + 5]), "=r"(v[h][ch + 6]), "=r"(v[h][ch + 7])
+                             : "r"(taddr));
+              }
+            }
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+          if (live) {
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+              if (orow + h < rv) {
+                float* dst = P.out + (size_t)n * P.K * plane + (size_t)(r0 + orow + h) * P.W + c;
+#pragma unroll
+                for (int o = 0; o < 24; ++o)
+                  if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+              }
             }
           }
         }
@@ -389,6 +424,9 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
   if (!img) return -1;
   const int nblk = (H + R - 1) / R;
   const int n_items = B * nblk * npanel;
+  // 3 x 3 window: the FFMA2 kernel is as fast unless there are enough row blocks to keep every SM busy (measured:
+  // (32,20,224,224) 0.32 ms vs 0.42 ms, (8,20,112,112) no gain)
+  if (pad == 1 && n_items < 2 * sms && !getenv("IIC_B200_TCRB_P1")) return -1;
   const int grid = n_items < sms ? n_items : sms;
   float* img_x = img;
   float* img_y = img + ((size_t)NS * wslice + 1023) / 1024 * 256;      // 1 KB aligned second image

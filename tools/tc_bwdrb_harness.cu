@@ -55,6 +55,18 @@ int main(int argc, char** argv) {
   err = cudaDeviceSynchronize();
   if (err != cudaSuccess) { printf("timed launches: %s\n", cudaGetErrorString(err)); return 1; }
   float ms; cudaEventElapsedTime(&ms, e0, e1); ms /= reps;
+#ifdef IIC_TC_TRACE
+  {
+    long long tr[4][64][6];
+    cudaMemcpyFromSymbol(tr, iic::bwdrb::g_trace, sizeof(tr));
+    const long long t0 = tr[0][0][0];
+    printf("stage | producer: enter waited | issuer0: enter a_full_ok issued | issuer1: enter a_full_ok issued | transform: enter a_empty_ok raw_ok done\n");
+    for (int k = 0; k < 30; ++k)
+      printf("%3d | %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld | %7lld %7lld %7lld %7lld\n", k + 40, tr[0][k][0] - t0, tr[0][k][1] - t0,
+             tr[1][k][0] - t0, tr[1][k][1] - t0, tr[1][k][2] - t0, tr[2][k][0] - t0, tr[2][k][1] - t0, tr[2][k][2] - t0,
+             tr[3][k][0] - t0, tr[3][k][1] - t0, tr[3][k][2] - t0, tr[3][k][3] - t0);
+  }
+#endif
   std::vector<float> gx(n), gy(n);
   cudaMemcpy(gx.data(), dgx, n * 4, cudaMemcpyDeviceToHost);
   cudaMemcpy(gy.data(), dgy, n * 4, cudaMemcpyDeviceToHost);
