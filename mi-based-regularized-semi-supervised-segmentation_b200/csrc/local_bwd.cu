@@ -213,6 +213,9 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
 int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                        long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
                        const float* grad_loss, float* gx, float* gy, cudaStream_t st);
+int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                         long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                         const float* grad_loss, float* gx, float* gy, cudaStream_t st);
 }
 using namespace iic;
 
@@ -242,6 +245,12 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
       const int rc_tc = local_bwd_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                          gx, gy, st);
       if (rc_tc >= 0) return rc_tc;
+      // 10 clusters, padding 1 (config 2): row-block tensor-core sweeps with the leftover-slot MMA (local_bwd_tcrb10.cu)
+      if (!getenv("IIC_B200_NO_TC10")) {
+        const int rc_10 = local_bwd_tcrb10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                               gx, gy, st);
+        if (rc_10 >= 0) return rc_10;
+      }
       // the reference's default cluster count (16 <= K <= 24), padding 1 or 3: row-block tensor-core sweeps
       // (local_bwd_tcrb.cu; at padding 1 only when the map has enough row blocks to fill the SMs, decided inside)
       {

@@ -131,6 +131,8 @@ LOCAL_CASES = [
     (1, 10, 20, 512, 1, 1024),    # wide map: the backward cuts it into column panels
     (1, 20, 18, 300, 3, 1024),    # wide map, 7 x 7, last panel narrower
     (2, 20, 56, 56, 1, 1024),     # K=20, p=1
+    (6, 10, 224, 224, 1, 512),    # config-2 shape with enough rows (>= 8 per SM) for the K = 10 tensor-core backward
+    (12, 9, 112, 112, 1, 512),    # K = 9 (one leftover channel), one pixel tile
     (2, 4, 33, 45, 2, 512),       # T=5, odd sizes, W % 4 != 0
     (1, 3, 30, 70, 0, 512),       # T=1
     (1, 5, 20, 40, 4, 512),       # T=9 (row jobs)
