@@ -56,6 +56,11 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)", 1965.0
 
 
+# dram bytes per launch of the dominant kernel from one `ncu --set full` capture (profiles/r01_ncu_tc_kernels.txt); None until measured
+TRAFFIC_BWD = (217.3e6, "ncu --set full, profiles/r01_ncu_local_bwd_tcrb10.txt: dram__bytes_read 133.4 MB + dram__bytes_write 83.8 MB per "
+               "launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)")
+
+
 def bf16_peak():
     """Measured dense bf16 TFLOP/s (burst figure: the kernel is timed alone), else the profiling guide's fallback."""
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -331,21 +336,27 @@ def run_b200(args):
     t_joint = timed_graph(lambda: iops.ops.local_joint(xs, ys, None, pad, patch, patch, half, half, True))
     t_epi = timed_graph(lambda: iops.ops.local_epilogue(J0, K, pad, 1.0))
     t_bwd = timed_graph(lambda: iops.ops.local_backward(xs, ys, None, Wx0, Wy0, one, pad, patch, patch, half, half))
-    bwd_launch_ms = t_bwd                                     # ONE launch does both sweeps (+ a 8.6 KB D2D copy node)
+    bwd_launch_ms = t_bwd                                     # ONE launch does both sweeps (+ the tiny weight-image launch)
+    tc10 = not os.environ.get("IIC_B200_NO_TC10") and not os.environ.get("IIC_B200_NO_TC")
     alg_bytes_launch = 16.0 * K * B * H * W                   # read both maps + write both gradients, fp32
     achieved = alg_bytes_launch / (bwd_launch_ms * 1e-3) / 1e9
     sm_mhz = (clocks or {}).get("sm_mhz") or sm_max
     fma_per_launch = 2 * K * K * (2 * pad + 1) ** 2 * B * H * W   # useful FMAs of both sweeps
     fp32_peak = 148 * 128 * sm_mhz * 1e6                      # FMA/s at the observed clock
-    roofline = {"kernel": "local_bwd_fast_kernel<10,1,16,4,5,false>", "bound": "hbm", "achieved": round(achieved, 1),
+    roofline = {"kernel": "local_bwd_tcrb10_kernel (tcgen05, both gradient sweeps in one launch)" if tc10
+                else "local_bwd_fast_kernel<10,1,16,4,5,false>", "bound": "hbm", "achieved": round(achieved, 1),
                 "peak": hbm_peak, "unit": "GB/s", "frac": round(achieved / hbm_peak, 4),
-                "traffic": 232.0e6, "traffic_source": "ncu --set full, profiles/r01_ncu_local_bwd_fast_v3.txt: "
-                                                      "dram__bytes_read 147.7 MB + dram__bytes_write 84.3 MB per launch "
-                                                      "(algorithmic 256.9 MB; the tail of the gradient writes is still in L2)",
+                "traffic": TRAFFIC_BWD[0] if tc10 else 232.0e6,
+                "traffic_source": TRAFFIC_BWD[1] if tc10 else
+                "ncu --set full, profiles/r01_ncu_local_bwd_fast_v3.txt: dram__bytes_read 147.7 MB + dram__bytes_write "
+                "84.3 MB per launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)",
                 "peak_source": peak_src, "launch_ms": round(bwd_launch_ms, 4),
-                "note": "the kernel is FP32-FMA bound, not HBM bound (AI = K*T^2/4 = 22.5 flop/B, ridge ~11): "
-                        "fp32_fma_frac is its share of 148 SM x 128 FMA/clk at the sampled SM clock; at 100 % of the "
-                        "FMA pipe the whole step would reach 0.51 of the HBM roofline",
+                "note": ("the backward runs on the tensor cores (one tf32 + one bf16 correction MMA per product, 8 MMAs per "
+                         "source row and 128-pixel tile): it is bound by the tensor pipe's ~62 clk per M=128 instruction, "
+                         "not by HBM; fp32_fma_frac compares its useful FMAs with the FP32 SIMT peak it replaced") if tc10 else
+                        ("the kernel is FP32-FMA bound, not HBM bound (AI = K*T^2/4 = 22.5 flop/B, ridge ~11): "
+                         "fp32_fma_frac is its share of 148 SM x 128 FMA/clk at the sampled SM clock; at 100 % of the "
+                         "FMA pipe the whole step would reach 0.51 of the HBM roofline"),
                 "fp32_fma_frac": round(fma_per_launch / (bwd_launch_ms * 1e-3) / fp32_peak, 4),
                 "step_breakdown_ms": {"local_joint+reduce(+simplex)": round(t_joint, 4), "local_epilogue": round(t_epi, 4),
                                       "local_backward": round(t_bwd, 4)},
@@ -466,9 +477,9 @@ def run_b200(args):
 
     if rank == 0:
         cpu_v, cpu_threads, cpu_best, cpu_times = cpu_port_throughput(args.cpu_sample_batch, 5)
-        # our kernels per step: local = joint + slot reduce + epilogue + backward (4; the simplex assertion is
-        # fused into the joint), global = joint + epilogue + backward (3)
-        launches = 7 * args.steps
+        # our kernels per step: local = joint + slot reduce + epilogue + weight image + backward (5; the simplex
+        # assertion is fused into the joint), global = joint + epilogue + backward (3)
+        launches = 8 * args.steps
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,

@@ -36,7 +36,7 @@ constexpr int WROWS = T * KP;            // 48 rows per weight chunk
 constexpr int W_TILE = 4 * WROWS * 16;   // 3072
 constexpr int W_IMG = 4 * W_TILE;        // tx 0, 1, 2 and the leftover tile
 constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
-constexpr int SMEM_BYTES = NA * A_SLOT + W_IMG + NRAW * RAW_SLOT + 1024;
+constexpr int SMEM_BYTES = NA * A_SLOT + 2 * W_IMG + NRAW * RAW_SLOT + 1024;   // both sweeps' weight images stay resident
 
 __device__ __forceinline__ uint64_t make_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
@@ -91,15 +91,17 @@ __device__ long long g_trace[4][64][6];
 
 struct Params {
   int B, H, W, K;
-  const float* wimg;
+  const float* wimg;            // two images: sweep 0 (dL/dx, source y) and sweep 1 (dL/dy, source x)
   const float* grad_loss;
-  float* out;
+  float* out[2];
 };
 
 // Wc[cin][ty*3+tx][Kp4] -> tiles tx = 0..2 (input channels 0-7) and the leftover tile (slots (ch 8, ch 9) x tx);
 // each tile {fp32 [2 chunks][48 rows][4 slots], bf16 [wh, wl][48 rows][8 slots]}, rows ordered (2-ty)*16 + o
-__global__ void weight_image_kernel(const float* __restrict__ Wc, float* __restrict__ img, int K, int Kp4) {
-  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void weight_image_kernel(const float* __restrict__ Wx, const float* __restrict__ Wy, float* __restrict__ img2, int K, int Kp4) {
+  const float* Wc = blockIdx.x == 0 ? Wx : Wy;
+  float* img = img2 + blockIdx.x * (W_IMG / 4);
+  const int e = threadIdx.x;
   if (e >= 4 * WROWS) return;
   const int row = e % WROWS, tile = e / WROWS;
   const int ty = T - 1 - row / KP, o = row % KP;
@@ -131,14 +133,14 @@ __device__ __forceinline__ Chunk next_chunk(long long r, long long R1, int H, in
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
+local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], a_full[NA], a_empty[NA], w_full, accum_full[2], tmem_ready[2];
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* a_ring = smem;
   unsigned char* w_img = smem + NA * A_SLOT;
-  unsigned char* raw_ring = w_img + W_IMG;
+  unsigned char* raw_ring = w_img + 2 * W_IMG;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows_total = (long long)P.B * P.H;
   const long long R0 = (long long)blockIdx.x * rows_total / gridDim.x;
@@ -169,9 +171,11 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
   if (wid == 0) {
     // ===== TMA producer: one source row (all K channels) per stage =====
     if (lane == 0) {
-      tma_prefetch_desc(&maps);
+      tma_prefetch_desc(&map0);
+      tma_prefetch_desc(&map1);
       int t = 0, s = 0;
       unsigned sph = 0;
+      for (int sweep = 0; sweep < 2; ++sweep)
       for (long long r = R0; r < R1;) {
         const Chunk c = next_chunk(r, R1, P.H, rc);
         for (int q = 0; q < c.nr + T - 1; ++q, ++t) {
@@ -179,7 +183,7 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
           if (t >= NRAW) mbar_wait(&raw_empty[s], sph ^ 1u, 1);
           { const int tt = t; (void)tt; TRACE(0, 1); }
           mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
-          tma_load_4d(raw_ring + s * RAW_SLOT, &maps, &raw_full[s], -4, c.h0 - PAD + q, 0, c.n);
+          tma_load_4d(raw_ring + s * RAW_SLOT, sweep == 0 ? &map0 : &map1, &raw_full[s], -4, c.h0 - PAD + q, 0, c.n);
           if (++s == NRAW) { s = 0; sph ^= 1u; }
         }
         r += c.nr;
@@ -188,8 +192,8 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
   } else if (wid == 3) {
     // ===== the weight image, once =====
     if (lane == 0) {
-      mbar_arrive_expect_tx(&w_full, W_IMG);
-      bulk_load(w_img, P.wimg, W_IMG, &w_full);
+      mbar_arrive_expect_tx(&w_full, 2 * W_IMG);
+      bulk_load(w_img, P.wimg, 2 * W_IMG, &w_full);
     }
   } else if (wid == 1 || wid == 2 || wid == 12 || wid == 13) {
     // ===== MMA issuers.  Traced with clock64(): one lane issues an MMA every ~88 clk and every mbarrier wait costs it
@@ -200,11 +204,13 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
     const int par = wid >= 12 ? 1 : 0;
     const bool mine = mt < ntile;
     mbar_wait(&w_full, 0u, 7);
-    const uint64_t w_base = make_desc_kmajor_noswz(smem_u32(w_img), WROWS * 16);
+    const uint64_t w_base0 = make_desc_kmajor_noswz(smem_u32(w_img), WROWS * 16);
     int a = 0, i = 0, tt = 0;
     (void)tt;
     unsigned aph = 0;
+    for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
+      const uint64_t w_base = w_base0 + (uint64_t)(sweep * (W_IMG / 16));
       const Chunk c = next_chunk(r, R1, P.H, rc);
       const int buf = i & 1;
       mbar_wait(&tmem_ready[buf], (unsigned)(i >> 1) & 1u, 6);   // this buffer's accumulators are zeroed
@@ -256,6 +262,7 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
     const int grp = wid >= 8 ? 1 : 0;
     int a = 0, s = 0, t = 0;
     unsigned aph = 0, sph = 0;
+    for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1;) {
       const Chunk c = next_chunk(r, R1, P.H, rc);
       for (int q = 0; q < c.nr + T - 1; ++q, ++t) {
@@ -324,6 +331,7 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
     zero_accumulators(0);
     zero_accumulators(1);
     int i = 0;
+    for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
       const Chunk c = next_chunk(r, R1, P.H, rc);
       const int buf = i & 1;
@@ -351,7 +359,7 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap maps, const Params P
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (orow + h < c.nr) {
-                float* dst = P.out + (size_t)c.n * P.K * plane + (size_t)(c.h0 + orow + h) * P.W + col;
+                float* dst = P.out[sweep] + (size_t)c.n * P.K * plane + (size_t)(c.h0 + orow + h) * P.W + col;
 #pragma unroll
                 for (int o = 0; o < 10; ++o)
                   if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
@@ -392,7 +400,7 @@ static float* weight_scratch(int device, cudaStream_t st) {
       cudaGetLastError();
       return nullptr;
     }
-    if (cudaMalloc(&buf[device], 2 * W_IMG) != cudaSuccess) {
+    if (cudaMalloc(&buf[device], 2 * W_IMG) != cudaSuccess) {   // both sweeps' images
       cudaGetLastError();
       buf[device] = nullptr;
     }
@@ -423,15 +431,11 @@ int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long lo
     attr_set = true;
   }
   const int Kp4 = (K + 3) & ~3;
-  float* img_x = img;
-  float* img_y = img + W_IMG / 4;
-  weight_image_kernel<<<1, 4 * WROWS, 0, st>>>(Wx, img_x, K, Kp4);
-  weight_image_kernel<<<1, 4 * WROWS, 0, st>>>(Wy, img_y, K, Kp4);
+  weight_image_kernel<<<2, 4 * WROWS, 0, st>>>(Wx, Wy, img, K, Kp4);
   IIC_CHECK_CUDA(cudaGetLastError());
-  Params Pgx{B, H, W, K, img_x, grad_loss, gx};
-  Params Pgy{B, H, W, K, img_y, grad_loss, gy};
-  local_bwd_tcrb10_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, Pgx);       // dL/dx from y
-  local_bwd_tcrb10_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(mx, Pgy);       // dL/dy from x
+  Params P{B, H, W, K, img, grad_loss, {gx, gy}};
+  // one launch, two sweeps per CTA: dL/dx from y (sweep 0), then dL/dy from x (sweep 1)
+  local_bwd_tcrb10_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
