@@ -32,7 +32,7 @@ constexpr int A_PART = 2 * APX * 16;     // fp32 part / bf16 part of one row buf
 constexpr int A_ROW = 2 * A_PART;        // 17408
 constexpr int NA_MAX = 6, NRAW_MAX = 8;  // ring depths are chosen per launch from the shared memory the weight slots leave
 constexpr int RAW_MAX = SL * 256 * 4;    // 8192
-constexpr int NTHREADS = 384;
+constexpr int NTHREADS = 448;            // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-7 transform, 8-11 epilogue
 constexpr int SMEM_LIMIT = 225 * 1024;    // dynamic shared memory we may ask for (the static barriers share the 227 KB)
 
 __device__ __forceinline__ uint64_t make_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo_bytes) {
@@ -143,8 +143,8 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 2); }
-    mbar_init(&accum_full, 2);
+    for (int s = 0; s < 2; ++s) { mbar_init(&w_full[s], 1); mbar_init(&w_empty[s], 4); }
+    mbar_init(&accum_full, 4);
     mbar_init(&tmem_ready, 4);
     mbar_fence_init();
   }
@@ -190,9 +190,12 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
                   P.wslice_bytes, &w_full[s]);
       }
     }
-  } else if (wid == 1 || wid == 2) {
-    // ===== MMA issuers: warp 1 = pixel tile 0, warp 2 = pixel tile 1 =====
-    const int mt = wid - 1;
+  } else if (wid == 1 || wid == 2 || wid == 12 || wid == 13) {
+    // ===== MMA issuers: (pixel tile 0 / 1) x (even / odd source rows).  A lane issues an MMA only every ~88 clk and pays
+    // ~300 clk per barrier poll, the pipe takes one every ~62 clk; the accumulators are zeroed and every MMA accumulates,
+    // so the issue order is free (see local_bwd_tcrb10.cu) =====
+    const int mt = (wid == 1 || wid == 12) ? 0 : 1;
+    const int par = wid >= 12 ? 1 : 0;
     const bool mine = mt < ntile;
     const uint32_t rows = (uint32_t)(T * KP);              // rows of one weight part chunk
     int a = 0, tt = 0;
@@ -205,11 +208,15 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
         mbar_wait(&w_full[ws], (unsigned)(w >> 1) & 1u, 7);
         const uint64_t w_base = make_desc_kmajor_noswz(smem_u32(w_ring + ws * wslot_bytes), rows * 16);
         for (int q = 0; q < NQ; ++q, ++tt) {
-          if (lane == 0) TRACE(1 + mt, 0);
+          if ((q & 1) != par) {                          // the other issuer of this tile takes this source row
+            if (++a == NA) { a = 0; aph ^= 1u; }
+            continue;
+          }
+          if (lane == 0 && par == 0) TRACE(1 + mt, 0);
           mbar_wait(&a_full[a], aph, 5);
           asm volatile("tcgen05.fence::after_thread_sync;");
           if (lane == 0) {
-            TRACE(1 + mt, 1);
+            if (par == 0) TRACE(1 + mt, 1);
             if (mine) {
               // source row q feeds output rows q - ty, 0 <= q - ty < R
               const int ty_max = q < T - 1 ? q : T - 1;
@@ -227,9 +234,9 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
                 umma_tf32(d_tmem, a_base + (uint64_t)tx, bt, idesc);
               }
             }
-            TRACE(1 + mt, 2);
+            if (par == 0) TRACE(1 + mt, 2);
             umma_commit(&a_empty[a]);
-            if (q == NQ - 1) {
+            if (q >= NQ - 2) {                             // this issuer's last source row of the slice
               umma_commit(&w_empty[ws]);
               if (js == NS - 1) umma_commit(&accum_full);
             }
@@ -274,7 +281,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
       if (++a == NA) { a = 0; aph ^= 1u; }
       if (++s == NRAW) { s = 0; sph ^= 1u; }
     }
-  } else if (wid >= 8) {
+  } else if (wid >= 8 && wid < 12) {
     // ===== epilogue: drain the R x tiles x KP accumulator columns, store, zero them for the next item =====
     const int q4 = wid & 3;
     const float g = P.grad_loss ? __ldg(P.grad_loss) : 1.f;
