@@ -336,7 +336,7 @@ def run_b200(args):
     t_joint = timed_graph(lambda: iops.ops.local_joint(xs, ys, None, pad, patch, patch, half, half, True))
     t_epi = timed_graph(lambda: iops.ops.local_epilogue(J0, K, pad, 1.0))
     t_bwd = timed_graph(lambda: iops.ops.local_backward(xs, ys, None, Wx0, Wy0, one, pad, patch, patch, half, half))
-    bwd_launch_ms = t_bwd                                     # ONE launch does both sweeps (+ the tiny weight-image launch)
+    bwd_launch_ms = t_bwd                                     # ONE launch does both sweeps
     tc10 = not os.environ.get("IIC_B200_NO_TC10") and not os.environ.get("IIC_B200_NO_TC")
     alg_bytes_launch = 16.0 * K * B * H * W                   # read both maps + write both gradients, fp32
     achieved = alg_bytes_launch / (bwd_launch_ms * 1e-3) / 1e9
@@ -477,9 +477,9 @@ def run_b200(args):
 
     if rank == 0:
         cpu_v, cpu_threads, cpu_best, cpu_times = cpu_port_throughput(args.cpu_sample_batch, 5)
-        # our kernels per step: local = joint + slot reduce + epilogue + weight image + backward (5; the simplex
-        # assertion is fused into the joint), global = joint + epilogue + backward (3)
-        launches = 8 * args.steps
+        # our kernels per step: local = joint + slot reduce + epilogue + backward (4; the simplex assertion is fused
+        # into the joint, the backward builds its weight images itself), global = joint + epilogue + backward (3)
+        launches = 7 * args.steps
         line = {
             "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_step, 4), "higher_is_better": True,

@@ -91,18 +91,17 @@ __device__ long long g_trace[4][64][6];
 
 struct Params {
   int B, H, W, K;
-  const float* wimg;            // two images: sweep 0 (dL/dx, source y) and sweep 1 (dL/dy, source x)
+  const float* Wc[2];           // coefficient tensors of iic_local_epilogue: sweep 0 = Wx (dL/dx, source y), sweep 1 = Wy
+  int Kp4;                      // their row length
   const float* grad_loss;
   float* out[2];
 };
 
 // Wc[cin][ty*3+tx][Kp4] -> tiles tx = 0..2 (input channels 0-7) and the leftover tile (slots (ch 8, ch 9) x tx);
-// each tile {fp32 [2 chunks][48 rows][4 slots], bf16 [wh, wl][48 rows][8 slots]}, rows ordered (2-ty)*16 + o
-__global__ void weight_image_kernel(const float* __restrict__ Wx, const float* __restrict__ Wy, float* __restrict__ img2, int K, int Kp4) {
-  const float* Wc = blockIdx.x == 0 ? Wx : Wy;
-  float* img = img2 + blockIdx.x * (W_IMG / 4);
-  const int e = threadIdx.x;
-  if (e >= 4 * WROWS) return;
+// each tile {fp32 [2 chunks][48 rows][4 slots], bf16 [wh, wl][48 rows][8 slots]}, rows ordered (2-ty)*16 + o.
+// Every CTA builds both sweeps' images (2 x 12 KB from 2 x 3.6 KB of L2-resident coefficients) straight into its own
+// shared memory: no extra launch, no scratch allocation.  e = row in [0, 2 * 4 * 48).
+__device__ __forceinline__ void build_weight_row(const float* __restrict__ Wc, unsigned char* img, int e, int K, int Kp4) {
   const int row = e % WROWS, tile = e / WROWS;
   const int ty = T - 1 - row / KP, o = row % KP;
   float v[8];
@@ -111,7 +110,7 @@ __global__ void weight_image_kernel(const float* __restrict__ Wx, const float* _
     int cin, tx;
     if (tile < 3) { cin = q; tx = tile; }
     else { cin = 8 + (q & 1); tx = q >> 1; }                 // slots (8,tx0) (9,tx0) (8,tx1) (9,tx1) (8,tx2) (9,tx2) - -
-    v[q] = (cin < K && o < K && tx < T) ? Wc[((size_t)cin * T * T + ty * T + tx) * Kp4 + o] : 0.f;
+    v[q] = (cin < K && o < K && tx < T) ? __ldg(Wc + ((size_t)cin * T * T + ty * T + tx) * Kp4 + o) : 0.f;
   }
   float4* t4 = reinterpret_cast<float4*>(img) + (size_t)tile * (4 * WROWS);
   t4[row] = make_float4(v[0], v[1], v[2], v[3]);
@@ -155,7 +154,7 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
   if (threadIdx.x == 0) {
     for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
-    mbar_init(&w_full, 1);
+    mbar_init(&w_full, 4);
     for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 4); mbar_init(&tmem_ready[s], 4); }
     mbar_fence_init();
   }
@@ -188,12 +187,6 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
         }
         r += c.nr;
       }
-    }
-  } else if (wid == 3) {
-    // ===== the weight image, once =====
-    if (lane == 0) {
-      mbar_arrive_expect_tx(&w_full, 2 * W_IMG);
-      bulk_load(w_img, P.wimg, 2 * W_IMG, &w_full);
     }
   } else if (wid == 1 || wid == 2 || wid == 12 || wid == 13) {
     // ===== MMA issuers.  Traced with clock64(): one lane issues an MMA every ~88 clk and every mbarrier wait costs it
@@ -330,6 +323,14 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
     };
     zero_accumulators(0);
     zero_accumulators(1);
+    // the weight images: these four warps are idle until the first chunk is finished
+    for (int e = threadIdx.x - 14 * 32; e < 2 * 4 * WROWS; e += 128) {
+      const int sweep = e / (4 * WROWS);
+      build_weight_row(P.Wc[sweep], w_img + sweep * W_IMG, e - sweep * 4 * WROWS, P.K, P.Kp4);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&w_full);
     int i = 0;
     for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
@@ -391,23 +392,6 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static float* weight_scratch(int device, cudaStream_t st) {
-  static float* buf[64] = {nullptr};
-  if (device < 0 || device >= 64) return nullptr;
-  if (!buf[device]) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    if (cudaMalloc(&buf[device], 2 * W_IMG) != cudaSuccess) {   // both sweeps' images
-      cudaGetLastError();
-      buf[device] = nullptr;
-    }
-  }
-  return buf[device];
-}
-
 }  // namespace bwdrb10
 
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
@@ -423,17 +407,13 @@ int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long lo
   CUtensorMap mx, my;
   if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh)) return -1;
   if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh)) return -1;
-  float* img = weight_scratch(device, st);
-  if (!img) return -1;
   static bool attr_set = false;
   if (!attr_set) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(local_bwd_tcrb10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   const int Kp4 = (K + 3) & ~3;
-  weight_image_kernel<<<2, 4 * WROWS, 0, st>>>(Wx, Wy, img, K, Kp4);
-  IIC_CHECK_CUDA(cudaGetLastError());
-  Params P{B, H, W, K, img, grad_loss, {gx, gy}};
+  Params P{B, H, W, K, {Wx, Wy}, Kp4, grad_loss, {gx, gy}};
   // one launch, two sweeps per CTA: dL/dx from y (sweep 0), then dL/dy from x (sweep 1)
   local_bwd_tcrb10_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
   IIC_CHECK_CUDA(cudaGetLastError());
