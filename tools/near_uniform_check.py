@@ -1,5 +1,14 @@
+"""Ill-conditioned inputs: near-uniform cluster maps (mutual information ~ 0, so J - min J cancels almost everything).
+
+    python tools/near_uniform_check.py
+
+Compares the tensor-core path, the FP32 path (IIC_B200_NO_TC=1) and the fp64 oracle on the loss and the gradients for
+K = 20 (padding 3) and K = 128 (padding 1) maps made by a weak random 1x1 head, the regime of the first training
+iterations.
+"""
 import os, sys, torch, numpy as np
-sys.path.insert(0, "/root/repo"); sys.path.insert(0, "/root/repo/oracle")
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "oracle"))
 import iic_b200, iic_oracle as O
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
