@@ -14,8 +14,9 @@
 // A work item is a block of R output rows of one image (all accumulators = R x tiles x 24 TMEM columns <= 512).  The
 // epilogue zeroes the accumulators after draining them, so every MMA accumulates.  Split product, pixel-major
 // no-swizzle K-major A operand with tap column shifts as descriptor start shifts: see local_bwd_tc.cu; four issuing
-// warps ((128-pixel tile 0 / 1) x (even / odd source rows)): see local_bwd_tcrb10.cu.  Per item: for each 8-channel slice the slice's weight image (64*T*T*24 bytes, double
-// buffered, one bulk copy) stays resident while the R + T - 1 source rows stream through a 3-slot operand ring.
+// warps ((128-pixel tile 0 / 1) x (even / odd source rows)): see local_bwd_tcrb10.cu.  Per item: for each 8-channel
+// slice the slice's weight image (64*T*T*24 bytes, double buffered, one bulk copy) stays resident while the
+// R + T - 1 source rows stream through the operand ring.
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
