@@ -192,14 +192,14 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
     // ===== MMA issuers.  Traced with clock64(): one lane issues an MMA every ~88 clk and every mbarrier wait costs it
     // ~300 clk even when the barrier is complete, yet the tensor pipe accepts the MMAs of two lanes side by side.  The
     // accumulators are zeroed and every MMA accumulates, so the issue order does not matter: four issuing warps --
-    // (pixel tile 0 / 1) x (even / odd source rows) -- each commit to the ring barriers. =====
+    // (pixel tile 0 / 1) x (even / odd stages) -- each commit to the ring barriers. =====
     const int mt = (wid == 1 || wid == 12) ? 0 : 1;
     const int par = wid >= 12 ? 1 : 0;
     const bool mine = mt < ntile;
     mbar_wait(&w_full, 0u, 7);
     const uint64_t w_base0 = make_desc_kmajor_noswz(smem_u32(w_img), WROWS * 16);
-    int a = 0, i = 0, tt = 0;
-    (void)tt;
+    static_assert(NA % 2 == 0 && NRAW % 2 == 0, "the stage-parity split needs even ring depths");
+    int a = 0, i = 0, tt = 0;                              // tt = global stage index
     unsigned aph = 0;
     for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
@@ -210,7 +210,11 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
       asm volatile("tcgen05.fence::after_thread_sync;");
       const int nq = c.nr + T - 1;
       for (int q = 0; q < nq; ++q, ++tt) {
-        if ((q & 1) != par) {                            // the other issuer of this tile takes this source row
+        // Split by the GLOBAL stage parity, like the transform groups, and with even ring depths: a ring slot then always
+        // belongs to the same transform group and the same issuer pair, who wait on every phase of its barriers.  (Split
+        // by the row index inside the chunk, a slot changes hands after a chunk with an odd number of rows, and an issuer
+        // that skipped a phase of a_full passes its parity wait two phases early: tools/barrier_sim.py.)
+        if ((tt & 1) != par) {                           // the other issuer of this tile takes this source row
           if (++a == NA) { a = 0; aph ^= 1u; }
           continue;
         }

@@ -1,0 +1,237 @@
+"""Randomised discrete-event model of the mbarrier protocols of the row-block tensor-core backward kernels
+(csrc/local_bwd_tcrb.cu, csrc/local_bwd_tcrb10.cu): every warp that arrives on or waits for a barrier is an agent, the
+scheduler interleaves them at random, `tcgen05.commit` arrivals are delayed until the issuer's earlier MMAs have
+"completed" (in issue order, after a random delay).  It looks for deadlocks (nobody can run, not everybody is done) and
+for ring-slot races (a slot rewritten before its readers are done, read before it is written).
+
+mbarrier semantics modelled: an expected arrival count per phase; the phase completes when that many arrivals have
+been counted -- whichever phase the arriving agent *meant*; `wait(parity)` succeeds when the barrier's current phase
+parity differs from `parity` (so a waiter that falls two phases behind aliases).
+
+    python tools/barrier_sim.py            # all configurations, 300 random schedules each
+
+No GPU needed; `tests/test_host_cpu.py` runs a short version.
+"""
+from __future__ import annotations
+
+import random
+import sys
+
+
+class Bar:
+    def __init__(self, name, count):
+        self.name, self.count, self.pending, self.phase = name, count, count, 0
+
+    def arrive(self):
+        self.pending -= 1
+        if self.pending == 0:
+            self.phase += 1
+            self.pending = self.count
+
+    def ready(self, parity):
+        return (self.phase & 1) != parity
+
+
+class Deadlock(Exception):
+    pass
+
+
+class Race(Exception):
+    pass
+
+
+class Sim:
+    """Agents are generators yielding ('wait', bar, parity) | ('arrive', bar) | ('commit', issuer_id, bar) |
+    ('mma', issuer_id) | ('own', slot, who) | ('release', slot, who) | ('work',)."""
+
+    def __init__(self, seed):
+        self.rng = random.Random(seed)
+        self.agents = []           # [name, generator, pending_request]
+        self.inflight = {}         # issuer -> list of ['mma' | ('commit', bar), remaining_delay]
+        self.slots = {}            # slot -> (state, who)
+        self.done = set()          # events that have happened: ('transformed', t, warp), ('mma_done', t, issuer)
+
+    def add(self, name, gen):
+        self.agents.append([name, gen, None])
+
+    def run(self, max_steps=2_000_000):
+        live = list(self.agents)
+        for ag in live:
+            ag[2] = next(ag[1], None)
+        steps = 0
+        while True:
+            steps += 1
+            if steps > max_steps:
+                raise Deadlock("step limit")
+            live = [a for a in live if a[2] is not None]
+            # tensor pipe: retire in-flight work of every issuer in order, with random progress
+            progressed = False
+            for iss, q in self.inflight.items():
+                if q and self.rng.random() < 0.5:
+                    q[0][1] -= 1
+                    if q[0][1] <= 0:
+                        kind = q.pop(0)[0]
+                        if kind != "mma":
+                            kind[1].arrive()
+                    progressed = True
+            if not live and not any(self.inflight.values()):
+                return steps
+            runnable = [a for a in live if a[2][0] != "wait" or a[2][1].ready(a[2][2])]
+            if not runnable:
+                if any(self.inflight.values()):
+                    continue
+                raise Deadlock("; ".join(f"{a[0]} waits {a[2][1].name} p{a[2][2]} (phase {a[2][1].phase})" for a in live))
+            ag = self.rng.choice(runnable)
+            req = ag[2]
+            if req[0] == "arrive":
+                req[1].arrive()
+            elif req[0] == "mma":
+                self.inflight.setdefault(req[1], []).append(["mma", self.rng.randint(1, 4)])
+            elif req[0] == "commit":
+                q = self.inflight.setdefault(req[1], [])
+                if q:
+                    q.append([("commit", req[2]), 1])
+                else:
+                    req[2].arrive()
+            elif req[0] == "own":
+                st = self.slots.get(req[1], ("free", None))
+                if st[0] != "free":
+                    raise Race(f"{ag[0]} takes {req[1]} while {st}")
+                self.slots[req[1]] = ("held", req[2])
+            elif req[0] == "release":
+                self.slots[req[1]] = ("free", None)
+            elif req[0] == "done":
+                self.done.add(req[1])
+            elif req[0] == "need":
+                if req[1] not in self.done:
+                    raise Race(f"{ag[0]} passed its wait for {req[1]} before it happened")
+            ag[2] = next(ag[1], None)
+
+
+def rowblock(sim, *, nit, ns, nq_of_item, na, nraw, groups, split_issuers, ntile=2, tmem_bufs=1, warps_per_group=4,
+             split_by="q"):
+    """The protocol of local_bwd_tcrb*.cu.  nq_of_item(i) = source rows (stages) of item i per channel slice."""
+    raw_full = [Bar(f"raw_full{s}", 1) for s in range(nraw)]
+    raw_empty = [Bar(f"raw_empty{s}", warps_per_group) for s in range(nraw)]
+    a_full = [Bar(f"a_full{s}", warps_per_group) for s in range(na)]
+    a_empty = [Bar(f"a_empty{s}", 2) for s in range(na)]
+    n_iss = 2 * (2 if split_issuers else 1)
+    accum_full = [Bar(f"accum_full{b}", n_iss) for b in range(tmem_bufs)]
+    tmem_ready = [Bar(f"tmem_ready{b}", 4) for b in range(tmem_bufs)]
+    stages = [(i, js, q) for i in range(nit) for js in range(ns) for q in range(nq_of_item(i))]
+
+    def producer():
+        s, sph = 0, 0
+        for t, _ in enumerate(stages):
+            if t >= nraw:
+                yield ("wait", raw_empty[s], sph ^ 1)
+            yield ("own", ("raw", s), "tma")
+            yield ("release", ("raw", s), "tma")
+            yield ("arrive", raw_full[s])
+            s += 1
+            if s == nraw:
+                s, sph = 0, sph ^ 1
+
+    def transform(grp, warp):
+        a = s = aph = sph = 0
+        for t, _ in enumerate(stages):
+            if groups == 1 or (t & 1) == grp:
+                if t >= na:
+                    yield ("wait", a_empty[a], aph ^ 1)
+                yield ("wait", raw_full[s], sph)
+                yield ("work",)
+                yield ("arrive", raw_empty[s])
+                yield ("done", ("transformed", t, warp))
+                yield ("arrive", a_full[a])
+            a += 1
+            if a == na:
+                a, aph = 0, aph ^ 1
+            s += 1
+            if s == nraw:
+                s, sph = 0, sph ^ 1
+
+    def issuer(mt, par, iid):
+        a = aph = 0
+        t = -1
+        for i in range(nit):
+            buf = i % tmem_bufs
+            yield ("wait", tmem_ready[buf], (i // tmem_bufs) & 1)
+            for js in range(ns):
+                nq = nq_of_item(i)
+                for q in range(nq):
+                    t += 1
+                    if not split_issuers or ((q if split_by == "q" else t) & 1) == par:
+                        yield ("wait", a_full[a], aph)
+                        for w in range(warps_per_group):
+                            yield ("need", ("transformed", t, w))
+                        if mt < ntile:
+                            yield ("mma", iid)
+                        yield ("commit", iid, a_empty[a])
+                        last = (q >= nq - 2) if split_issuers else (q == nq - 1)
+                        if last and js == ns - 1:
+                            yield ("commit", iid, accum_full[buf])
+                    a += 1
+                    if a == na:
+                        a, aph = 0, aph ^ 1
+
+    def epilogue(warp):
+        for b in range(tmem_bufs):
+            yield ("arrive", tmem_ready[b])
+        for i in range(nit):
+            buf = i % tmem_bufs
+            yield ("wait", accum_full[buf], (i // tmem_bufs) & 1)
+            yield ("work",)
+            if tmem_bufs > 1 or i + 1 < nit:
+                yield ("arrive", tmem_ready[buf])
+
+    sim.add("producer", producer())
+    for g in range(groups):
+        for w in range(warps_per_group):
+            sim.add(f"transform g{g} w{w}", transform(g, w))
+    iid = 0
+    for mt in range(2):
+        for par in range(2 if split_issuers else 1):
+            sim.add(f"issuer mt{mt} par{par}", issuer(mt, par, iid))
+            iid += 1
+    for w in range(4):
+        sim.add(f"epilogue w{w}", epilogue(w))
+
+
+CONFIGS = {
+    # the K = 10 kernel: two transform groups, four issuers, double-buffered accumulators, even ring depths 4 / 6, and
+    # issuers split by the GLOBAL stage parity, so that a ring slot always belongs to the same group and issuer pair
+    "tcrb10 (adopted)": dict(nit=7, ns=1, nq_of_item=lambda i: [10, 9, 10, 3, 10, 5, 10][i], na=4, nraw=6, groups=2,
+                             split_issuers=True, tmem_bufs=2, split_by="t"),
+    "tcrb10, one pixel tile": dict(nit=5, ns=1, nq_of_item=lambda i: [10, 9, 7, 10, 4][i], na=4, nraw=6, groups=2,
+                                   split_issuers=True, tmem_bufs=2, ntile=1, split_by="t"),
+    # its first version split the issuers by the row index inside a chunk: after a chunk with an odd number of rows a
+    # slot alternates between issuer pairs, and an issuer that skipped a phase of a_full passes its parity wait early
+    "tcrb10 with issuers split by row-in-chunk (bug)": dict(nit=7, ns=1, nq_of_item=lambda i: [10, 9, 10, 3, 10, 5, 10][i], na=4,
+                                                            nraw=6, groups=2, split_issuers=True, tmem_bufs=2),
+    # the K = 20 kernel as built: one transform group, four issuers
+    "tcrb T=7 (adopted)": dict(nit=3, ns=3, nq_of_item=lambda i: 27, na=3, nraw=3, groups=1, split_issuers=True),
+    "tcrb T=3 (adopted)": dict(nit=3, ns=3, nq_of_item=lambda i: 12, na=6, nraw=8, groups=1, split_issuers=True),
+    # the reverted experiment: two transform groups with the odd ring depths of T = 7
+    "tcrb T=7, two transform groups (reverted)": dict(nit=3, ns=3, nq_of_item=lambda i: 27, na=3, nraw=3, groups=2,
+                                                      split_issuers=True, ntile=1),
+}
+
+
+def check(name, cfg, runs, seed0=0):
+    bad = None
+    for r in range(runs):
+        sim = Sim(seed0 + r)
+        rowblock(sim, **cfg)
+        try:
+            sim.run()
+        except (Deadlock, Race) as e:
+            bad = f"seed {seed0 + r}: {type(e).__name__}: {e}"
+            break
+    return bad
+
+
+if __name__ == "__main__":
+    runs = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    for name, cfg in CONFIGS.items():
+        bad = check(name, cfg, runs)
+        print(f"{name:45s} {'OK (' + str(runs) + ' schedules)' if bad is None else bad}")
