@@ -21,3 +21,8 @@ def test_shipped_protocols_hold(name):
 def test_broken_protocols_are_caught(name):
     bad = S.check(name, S.CONFIGS[name], runs=25)
     assert bad is not None and ("Race" in bad or "Deadlock" in bad)
+
+
+@pytest.mark.parametrize("name", list(S.FORWARD_CONFIGS))
+def test_joint_kernel_protocols_hold(name):
+    assert S.check(name, S.FORWARD_CONFIGS[name], runs=15) is None

@@ -197,6 +197,68 @@ def rowblock(sim, *, nit, ns, nq_of_item, na, nraw, groups, split_issuers, ntile
         sim.add(f"epilogue w{w}", epilogue(w))
 
 
+def forward(sim, *, nkb, seg, nop, nraw, n_tw, n_iss, n_drain):
+    """The protocol of the joint kernels (local_fwd_tc.cu: n_tw = 8 transform warps that also drain, one issuer;
+    local_fwd_tcp.cu: 12 transform warps of which 8 drain, two issuers that both take every k-block)."""
+    raw_full = [Bar(f"raw_full{s}", 1) for s in range(nraw)]
+    raw_empty = [Bar(f"raw_empty{s}", n_tw) for s in range(nraw)]
+    op_full = [Bar(f"op_full{s}", n_tw) for s in range(nop)]
+    op_empty = [Bar(f"op_empty{s}", n_iss) for s in range(nop)]
+    accum = Bar("accum", n_iss)
+    drained = Bar("drained", n_tw)
+    nseg = (nkb + seg - 1) // seg
+
+    def producer():
+        for k in range(nkb):
+            s = k % nraw
+            if k >= nraw:
+                yield ("wait", raw_empty[s], ((k // nraw) & 1) ^ 1)
+            yield ("arrive", raw_full[s])
+
+    def issuer(iid):
+        for k in range(nkb):
+            o, kin = k % nop, k % seg
+            if kin == 0 and k > 0:
+                yield ("wait", drained, (k // seg - 1) & 1)
+            yield ("wait", op_full[o], (k // nop) & 1)
+            for w in range(n_tw):
+                yield ("need", ("transformed", k, w))
+            yield ("mma", iid)
+            yield ("commit", iid, op_empty[o])
+            if kin == seg - 1 or k == nkb - 1:
+                yield ("commit", iid, accum)
+
+    def transform(w):
+        for k in range(nkb):
+            s, o = k % nraw, k % nop
+            yield ("wait", raw_full[s], (k // nraw) & 1)
+            if k >= nop:
+                yield ("wait", op_empty[o], ((k // nop) & 1) ^ 1)
+            yield ("work",)
+            yield ("done", ("transformed", k, w))
+            yield ("arrive", op_full[o])
+            yield ("arrive", raw_empty[s])
+            if (k % seg) == seg - 1 or k == nkb - 1:
+                sg = k // seg
+                yield ("wait", accum, sg & 1)
+                yield ("work",)
+                if sg + 1 < nseg:
+                    yield ("arrive", drained)
+
+    sim.add("producer", producer())
+    for i in range(n_iss):
+        sim.add(f"issuer {i}", issuer(i))
+    for w in range(n_tw):
+        sim.add(f"transform w{w}", transform(w))
+
+
+FORWARD_CONFIGS = {
+    "joint K=128 (local_fwd_tc.cu)": dict(nkb=70, seg=32, nop=2, nraw=4, n_tw=8, n_iss=1, n_drain=8),
+    "packed joint K=20, T=7 (local_fwd_tcp.cu)": dict(nkb=150, seg=64, nop=3, nraw=4, n_tw=12, n_iss=2, n_drain=8),
+    "packed joint K=20, T=3": dict(nkb=150, seg=64, nop=4, nraw=4, n_tw=12, n_iss=2, n_drain=8),
+}
+
+
 CONFIGS = {
     # the K = 10 kernel: two transform groups, four issuers, double-buffered accumulators, even ring depths 4 / 6, and
     # issuers split by the GLOBAL stage parity, so that a ring slot always belongs to the same group and issuer pair
@@ -217,11 +279,12 @@ CONFIGS = {
 }
 
 
-def check(name, cfg, runs, seed0=0):
+def check(name, cfg, runs, seed0=0, builder=None):
     bad = None
+    builder = builder or (forward if name in FORWARD_CONFIGS else rowblock)
     for r in range(runs):
         sim = Sim(seed0 + r)
-        rowblock(sim, **cfg)
+        builder(sim, **cfg)
         try:
             sim.run()
         except (Deadlock, Race) as e:
@@ -232,6 +295,6 @@ def check(name, cfg, runs, seed0=0):
 
 if __name__ == "__main__":
     runs = int(sys.argv[1]) if len(sys.argv) > 1 else 300
-    for name, cfg in CONFIGS.items():
+    for name, cfg in list(CONFIGS.items()) + list(FORWARD_CONFIGS.items()):
         bad = check(name, cfg, runs)
         print(f"{name:45s} {'OK (' + str(runs) + ' schedules)' if bad is None else bad}")
