@@ -25,14 +25,15 @@
 //              chunk; bf16: chunk 0 = al, chunk 1 = ah of the 8 channels)
 //   warps 1-2  MMA issuers (one lane each, one output row each): 9 taps x 2 tiles x 2 MMAs per slice and row
 //   warps 8-11 epilogue after the 16th slice: tcgen05.ld (lane = pixel, columns = channels), scale by g, coalesced stores
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tma.cuh"
 
 namespace iic {
 namespace bwdtc {
+using namespace tc;
 
 constexpr int KC = 128;                  // channels (UMMA N = output channels, reduction = input channels)
 constexpr int SL = 8;                    // input channels per slice (one UMMA K step of tf32)
@@ -49,57 +50,6 @@ constexpr int RAW_HALF_MAX = SL * 2 * 256 * 4;   // 16384 (8 ch x 2 rows x up to
 constexpr int SMEM_BYTES = NA * A_SLOT + NW * W_TILE + 2 * RAW_HALF_MAX + 1024;
 constexpr int NTHREADS = 384;
 
-__device__ __forceinline__ uint64_t make_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo_bytes) {
-  // K-major, no swizzle: ((8,n),2):((16 B, SBO), LBO); SBO = 128: consecutive 8-row core matrices are contiguous
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(128 >> 4) << 32;
-  d |= (uint64_t)1 << 46;                     // descriptor version (sm_100)
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__host__ __device__ __forceinline__ float tf32_hi(float v) {
-#ifdef __CUDA_ARCH__
-  return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
-#else
-  uint32_t u; memcpy(&u, &v, 4); u &= 0xFFFFE000u; memcpy(&v, &u, 4); return v;
-#endif
-}
-__device__ __forceinline__ float tf32_lo(float v) { return v - tf32_hi(v); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {     // a at the lower address
-  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-// eight fp32 values -> 16 bytes of bf16; LO selects the tf32 remainder instead of the value
-template <bool LO>
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  float t[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
-  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
-}
 
 struct Params {
   int B, H, W;

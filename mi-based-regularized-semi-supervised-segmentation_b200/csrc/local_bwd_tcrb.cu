@@ -17,14 +17,15 @@
 // warps ((128-pixel tile 0 / 1) x (even / odd source rows)): see local_bwd_tcrb10.cu.  Per item: for each 8-channel
 // slice the slice's weight image (64*T*T*24 bytes, double buffered, one bulk copy) stays resident while the
 // R + T - 1 source rows stream through the operand ring.
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tma.cuh"
 
 namespace iic {
 namespace bwdrb {
+using namespace tc;
 
 constexpr int SL = 8;                    // input channels per slice
 constexpr int APX = 272;                 // pixels per row buffer; buffer pixel b holds column b - 8
@@ -36,48 +37,6 @@ constexpr int RAW_MAX = SL * 256 * 4;    // 8192
 constexpr int NTHREADS = 448;            // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-7 transform, 8-11 epilogue
 constexpr int SMEM_LIMIT = 225 * 1024;    // dynamic shared memory we may ask for (the static barriers share the 227 KB)
 
-__device__ __forceinline__ uint64_t make_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(128 >> 4) << 32;            // SBO = 128: consecutive 8-row core matrices are contiguous
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-template <bool LO>
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  float t[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
-  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
-}
 
 #ifdef IIC_TC_TRACE
 __device__ long long g_trace[4][64][6];

@@ -10,14 +10,15 @@
 //  * the B*H image rows are dealt to the CTAs as equal contiguous shares cut into chunks of at most 16 rows (no tail
 //    wave; an item is a chunk, not a fixed block), and the whole weight image (12 KB) is loaded once per CTA.
 //   out[n,o,r,c] = g * sum_{cin,ty,tx} Wc[cin][ty*3+tx][o] * src[n,cin,r+ty-1,c+tx-1]     (iic_loss.py:123, backward)
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tma.cuh"
 
 namespace iic {
 namespace bwdrb10 {
+using namespace tc;
 
 constexpr int T = 3, PAD = 1;
 constexpr int KP = 16;                   // accumulator columns per output row (10 channels used)
@@ -38,48 +39,6 @@ constexpr int W_IMG = 4 * W_TILE;        // tx 0, 1, 2 and the leftover tile
 constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
 constexpr int SMEM_BYTES = NA * A_SLOT + 2 * W_IMG + NRAW * RAW_SLOT + 1024;   // both sweeps' weight images stay resident
 
-__device__ __forceinline__ uint64_t make_desc_kmajor_noswz(uint32_t saddr, uint32_t lbo_bytes) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(128 >> 4) << 32;            // SBO = 128: consecutive 8-row core matrices are contiguous
-  d |= (uint64_t)1 << 46;
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, 1, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void bulk_load(void* dst_smem, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-               ::"r"(smem_u32(dst_smem)), "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-template <bool LO>
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  float t[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
-  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
-}
 
 
 #ifdef IIC_TC_TRACE

@@ -17,14 +17,15 @@
 //   warps 1, 3 MMA issuers (one row tile each)
 // The slot holds D in a coalesced permuted order; reduce_packed_kernel adds the slots in fp64 in a fixed order and
 // writes J in its [dy][dx][i][j] layout.
-#include <cuda_bf16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 #include "tma.cuh"
 
 namespace iic {
 namespace fwdtcp {
+using namespace tc;
 
 constexpr int PXB = 16;                        // pixels per k-block (64-byte operand rows)
 constexpr int XRW = 28, XRU = 24;              // staged / used x columns per k-block (see local_fwd_tc.cu)
@@ -36,44 +37,6 @@ constexpr int SEG_KB_DEFAULT = 64;             // k-blocks per TMEM accumulation
                                                // see local_fwd_tc.cu; the drain is costlier here relative to the MMAs)
 constexpr int SMEM_LIMIT = 225 * 1024;
 
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
-  d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;                     // SWIZZLE_64B
-  return d;
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ float tf32_lo(float v) { return v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  const __nv_bfloat162 p = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<const uint32_t*>(&p);
-}
-template <bool LO>
-__device__ __forceinline__ uint4 pack8(const float* v) {
-  float t[8];
-#pragma unroll
-  for (int q = 0; q < 8; ++q) t[q] = LO ? tf32_lo(v[q]) : v[q];
-  return make_uint4(pack_bf16(t[0], t[1]), pack_bf16(t[2], t[3]), pack_bf16(t[4], t[5]), pack_bf16(t[6], t[7]));
-}
 
 #ifdef IIC_TC_TRACE
 __device__ long long g_trace[3][64][6];
