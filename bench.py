@@ -427,6 +427,24 @@ def run_b200(args):
             del xc, yc
     except Exception as e:  # noqa: BLE001
         extra["error"] = f"{type(e).__name__}: {e}"
+    try:
+        # supervised branch (semi_seg/epocher.py:165-166,183-184): softmax -> KL(one-hot) + Dice counts, fwd+bwd
+        gs = torch.Generator(device=dev).manual_seed(199 + rank)
+        Cs = 4
+        s1 = (torch.randn(B, Cs, H, W, device=dev, generator=gs) * 2).requires_grad_(True)
+        lab = torch.randint(0, Cs, (B, H, W), device=dev, generator=gs)
+        ms_sup = timed_graph(lambda: torch.autograd.grad(
+            iic_b200.sup_kl_from_logits(s1, lab, return_dice=True)[0], (s1,)))
+        sup_bytes = (12.0 * Cs + 16.0) * B * H * W     # fwd: C floats + one int64 label; bwd: the same + C floats out
+        extra["supervised_kl_dice_from_logits"] = {
+            "what": "supervised KL(one-hot) + per-sample Dice counts from logits, (B,4,H,W) + int64 labels, fwd+bwd; "
+                    "algorithmic bytes 12*C + 16 per pixel",
+            "ms": round(ms_sup, 4), "gb_s": round(sup_bytes / (ms_sup * 1e-3) / 1e9, 1),
+            "hbm_frac": round(sup_bytes / (ms_sup * 1e-3) / 1e9 / hbm_peak, 4),
+            "note": "working set below the L2 size: an upper bound on HBM efficiency"}
+        del s1, lab
+    except Exception as e:  # noqa: BLE001
+        extra["supervised_error"] = f"{type(e).__name__}: {e}"
 
     # ---- end to end through the public API with HOST buffers ----
     hx, hy, hgx, hgy = (t.detach().cpu().pin_memory() for t in sets[0])

@@ -26,11 +26,12 @@
 extern "C" {
 #endif
 
-#define IIC_B200_ABI_VERSION 3
+#define IIC_B200_ABI_VERSION 4
 
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
 #define IIC_FLAG_NOT_SIMPLEX 2   /* dc2:utils/assertion.py:56-65 -> AssertionError on the host */
+#define IIC_FLAG_BAD_LABEL 4     /* dc2:utils/general.py class2one_hot `assert sset(seg, range(C))` -> AssertionError */
 
 /* return code of the *_from_logits entry points for shapes their fused kernels do not cover */
 #define IIC_UNSUPPORTED 3
@@ -162,6 +163,29 @@ int iic_uda_forward(const float* prob, const float* target, long long outer, int
 int iic_uda_backward(const float* prob, const float* target, long long outer, int C, long long inner,
                      int kind, double eps, const float* weight, int from_logits,
                      const float* grad_loss, float* grad_prob, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Supervised branch of the udaiic iteration, softmax and one-hot fused:
+ *   loss = KL_div()(softmax(logits, 1), class2one_hot(labels, C))       semi_seg/epocher.py:165-166,
+ *          = mean over outer*inner of  -log((p[label] + eps) / (1 + eps)) * w[label]
+ *            (dc2:deepclustering2/loss/kl_losses.py:107-126 with a one-hot target; eps > 0)
+ *   dice_out (nullable, 2*outer*C int64, overwritten): what UniversalDice.add appends for
+ *          (logits.max(1)[1], labels) at semi_seg/epocher.py:183-184
+ *          (dc2:deepclustering2/meters2/individual_meters/general_dice_meter.py:41-95):
+ *          dice_out[0][o][c] = #pixels(argmax == c and label == c)       (_intersaction)
+ *          dice_out[1][o][c] = #pixels(argmax == c) + #pixels(label == c) (_union)
+ * logits (outer, C, inner) contiguous float32, C <= 8; labels (outer, inner) contiguous int64 class
+ * indices; weight (nullable) C floats, already normalised as at kl_losses.py:100.  A label outside
+ * [0, C) sets IIC_FLAG_BAD_LABEL and contributes nothing.  workspace >= iic_sup_workspace_bytes,
+ * zero-initialised once by the caller.  The backward writes d loss / d logits (dense, same layout).
+ * ---------------------------------------------------------------------------------------------- */
+size_t iic_sup_workspace_bytes(int device, long long outer);
+int iic_sup_forward(const float* logits, const long long* labels, long long outer, int C, long long inner,
+                    double eps, const float* weight, float* loss_out, long long* dice_out, int* flags,
+                    void* workspace, void* stream);
+int iic_sup_backward(const float* logits, const long long* labels, long long outer, int C, long long inner,
+                     double eps, const float* weight, const float* grad_loss, float* grad_logits,
+                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Joint exchange over NVLink peer memory (multi-GPU, one process per GPU).  The path's only collective

@@ -10,9 +10,10 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libiic_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 FLAG_NAN_LOSS = 1
 FLAG_NOT_SIMPLEX = 2
+FLAG_BAD_LABEL = 4
 UNSUPPORTED = 3
 
 _p = C.c_void_p
@@ -47,6 +48,9 @@ PROTOTYPES = {
     "iic_uda_workspace_bytes": (_sz, [_i]),
     "iic_uda_forward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _i, _p, _p]),
     "iic_uda_backward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _p]),
+    "iic_sup_workspace_bytes": (_sz, [_i, _ll]),
+    "iic_sup_forward": (_i, [_p, _p, _ll, _i, _ll, _d, _p, _p, _p, _p, _p, _p]),
+    "iic_sup_backward": (_i, [_p, _p, _ll, _i, _ll, _d, _p, _p, _p, _p]),
     "iic_xchg_buffer_bytes": (_sz, [_i, _ll]),
     "iic_xchg_create": (_i, [_i, _ll, _p]),
     "iic_xchg_export": (_i, [_p, _p]),

@@ -68,6 +68,8 @@ def raise_if_flagged(device, loss=None, simplex_msg: str = "input is not a simpl
     v = read_and_clear(device)
     if v & _lib.FLAG_NOT_SIMPLEX:
         raise AssertionError(simplex_msg)
+    if v & _lib.FLAG_BAD_LABEL:     # class2one_hot's `assert sset(seg, list(range(C)))`
+        raise AssertionError("a label lies outside [0, C)")
     if v & _lib.FLAG_NAN_LOSS:
         raise RuntimeError(loss if loss is not None else "IIC loss is NaN")
 

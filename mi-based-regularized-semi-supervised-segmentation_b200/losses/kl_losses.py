@@ -4,6 +4,11 @@
 ``torch.nn.MSELoss()`` the reference builds at semi_seg/trainer.py:137,194.  Both are called as
 ``criterion(softmax(tf_logits), softmax(logits_tf).detach())`` at semi_seg/epocher.py:221-224.
 ``uda_from_logits`` fuses those two softmaxes into the loss kernels.
+
+``sup_kl_from_logits`` is the supervised branch of the same iteration:
+``KL_div()(label_logits.softmax(1), class2one_hot(labeled_target.squeeze(1), C))`` at
+semi_seg/epocher.py:165-166, with the softmax and the one-hot fused into one pass that can also count
+what the ``sup_dice`` meter needs (epocher.py:183-184).
 """
 from __future__ import annotations
 
@@ -13,7 +18,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import checks
-from ..ops import UDAFunction
+from ..ops import SupervisedKLFunction, UDAFunction
 
 _KIND = {"mse": 0, "kl": 1}
 
@@ -82,3 +87,38 @@ def uda_from_logits(student_logits: Tensor, teacher_logits: Tensor, kind: str = 
     (semi_seg/epocher.py:221-224); the gradient is returned w.r.t. ``student_logits``."""
     assert student_logits.shape == teacher_logits.shape
     return UDAFunction.apply(student_logits, teacher_logits.detach(), _KIND[kind], float(eps), None, True, False)
+
+
+def _normalised_weight(weight) -> Optional[Tensor]:
+    if weight is None:
+        return None
+    w = torch.as_tensor(weight).float()
+    return w / w.sum() * len(w)                                                   # kl_losses.py:100
+
+
+def sup_kl_from_logits(logits: Tensor, target: Tensor, weight: Union[List[float], Tensor] = None,
+                       eps: float = 1e-16, return_dice: bool = False):
+    """``KL_div(weight=weight, eps=eps)(logits.softmax(1), class2one_hot(target, C))`` without the
+    probability map or the one-hot tensor (semi_seg/epocher.py:165-166; dc2:loss/kl_losses.py:107-126).
+
+    ``target`` holds int64 class indices, shaped (B, *spatial) or (B, 1, *spatial) as the loaders emit it.
+    With ``return_dice`` the call also returns ``(intersection, union)``, the two (B, C) int64 tensors
+    ``UniversalDice.add(logits.max(1)[1], target)`` would append (dc2:general_dice_meter.py:41-95), counted in
+    the same pass.  A label outside [0, C) raises AssertionError like ``class2one_hot`` (per the check mode).
+    """
+    if target.dim() == logits.dim() and target.shape[1] == 1:
+        target = target.squeeze(1)
+    assert not target.requires_grad
+    if not eps > 0:
+        raise ValueError("sup_kl_from_logits needs eps > 0 (the reference's loss is NaN at eps = 0)")
+    loss, dice = SupervisedKLFunction.apply(logits, target, float(eps), _normalised_weight(weight), bool(return_dice))
+    checks.finish(logits.device, loss, "prob / target is not a simplex over dim 1")
+    if return_dice:
+        return loss, (dice[0], dice[1])
+    return loss
+
+
+def dice_from_counts(intersection: Tensor, union: Tensor) -> Tensor:
+    """Per-class Dice of one group, as UniversalDice.log computes it from the summed counts
+    (dc2:general_dice_meter.py:96-108): (2 * sum_b I + 1e-6) / (sum_b U + 1e-6)."""
+    return (2 * intersection.sum(0) + 1e-6) / (union.sum(0) + 1e-6)

@@ -32,6 +32,8 @@ _LIBDEF.define("uda_forward(Tensor prob, Tensor target, int kind, float eps, Ten
 _LIBDEF.define("uda_backward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
                "Tensor grad) -> Tensor")
 _LIBDEF.define("simplex_check(Tensor t, int axis) -> ()")
+_LIBDEF.define("sup_forward(Tensor logits, Tensor labels, float eps, Tensor? weight, bool want_dice) -> (Tensor, Tensor)")
+_LIBDEF.define("sup_backward(Tensor logits, Tensor labels, float eps, Tensor? weight, Tensor grad) -> Tensor")
 
 
 # ---- per (device, stream) persistent state ---------------------------------------------------------
@@ -43,6 +45,13 @@ class _StreamState:
         self.flags = torch.zeros(1, dtype=torch.int32, device=device)
         self.uda_ws = torch.zeros(lib.iic_uda_workspace_bytes(device.index or 0), dtype=torch.uint8, device=device)
         self.epi_ws = {}
+        self.sup_ws = None
+
+    def supervised_ws(self, outer: int, device) -> torch.Tensor:
+        nbytes = _lib.load().iic_sup_workspace_bytes(device.index or 0, outer)
+        if self.sup_ws is None or self.sup_ws.numel() < nbytes:
+            self.sup_ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        return self.sup_ws
 
     def epilogue_ws(self, K: int, pad: int, n_patches: int, device) -> torch.Tensor:
         key = (pad, n_patches)
@@ -337,7 +346,52 @@ def _simplex_check(t, axis):
     _lib.check(rc, "iic_simplex_check")
 
 
+def _sup_args(logits, labels, weight):
+    _require_cuda_f32("logits", logits)
+    if labels.dtype != torch.int64 or labels.device != logits.device:
+        raise TypeError(f"iic_b200.sup: labels must be an int64 tensor on {logits.device}, got {labels.dtype} on "
+                        f"{labels.device}")
+    if logits.dim() < 2 or labels.shape != logits.shape[:1] + logits.shape[2:]:
+        raise ValueError(f"iic_b200.sup: logits {tuple(logits.shape)} need labels of shape "
+                         f"{tuple(logits.shape[:1] + logits.shape[2:])}, got {tuple(labels.shape)}")
+    if weight is not None:
+        if weight.numel() != logits.shape[1]:
+            raise ValueError(f"iic_b200.sup: {weight.numel()} class weights for {logits.shape[1]} classes")
+        weight = weight.to(device=logits.device, dtype=torch.float32).contiguous()
+    return logits.contiguous(), labels.contiguous(), weight
+
+
+def _sup_forward(logits, labels, eps, weight, want_dice):
+    lib = _lib.load()
+    logits, labels, weight = _sup_args(logits, labels, weight)
+    outer, C, inner = _as_oci(logits)
+    st = _state(logits.device)
+    loss = torch.empty((), dtype=torch.float32, device=logits.device)
+    dice = torch.empty((2, outer, C) if want_dice else (0,), dtype=torch.int64, device=logits.device)
+    with torch.cuda.device(logits.device):
+        rc = lib.iic_sup_forward(logits.data_ptr(), labels.data_ptr(), outer, C, inner, float(eps), _ptr(weight),
+                                 loss.data_ptr(), dice.data_ptr() if want_dice else None, st.flags.data_ptr(),
+                                 st.supervised_ws(outer, logits.device).data_ptr(), _stream(logits.device))
+    _lib.check(rc, "iic_sup_forward")
+    return loss, dice
+
+
+def _sup_backward(logits, labels, eps, weight, grad):
+    lib = _lib.load()
+    logits, labels, weight = _sup_args(logits, labels, weight)
+    outer, C, inner = _as_oci(logits)
+    out = torch.empty_like(logits)
+    grad = grad.to(torch.float32).reshape(())
+    with torch.cuda.device(logits.device):
+        rc = lib.iic_sup_backward(logits.data_ptr(), labels.data_ptr(), outer, C, inner, float(eps), _ptr(weight),
+                                  grad.data_ptr(), out.data_ptr(), _stream(logits.device))
+    _lib.check(rc, "iic_sup_backward")
+    return out
+
+
 _LIBIMPL = torch.library.Library("iic_b200", "IMPL", "CUDA")
+_LIBIMPL.impl("sup_forward", _sup_forward)
+_LIBIMPL.impl("sup_backward", _sup_backward)
 _LIBIMPL.impl("local_joint", _local_joint)
 _LIBIMPL.impl("local_epilogue", _local_epilogue)
 _LIBIMPL.impl("local_backward", _local_backward)
@@ -361,7 +415,7 @@ def _cpu_refusal(name):
 
 _LIBCPU = torch.library.Library("iic_b200", "IMPL", "CPU")
 for _n in ("local_joint", "local_epilogue", "local_backward", "local_joint_logits", "local_backward_logits", "global_joint", "global_epilogue",
-           "global_backward", "uda_forward", "uda_backward", "simplex_check"):
+           "global_backward", "uda_forward", "uda_backward", "simplex_check", "sup_forward", "sup_backward"):
     _LIBCPU.impl(_n, _cpu_refusal(_n))
 
 ops = torch.ops.iic_b200
@@ -559,3 +613,22 @@ class UDAFunction(torch.autograd.Function):
         kind, eps, from_logits = ctx.cfg
         g = ops.uda_backward(prob, target, kind, eps, weight, from_logits, grad.contiguous())
         return g, None, None, None, None, None, None
+
+
+class SupervisedKLFunction(torch.autograd.Function):
+    """KL_div()(softmax(logits), one_hot(labels)) (semi_seg/epocher.py:165-166) and the Dice counts of the
+    `sup_dice` meter (epocher.py:183-184) from one pass over the logits; the gradient flows to `logits` only."""
+
+    @staticmethod
+    def forward(ctx, logits, labels, eps, weight, want_dice):
+        loss, dice = ops.sup_forward(logits, labels, eps, weight, want_dice)
+        ctx.save_for_backward(logits, labels, weight)
+        ctx.eps = eps
+        ctx.mark_non_differentiable(dice)
+        return loss, dice
+
+    @staticmethod
+    def backward(ctx, grad, _grad_dice):
+        logits, labels, weight = ctx.saved_tensors
+        g = ops.sup_backward(logits, labels, ctx.eps, weight, grad.contiguous())
+        return g, None, None, None, None

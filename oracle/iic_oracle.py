@@ -305,3 +305,41 @@ def kl_div(prob, target, eps: float = EPS_KL, reduction: str = "mean", weight=No
     if with_grads:
         return out, g
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# supervised branch
+# --------------------------------------------------------------------------------------------
+def class2one_hot(seg, C: int):
+    """dc2:deepclustering2/utils/assertion.py:101-116 -- integer one-hot over a new axis 1; labels
+    outside range(C) fail the reference's ``assert sset(seg, list(range(C)))``."""
+    seg = np.asarray(seg)
+    if seg.ndim == 2:
+        seg = seg[None]
+    assert set(np.unique(seg).tolist()) <= set(range(C)), "a label lies outside [0, C)"
+    return np.stack([seg == c for c in range(C)], axis=1).astype(np.int64)
+
+
+def sup_kl_from_logits(logits, labels, eps: float = EPS_KL, weight=None, with_grads: bool = False):
+    """semi_seg/epocher.py:165-166: ``KL_div()(label_logits.softmax(1), class2one_hot(target, C))``.
+
+    Composition of :func:`softmax`, :func:`class2one_hot` and :func:`kl_div`; the gradient is taken back
+    through the softmax to the logits."""
+    p = softmax(logits, axis=1)
+    t = class2one_hot(labels, p.shape[1])
+    if not with_grads:
+        return kl_div(p, t, eps=eps, weight=weight)
+    loss, gp = kl_div(p, t, eps=eps, weight=weight, with_grads=True)
+    return loss, softmax_backward(p, gp, axis=1)
+
+
+def dice_counts(logits, labels):
+    """What ``UniversalDice.add(logits.max(1)[1], labels)`` appends (semi_seg/epocher.py:183-184;
+    dc2:meters2/individual_meters/general_dice_meter.py:41-95,142-172): per sample and class,
+    intersection = sum(pred * target) and union = sum(pred + target) of the two one-hot maps."""
+    z = np.asarray(logits)
+    C = z.shape[1]
+    pred = class2one_hot(z.argmax(axis=1), C)       # first maximal index, like torch.max
+    tgt = class2one_hot(labels, C)
+    axes = tuple(range(2, z.ndim))
+    return (pred * tgt).sum(axis=axes), (pred + tgt).sum(axis=axes)

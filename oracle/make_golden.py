@@ -112,11 +112,65 @@ def run_uda(ns, p32, t32, kind, weight=None):
     return out
 
 
+def run_sup(ns, logits32, labels, weight=None):
+    """The reference's supervised branch, verbatim (semi_seg/epocher.py:165-166,183-184): a `long` one-hot from
+    class2one_hot, KL_div on the softmax, UniversalDice.add on the argmax."""
+    torch = ns.torch
+    C = logits32.shape[1]
+    out = {}
+    for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+        lg = logits32.to(dt).clone().requires_grad_(True)
+        crit = ns.KL_div(weight=weight, verbose=False)
+        if weight is not None:
+            crit._weight = crit._weight.to(dt)
+        onehot_target = ns.class2one_hot(labels.squeeze(1), C)
+        loss = crit(lg.softmax(1), onehot_target)
+        (g,) = torch.autograd.grad(loss, (lg,))
+        out[f"loss_{tag}"] = loss.item()
+        if tag == "f64":
+            out["g_f64"] = g.numpy()
+        else:
+            out["gerr_f32"] = _relmax(g.numpy(), out["g_f64"])
+    meter = ref_loader.load_dice()(C=C)
+    meter.add(logits32.max(1)[1], labels.squeeze(1), group_name=["g"] * len(labels))
+    out["intersection"] = meter._intersections[0].numpy()
+    out["union"] = meter._unions[0].numpy()
+    out["dice"] = meter.log.numpy()[0]
+    return out
+
+
+def make_sup(ns):
+    """Supervised-branch fixtures; their own generator so the older fixtures stay byte-identical."""
+    torch = ns.torch
+    rng = np.random.default_rng(20260119)
+    for name, shape, weight in (("s_2x4x6x5", (2, 4, 6, 5), None),            # ragged rows: scalar kernels
+                                ("s_3x4x16x16", (3, 4, 16, 16), None),        # 16-byte rows: vector kernels
+                                ("s_w_2x4x12x12", (2, 4, 12, 12), [1.0, 2.0, 0.5, 1.5]),   # square: kl_losses.py:118 transposes H and W
+                                ("s_2x2x7x9", (2, 2, 7, 9), None),
+                                ("s_1x8x8x8", (1, 8, 8, 8), None)):
+        B, C = shape[:2]
+        labels = torch.from_numpy(rng.integers(0, C, size=(B, 1) + shape[2:]).astype(np.int64))
+        # logits that agree with the labels on roughly half of the pixels, so the Dice counts are not trivial
+        lg = rng.standard_normal(shape) * 2
+        agree = rng.random((B,) + shape[2:]) < 0.5
+        onehot = np.stack([labels.squeeze(1).numpy() == c for c in range(C)], axis=1)
+        lg = lg + 4.0 * onehot * agree[:, None]
+        lg = torch.from_numpy(lg.astype(np.float32))
+        res = run_sup(ns, lg, labels, weight)
+        extra = {} if weight is None else {"weight": np.asarray(weight, dtype=np.float64)}
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), kind="sup", logits=lg.numpy(), labels=labels.numpy(),
+                            **extra, **res)
+        print(name, res["loss_f64"], res["loss_f32"], res["dice"])
+
+
 def main():
     ns = ref_loader.load()
     torch = ns.torch
     torch.set_num_threads(4)
     os.makedirs(OUT, exist_ok=True)
+    if "--sup-only" in sys.argv:
+        make_sup(ns)
+        return
     rng = np.random.default_rng(20260118)
 
     # ---- global IIDLoss ---------------------------------------------------------------
@@ -211,6 +265,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "simplex_cases.npz"), cases=np.stack(cases),
                         verdicts=np.asarray(verdicts))
     print("simplex verdicts", verdicts)
+
+    make_sup(ns)
 
 
 if __name__ == "__main__":

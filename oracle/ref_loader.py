@@ -125,9 +125,45 @@ def load():
         IIDLoss=iic.IIDLoss, compute_joint=iic.compute_joint,
         IIDSegmentationLoss=iic.IIDSegmentationLoss, patch_generator=iic.patch_generator,
         IIDSegmentationSmallPathLoss=iic.IIDSegmentationSmallPathLoss,
-        KL_div=kl.KL_div, simplex=assertion.simplex,
+        KL_div=kl.KL_div, simplex=assertion.simplex, class2one_hot=assertion.class2one_hot,
+        _assertion=assertion,
         average_iter=helper_utils.average_iter, weighted_average_iter=helper_utils.weighted_average_iter,
         torch=torch,
     )
     _cache["ns"] = ns
     return ns
+
+
+def load_dice():
+    """The reference's unmodified ``UniversalDice`` meter (dc2:meters2/individual_meters/general_dice_meter.py),
+    loaded by path.  Its imports are satisfied by the wheel's own assertion helpers plus three trivial stubs for
+    things the counting code never touches (the ``_Metric`` base class, ``to_float``, ``iter_average``)."""
+    if "dice" in _cache:
+        return _cache["dice"]
+    ns = load()
+    a = ns._assertion
+    names = ("deepclustering2", "deepclustering2.utils", "deepclustering2.type", "deepclustering2.meters2",
+             "deepclustering2.meters2.individual_meters", "deepclustering2.meters2.individual_meters._metric")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        mods = {k: types.ModuleType(k) for k in names}
+        for m in mods.values():
+            m.__path__ = []
+        u = mods["deepclustering2.utils"]
+        u.simplex, u.one_hot, u.class2one_hot, u.probs2one_hot = a.simplex, a.one_hot, a.class2one_hot, a.probs2one_hot
+        u.iter_average = lambda xs: sum(xs) / len(list(xs))
+        mods["deepclustering2.type"].to_float = float
+        metric = mods["deepclustering2.meters2.individual_meters._metric"]
+        metric._Metric = type("_Metric", (), {"__init__": lambda self: None})
+        metric.MeterResultDict = dict
+        sys.modules.update(mods)
+        dice = _load_by_path("_ref_dc2_general_dice_meter",
+                             _extract_wheel_member("deepclustering2/meters2/individual_meters/general_dice_meter.py"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache["dice"] = dice.UniversalDice
+    return dice.UniversalDice

@@ -25,6 +25,8 @@ def golden_names(kind):
             out.append(n)
         elif kind == "uda" and n.startswith("u_"):
             out.append(n)
+        elif kind == "sup" and n.startswith("s_"):
+            out.append(n)
     return out
 
 

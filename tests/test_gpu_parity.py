@@ -314,6 +314,75 @@ def test_uda_vs_oracle(iic, cuda_device, kind, shape):
 
 
 # ---------------------------------------------------------------------------------------------------
+# supervised branch: fused softmax -> KL(one-hot) and the Dice counts
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("sup"))
+def test_supervised_golden(iic, cuda_device, name):
+    g = load_golden(name)
+    lg = torch.from_numpy(g["logits"]).to(cuda_device).requires_grad_(True)
+    tgt = torch.from_numpy(g["labels"]).to(cuda_device)                  # (B, 1, H, W) as the loader emits it
+    w = g["weight"].tolist() if "weight" in g else None
+    loss, (inter, union) = iic.sup_kl_from_logits(lg, tgt, weight=w, return_dice=True)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_f64"])) <= LOSS_RTOL * abs(float(g["loss_f64"]))
+    assert relmax(lg.grad.cpu().numpy(), g["g_f64"]) <= GRAD_RTOL
+    assert inter.dtype == torch.int64 and tuple(inter.shape) == g["intersection"].shape
+    assert np.array_equal(inter.cpu().numpy(), g["intersection"])       # integer counts: bit-exact
+    assert np.array_equal(union.cpu().numpy(), g["union"])
+    assert relmax(iic.dice_from_counts(inter, union).cpu().numpy(), g["dice"]) < 1e-6
+
+
+@pytest.mark.parametrize("shape", [(4, 4, 224, 224), (3, 4, 37, 53), (5, 7), (2, 8, 9, 12), (300, 2, 4, 4)])
+def test_supervised_vs_oracle(iic, cuda_device, shape):
+    rng = np.random.default_rng(100 + len(shape) + shape[1])
+    C = shape[1]
+    lg = (rng.standard_normal(shape) * 2).astype(np.float32)
+    lab = rng.integers(0, C, size=shape[:1] + shape[2:]).astype(np.int64)
+    w = None if C != 4 else [0.5, 1.0, 2.0, 1.5]
+    ld = torch.from_numpy(lg).to(cuda_device).requires_grad_(True)
+    loss, (inter, union) = iic.sup_kl_from_logits(ld, torch.from_numpy(lab).to(cuda_device), weight=w,
+                                                  return_dice=True)
+    (3.0 * loss).backward()
+    ol, og = O.sup_kl_from_logits(lg, lab, weight=w, with_grads=True)
+    assert abs(loss.item() - ol) <= LOSS_RTOL * abs(ol)
+    assert relmax(ld.grad.cpu().numpy(), 3.0 * og) <= GRAD_RTOL
+    oi, ou = O.dice_counts(lg, lab)
+    assert np.array_equal(inter.cpu().numpy(), oi) and np.array_equal(union.cpu().numpy(), ou)
+    # the loss-only call (no Dice buffer) gives the same bits, twice (deterministic reduction)
+    l2 = iic.sup_kl_from_logits(ld.detach().requires_grad_(True), torch.from_numpy(lab).to(cuda_device), weight=w)
+    l3 = iic.sup_kl_from_logits(ld.detach().requires_grad_(True), torch.from_numpy(lab).to(cuda_device), weight=w)
+    assert l2.item() == loss.item() == l3.item()
+
+
+def test_supervised_matches_probability_path_and_flags_bad_labels(iic, cuda_device):
+    """The fused call equals the drop-in KL_div on (softmax, float one-hot); a label outside [0, C) raises the
+    AssertionError of class2one_hot and leaves no gradient on that pixel."""
+    rng = np.random.default_rng(5)
+    lg = torch.from_numpy((rng.standard_normal((2, 4, 16, 20)) * 2).astype(np.float32)).to(cuda_device)
+    lab = torch.from_numpy(rng.integers(0, 4, size=(2, 16, 20))).to(cuda_device)
+    a = lg.clone().requires_grad_(True)
+    fused = iic.sup_kl_from_logits(a, lab)
+    fused.backward()
+    b = lg.clone().requires_grad_(True)
+    onehot = torch.nn.functional.one_hot(lab, 4).permute(0, 3, 1, 2).float().contiguous()
+    plain = iic.KL_div(verbose=False)(b.softmax(1), onehot)
+    plain.backward()
+    assert abs(fused.item() - plain.item()) <= 2e-6 * abs(plain.item())
+    assert relmax(a.grad.cpu().numpy(), b.grad.cpu().numpy()) <= 1e-5
+    bad = lab.clone()
+    bad[1, 3, 5] = 4
+    with pytest.raises(AssertionError):
+        iic.sup_kl_from_logits(lg.clone().requires_grad_(True), bad)
+    with iic.check_mode("deferred"):
+        c = lg.clone().requires_grad_(True)
+        iic.sup_kl_from_logits(c, bad).backward()
+        assert float(c.grad[1, :, 3, 5].abs().max()) == 0.0
+        with pytest.raises(AssertionError):
+            iic.raise_if_flagged(cuda_device)
+    iic.raise_if_flagged(cuda_device)                 # clean again
+
+
+# ---------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE config-2 size (32 x 10 x 224 x 224, padding 1)
 # ---------------------------------------------------------------------------------------------------
 def test_full_size_properties(iic, cuda_device):

@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"libiic_b200.so does not export {name}"
     assert declared == set(built._lib.PROTOTYPES), declared ^ set(built._lib.PROTOTYPES)
-    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 3
+    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 4
 
 
 def test_patch_count_matches_reference_windows(built):
@@ -89,6 +89,9 @@ def test_no_cpu_fallback(built):
     assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
     with pytest.raises(Exception):
         built.MSELoss()(x, x.detach())
+    with pytest.raises(Exception) as ei:
+        built.sup_kl_from_logits(torch.randn(2, 4, 8, 8, requires_grad=True), torch.zeros(2, 8, 8, dtype=torch.int64))
+    assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
 
 
 def test_product_never_imports_oracle():

@@ -63,6 +63,25 @@ def test_uda_oracle_matches_reference(name):
     assert relmax(grad, g["g_f64"]) < 1e-12
 
 
+@pytest.mark.parametrize("name", golden_names("sup"))
+def test_supervised_oracle_matches_reference(name):
+    """semi_seg/epocher.py:165-166,183-184 as run by oracle/make_golden.py::run_sup."""
+    g = load_golden(name)
+    labels = g["labels"][:, 0]
+    loss, grad = O.sup_kl_from_logits(g["logits"], labels, weight=g.get("weight"), with_grads=True)
+    assert abs(loss - g["loss_f64"]) <= 1e-12 * max(1.0, abs(g["loss_f64"]))
+    assert relmax(grad, g["g_f64"]) < 1e-11
+    inter, union = O.dice_counts(g["logits"], labels)
+    assert np.array_equal(inter, g["intersection"]) and np.array_equal(union, g["union"])
+    dice = (2 * inter.sum(0) + 1e-6) / (union.sum(0) + 1e-6)
+    assert relmax(dice, g["dice"]) < 1e-6          # the meter divides in float32
+
+
+def test_supervised_oracle_rejects_bad_labels():
+    with pytest.raises(AssertionError):
+        O.class2one_hot(np.array([[[0, 4]]]), 4)
+
+
 def test_patch_windows_match_reference():
     g = load_golden("patch_windows")
     for key, wins in g.items():
@@ -143,3 +162,21 @@ def test_live_reference_agrees_with_oracle_on_fresh_inputs():
                                                     with_grads=True)
     assert abs(loss.item() - l2) < 1e-11
     assert relmax(ox, gx.numpy()) < 1e-8 and relmax(oy, gy.numpy()) < 1e-8
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_supervised_branch():
+    ns = ref_loader.load()
+    torch = ns.torch
+    rng = np.random.default_rng(11)
+    lg = torch.from_numpy(rng.standard_normal((2, 4, 10, 10)) * 2).requires_grad_(True)
+    tgt = torch.from_numpy(rng.integers(0, 4, size=(2, 1, 10, 10)))
+    loss = ns.KL_div(verbose=False)(lg.softmax(1), ns.class2one_hot(tgt.squeeze(1), 4))
+    (g,) = torch.autograd.grad(loss, (lg,))
+    ol, og = O.sup_kl_from_logits(lg.detach().numpy(), tgt.numpy()[:, 0], with_grads=True)
+    assert abs(loss.item() - ol) < 1e-12 and relmax(og, g.numpy()) < 1e-11
+    meter = ref_loader.load_dice()(C=4)
+    meter.add(lg.detach().max(1)[1], tgt.squeeze(1))
+    inter, union = O.dice_counts(lg.detach().numpy(), tgt.numpy()[:, 0])
+    assert np.array_equal(meter._intersections[0].numpy(), inter)
+    assert np.array_equal(meter._unions[0].numpy(), union)
