@@ -8,7 +8,8 @@
 // With a one-hot target only the labelled class contributes: -1 * log((p_l + eps) / (1 + eps)) * w_l, the other
 // classes give -0 * log(finite) = 0 (eps > 0).  The softmax, the one-hot and the argmax live in registers; the
 // (B,C,H,W) int64 one-hot (8*C bytes per pixel) and the probability map are never materialised.
-// A thread owns V consecutive pixels of one sample (V = 4 with 16-byte loads when the rows allow it).
+// A thread owns V consecutive pixels of one sample (V = 4 with 16-byte loads when the rows allow it) and keeps NC
+// channels in registers: NC = C for the usual 2..4 classes (no padded work), NC = 8 with run-time guards otherwise.
 #include "common.cuh"
 
 namespace iic {
@@ -21,11 +22,11 @@ struct SupWorkspace {
   // followed by double partial[gridDim.x * gridDim.y]
 };
 
-template <int V>
+template <int V, int NC>
 __device__ __forceinline__ void sup_load(const float* __restrict__ src, long long inner, int C,
-                                         float (&v)[SUP_CMAX][V]) {
+                                         float (&v)[NC][V]) {
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) {
+  for (int c = 0; c < NC; ++c) {
     if (c < C) {
       if (V == 4) {
         const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)c * inner));
@@ -52,27 +53,27 @@ __device__ __forceinline__ void sup_load_labels(const long long* __restrict__ sr
 }
 
 // softmax over the channels of pixel e, in place; returns the index of the first maximal logit
-template <int V>
-__device__ __forceinline__ int sup_softmax(float (&v)[SUP_CMAX][V], int e) {
+template <int V, int NC>
+__device__ __forceinline__ int sup_softmax(float (&v)[NC][V], int e) {
   float mx = v[0][e];
   int arg = 0;
 #pragma unroll
-  for (int c = 1; c < SUP_CMAX; ++c) {
+  for (int c = 1; c < NC; ++c) {
     if (v[c][e] > mx) { mx = v[c][e]; arg = c; }
   }
   float s = 0.f;
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) { v[c][e] = __expf(v[c][e] - mx); s += v[c][e]; }   // exp(-inf) = 0 pads
+  for (int c = 0; c < NC; ++c) { v[c][e] = __expf(v[c][e] - mx); s += v[c][e]; }   // exp(-inf) = 0 pads
   const float inv = 1.f / s;
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) v[c][e] *= inv;
+  for (int c = 0; c < NC; ++c) v[c][e] *= inv;
   return arg;
 }
 
 // grid (gx, outer): blockIdx.y = sample, so the Dice counters of a CTA belong to one sample
-template <int V>
-__global__ void __launch_bounds__(256) sup_fwd_kernel(const float* __restrict__ logits,
-                                                      const long long* __restrict__ labels, int C,
+template <int V, int NC>
+__global__ void __launch_bounds__(256, NC <= 4 ? 3 : 2) sup_fwd_kernel(const float* __restrict__ logits,
+                                                      const long long* __restrict__ labels, int C_rt,
                                                       long long inner, float eps, const float* __restrict__ weight,
                                                       double denom, float* __restrict__ loss_out,
                                                       long long* __restrict__ dice_out, int* __restrict__ flags,
@@ -81,35 +82,36 @@ __global__ void __launch_bounds__(256) sup_fwd_kernel(const float* __restrict__ 
   __shared__ unsigned int s_cnt[2][SUP_CMAX];
   __shared__ bool is_last;
   double* partial = reinterpret_cast<double*>(ws + 1);
+  const int C = NC < SUP_CMAX ? NC : C_rt;      // the host picks NC == C for C <= 4
   const long long o = blockIdx.y, outer = gridDim.y;
   const float* lg = logits + o * C * inner;
   const long long* lb = labels + o * inner;
   if (threadIdx.x < 2 * SUP_CMAX) (&s_cnt[0][0])[threadIdx.x] = 0u;
   __syncthreads();
-  float w[SUP_CMAX];
+  float w[NC];
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) w[c] = (weight && c < C) ? __ldg(weight + c) : 1.f;
-  unsigned int ci[SUP_CMAX], cu[SUP_CMAX];
+  for (int c = 0; c < NC; ++c) w[c] = (weight && c < C) ? __ldg(weight + c) : 1.f;
+  unsigned int ci[NC], cu[NC];
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) { ci[c] = 0u; cu[c] = 0u; }
+  for (int c = 0; c < NC; ++c) { ci[c] = 0u; cu[c] = 0u; }
   float local = 0.f;
   bool bad = false;
   const long long ngroups = inner / V;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ngroups;
        q += (long long)gridDim.x * blockDim.x) {
-    float p[SUP_CMAX][V];
+    float p[NC][V];
     long long l[V];
-    sup_load<V>(lg + q * V, inner, C, p);
+    sup_load<V, NC>(lg + q * V, inner, C, p);
     sup_load_labels<V>(lb + q * V, l);
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      const int arg = sup_softmax<V>(p, e);
+      const int arg = sup_softmax<V, NC>(p, e);
       const bool ok = (l[e] >= 0 && l[e] < C);
       bad |= !ok;
       const int li = ok ? (int)l[e] : -1;
       float pl = 1.f, wl = 0.f;
 #pragma unroll
-      for (int c = 0; c < SUP_CMAX; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (c == li) { pl = p[c][e]; wl = w[c]; }
         ci[c] += (unsigned)((c == arg) & (c == li));
         cu[c] += (unsigned)(c == arg) + (unsigned)(c == li);
@@ -121,7 +123,7 @@ __global__ void __launch_bounds__(256) sup_fwd_kernel(const float* __restrict__ 
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(flags, IIC_FLAG_BAD_LABEL);
   if (dice_out != nullptr) {
 #pragma unroll
-    for (int c = 0; c < SUP_CMAX; ++c) {
+    for (int c = 0; c < NC; ++c) {
       if (c < C) {
         const unsigned a = __reduce_add_sync(0xffffffffu, ci[c]);
         const unsigned b = __reduce_add_sync(0xffffffffu, cu[c]);
@@ -168,43 +170,44 @@ __global__ void __launch_bounds__(256) sup_fwd_kernel(const float* __restrict__ 
 
 // d loss / d logits: gp_l = -w_l / (p_l + eps) * g / (outer*inner) on the labelled class only, then the softmax
 // adjoint p_c * (gp_c - sum_k gp_k p_k).  A pixel with an out-of-range label gets a zero gradient.
-template <int V>
-__global__ void __launch_bounds__(256) sup_bwd_kernel(const float* __restrict__ logits,
-                                                      const long long* __restrict__ labels, int C,
+template <int V, int NC>
+__global__ void __launch_bounds__(256, NC <= 4 ? 3 : 2) sup_bwd_kernel(const float* __restrict__ logits,
+                                                      const long long* __restrict__ labels, int C_rt,
                                                       long long inner, float eps, const float* __restrict__ weight,
                                                       float inv_denom, const float* __restrict__ grad_loss,
                                                       float* __restrict__ grad_logits) {
+  const int C = NC < SUP_CMAX ? NC : C_rt;
   const long long o = blockIdx.y;
   const float* lg = logits + o * C * inner;
   const long long* lb = labels + o * inner;
   float* gl = grad_logits + o * C * inner;
   const float g = (grad_loss ? __ldg(grad_loss) : 1.f) * inv_denom;
-  float w[SUP_CMAX];
+  float w[NC];
 #pragma unroll
-  for (int c = 0; c < SUP_CMAX; ++c) w[c] = (weight && c < C) ? __ldg(weight + c) : 1.f;
+  for (int c = 0; c < NC; ++c) w[c] = (weight && c < C) ? __ldg(weight + c) : 1.f;
   const long long ngroups = inner / V;
   for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < ngroups;
        q += (long long)gridDim.x * blockDim.x) {
-    float p[SUP_CMAX][V];
+    float p[NC][V];
     long long l[V];
-    sup_load<V>(lg + q * V, inner, C, p);
+    sup_load<V, NC>(lg + q * V, inner, C, p);
     sup_load_labels<V>(lb + q * V, l);
 #pragma unroll
     for (int e = 0; e < V; ++e) {
-      sup_softmax<V>(p, e);
+      sup_softmax<V, NC>(p, e);
       const int li = (l[e] >= 0 && l[e] < C) ? (int)l[e] : -1;
       float pl = 1.f, wl = 0.f;
 #pragma unroll
-      for (int c = 0; c < SUP_CMAX; ++c) {
+      for (int c = 0; c < NC; ++c) {
         if (c == li) { pl = p[c][e]; wl = w[c]; }
       }
       const float gpl = -wl / (pl + eps) * g;       // 0 when the label is out of range (wl = 0)
       const float dot = gpl * pl;
 #pragma unroll
-      for (int c = 0; c < SUP_CMAX; ++c) p[c][e] = p[c][e] * ((c == li ? gpl : 0.f) - dot);
+      for (int c = 0; c < NC; ++c) p[c][e] = p[c][e] * ((c == li ? gpl : 0.f) - dot);
     }
 #pragma unroll
-    for (int c = 0; c < SUP_CMAX; ++c) {
+    for (int c = 0; c < NC; ++c) {
       if (c < C) {
         if (V == 4)
           *reinterpret_cast<float4*>(gl + (long long)c * inner + q * V) =
@@ -216,12 +219,15 @@ __global__ void __launch_bounds__(256) sup_bwd_kernel(const float* __restrict__ 
   }
 }
 
-static int sup_ctas_per_sample(long long outer, long long groups) {
+// CTAs per sample for one resident wave (launch bounds: 3 CTAs per SM for C <= 4, else 2) with every thread
+// walking the same number of pixel groups: k = iterations per thread, then just enough CTAs for k.
+static int sup_ctas_per_sample(long long outer, long long groups, int C) {
   int sms = sm_count_cached(current_device());
   if (sms <= 0) sms = 148;
-  long long gx = (groups + 255) / 256;
-  const long long cap = ((long long)sms * 8) / outer;     // total CTAs <= max(sms*8, outer)
-  if (gx > cap) gx = cap;
+  long long cap = ((long long)sms * (C <= 4 ? 3 : 2)) / outer;     // total CTAs <= max(sms*3, outer)
+  if (cap < 1) cap = 1;
+  const long long k = (groups + 256 * cap - 1) / (256 * cap);
+  long long gx = (groups + 256 * k - 1) / (256 * k);
   if (gx < 1) gx = 1;
   return (int)gx;
 }
@@ -254,15 +260,14 @@ extern "C" int iic_sup_forward(const float* logits, const long long* labels, lon
   cudaStream_t st = (cudaStream_t)stream;
   if (dice_out) IIC_CHECK_CUDA(cudaMemsetAsync(dice_out, 0, (size_t)2 * outer * C * sizeof(long long), st));
   const double denom = (double)outer * (double)inner;
-  if (sup_vec_ok(logits, labels, logits, inner)) {
-    const dim3 grid(sup_ctas_per_sample(outer, inner / 4), (unsigned)outer);
-    sup_fwd_kernel<4><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, denom, loss_out, dice_out,
-                                            flags, (SupWorkspace*)workspace);
-  } else {
-    const dim3 grid(sup_ctas_per_sample(outer, inner), (unsigned)outer);
-    sup_fwd_kernel<1><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, denom, loss_out, dice_out,
-                                            flags, (SupWorkspace*)workspace);
-  }
+  const bool vec = sup_vec_ok(logits, labels, logits, inner);
+  const dim3 grid(sup_ctas_per_sample(outer, vec ? inner / 4 : inner, C), (unsigned)outer);
+#define IIC_SUP_FWD(VV, NN)                                                                                      \
+  sup_fwd_kernel<VV, NN><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, denom, loss_out,    \
+                                               dice_out, flags, (SupWorkspace*)workspace)
+  if (vec) { if (C == 2) IIC_SUP_FWD(4, 2); else if (C == 3) IIC_SUP_FWD(4, 3); else if (C == 4) IIC_SUP_FWD(4, 4); else IIC_SUP_FWD(4, SUP_CMAX); }
+  else     { if (C == 2) IIC_SUP_FWD(1, 2); else if (C == 3) IIC_SUP_FWD(1, 3); else if (C == 4) IIC_SUP_FWD(1, 4); else IIC_SUP_FWD(1, SUP_CMAX); }
+#undef IIC_SUP_FWD
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -277,15 +282,14 @@ extern "C" int iic_sup_backward(const float* logits, const long long* labels, lo
   IIC_REQUIRE(eps > 0.0, "iic_sup_backward: eps must be > 0");
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_denom = (float)(1.0 / ((double)outer * (double)inner));
-  if (sup_vec_ok(logits, labels, grad_logits, inner)) {
-    const dim3 grid(sup_ctas_per_sample(outer, inner / 4), (unsigned)outer);
-    sup_bwd_kernel<4><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, inv_denom, grad_loss,
-                                            grad_logits);
-  } else {
-    const dim3 grid(sup_ctas_per_sample(outer, inner), (unsigned)outer);
-    sup_bwd_kernel<1><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, inv_denom, grad_loss,
-                                            grad_logits);
-  }
+  const bool vec = sup_vec_ok(logits, labels, grad_logits, inner);
+  const dim3 grid(sup_ctas_per_sample(outer, vec ? inner / 4 : inner, C), (unsigned)outer);
+#define IIC_SUP_BWD(VV, NN)                                                                                      \
+  sup_bwd_kernel<VV, NN><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, inv_denom,          \
+                                               grad_loss, grad_logits)
+  if (vec) { if (C == 2) IIC_SUP_BWD(4, 2); else if (C == 3) IIC_SUP_BWD(4, 3); else if (C == 4) IIC_SUP_BWD(4, 4); else IIC_SUP_BWD(4, SUP_CMAX); }
+  else     { if (C == 2) IIC_SUP_BWD(1, 2); else if (C == 3) IIC_SUP_BWD(1, 3); else if (C == 4) IIC_SUP_BWD(1, 4); else IIC_SUP_BWD(1, SUP_CMAX); }
+#undef IIC_SUP_BWD
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
