@@ -53,6 +53,10 @@ class KL_div(nn.Module):
             raise NotImplementedError("KL_div(reduction='none') is not on the udaiic path; use the reference for it")
         if self._weight is not None:
             assert len(self._weight) == target.shape[1]
+        if not target.is_floating_point():
+            # the supervised call passes class2one_hot's `long` tensor (semi_seg/epocher.py:165-166); the reference's
+            # `target + eps` promotes it to the default float dtype (kl_losses.py:115)
+            target = target.to(prob.dtype)
         loss = UDAFunction.apply(prob, target, _KIND["kl"], float(self._eps), self._weight, False,
                                  bool(do_assert and checks.want_simplex_kernels()))
         if self._reduction == "sum":

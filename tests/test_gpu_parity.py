@@ -364,7 +364,7 @@ def test_supervised_matches_probability_path_and_flags_bad_labels(iic, cuda_devi
     fused = iic.sup_kl_from_logits(a, lab)
     fused.backward()
     b = lg.clone().requires_grad_(True)
-    onehot = torch.nn.functional.one_hot(lab, 4).permute(0, 3, 1, 2).float().contiguous()
+    onehot = torch.nn.functional.one_hot(lab, 4).permute(0, 3, 1, 2).contiguous()      # `long`, like class2one_hot
     plain = iic.KL_div(verbose=False)(b.softmax(1), onehot)
     plain.backward()
     assert abs(fused.item() - plain.item()) <= 2e-6 * abs(plain.item())
