@@ -13,10 +13,11 @@ The JSON line carries, beyond the base contract:
   value     device-timed throughput, inputs resident in HBM (CUDA-graph replay of the public-API step)
   e2e       the same through the public modules with HOST (pinned) inputs: H2D of both views and the
             global rows, forward, backward, D2H of the loss, every step
-  roofline  the dominant kernel (local_bwd_tma_kernel, one launch per step): algorithmic bytes per
-            launch (16*K bytes/px: read both K-channel maps, write both gradients) over its
-            CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
+  roofline  the dominant kernel (the local backward, local_bwd_tcrb10_kernel at K = 10; one launch per step):
+            algorithmic bytes per launch (16*K bytes/px: read both K-channel maps, write both gradients) over
+            its CUDA-event duration, against MEASURED_PEAKS.json's HBM copy bandwidth
   cpu_baseline  oracle/torch_port.py (the reference's operator sequence) on the host cores, bounded sample
+  extra     secondary shapes and terms (softmax-fused local term, UDA, supervised branch, configs 3-5)
 """
 from __future__ import annotations
 
@@ -137,7 +138,7 @@ def make_inputs(torch, device, seed, B, K, H, W):
 # ---------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: oracle/torch_port.py on the host cores
 # ---------------------------------------------------------------------------------------------------
-def cpu_port_throughput(batch, reps, threads=None):
+def cpu_port_throughput(batch, reps, threads=None, warm=1):
     import torch
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import torch_port as TP
@@ -159,7 +160,8 @@ def cpu_port_throughput(batch, reps, threads=None):
         loss.backward()
         return loss.item()
 
-    step()  # warm
+    for _ in range(max(warm, 1)):
+        step()
     times = []
     for _ in range(reps):
         t0 = time.perf_counter()
@@ -177,15 +179,14 @@ def run_reference(args):
     steps, warm = max(args.steps, 1), args.warmup
     batch = args.cpu_sample_batch
     # bound the whole run: at ~1 Mpx/s a batch-2 step is ~0.1-0.2 s
-    reps = min(steps, 20)
-    for _ in range(min(warm, 3)):
-        pass
-    v, threads, best, times = cpu_port_throughput(batch, reps)
+    reps, warm = min(steps, 20), min(max(warm, 1), 3)
+    _, threads, _, times = cpu_port_throughput(batch, reps, warm=warm)
     ms = statistics.mean(times) * 1e3
+    v = (batch * CFG["H"] * CFG["W"] + batch) / (ms * 1e-3) / 1e6      # the timed steps' own mean, like the B200 arm
     sample = (f"config-2 shape at batch {batch} (of 32) x {CFG['K']} x {CFG['H']} x {CFG['W']}, local p=1 + global, "
-              f"fwd+bwd, best of {reps} steps, {threads} threads")
+              f"fwd+bwd, mean of {reps} timed steps after {warm} warm-up, {threads} threads")
     line = {"impl": "reference", "metric": METRIC, "value": round(v, 4), "unit": UNIT, "n_gpus": args.gpus,
-            "steps": reps, "warmup": 1, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
+            "steps": reps, "warmup": warm, "ms_per_step": round(ms, 3), "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "config2: global+local IIC (padding=1, patch 512) batch 32 fp32 [CPU sample]",
                        "batch_sample": batch, "K": CFG["K"], "H": CFG["H"], "W": CFG["W"], "padding": CFG["pad"]},
