@@ -446,6 +446,32 @@ def run_b200(args):
         del s1, lab
     except Exception as e:  # noqa: BLE001
         extra["supervised_error"] = f"{type(e).__name__}: {e}"
+    try:
+        # flip alignment (semi_seg/epocher.py:160-161,221-224): UDA read through per-sample flips vs the reference's
+        # sequence (B per-sample clone/flip chains + stack, then the UDA term) on the same logits
+        gf = torch.Generator(device=dev).manual_seed(299 + rank)
+        f1 = (torch.randn(B, 4, H, W, device=dev, generator=gf) * 2).requires_grad_(True)
+        f2 = torch.randn(B, 4, H, W, device=dev, generator=gf) * 2
+        fl = iic_b200.draw_flip_flags(1234, B).to(dev)
+        ms_ff = timed_graph(lambda: torch.autograd.grad(iic_b200.uda_from_logits(f1, f2, "mse", teacher_flips=fl), (f1,)))
+        ms_fb = timed_graph(lambda: iic_b200.flip_stack(f2, fl))
+        flist = [int(v) for v in fl.tolist()]
+
+        def ref_seq():
+            tf = torch.stack([x.clone().flip([d for d, bit in ((1, 1), (2, 2)) if f & bit]) if f else x.clone()
+                              for x, f in zip(f2, flist)], dim=0)
+            return torch.autograd.grad(iic_b200.uda_from_logits(f1, tf, "mse"), (f1,))
+        ms_fr = timed_graph(ref_seq)
+        extra["uda_through_flips"] = {
+            "what": "UDA (mse, from logits) fwd+bwd with the teacher read through per-sample flips, (B,4,H,W); "
+                    "flip_stack = the batched flip alone (8*C bytes per pixel); torch_flip_stack_plus_uda = per-sample "
+                    "torch clone/flip + stack, then the fused UDA kernels",
+            "fused_ms": round(ms_ff, 4), "flip_stack_ms": round(ms_fb, 4), "torch_flip_stack_plus_uda_ms": round(ms_fr, 4),
+            "fused_gb_s": round(20.0 * 4 * B * H * W / (ms_ff * 1e-3) / 1e9, 1),
+            "flip_stack_gb_s": round(8.0 * 4 * B * H * W / (ms_fb * 1e-3) / 1e9, 1)}
+        del f1, f2
+    except Exception as e:  # noqa: BLE001
+        extra["flip_error"] = f"{type(e).__name__}: {e}"
 
     # ---- end to end through the public API with HOST buffers ----
     hx, hy, hgx, hgy = (t.detach().cpu().pin_memory() for t in sets[0])

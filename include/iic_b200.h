@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define IIC_B200_ABI_VERSION 4
+#define IIC_B200_ABI_VERSION 5
 
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
@@ -186,6 +186,33 @@ int iic_sup_forward(const float* logits, const long long* labels, long long oute
 int iic_sup_backward(const float* logits, const long long* labels, long long outer, int C, long long inner,
                      double eps, const float* weight, const float* grad_loss, float* grad_logits,
                      void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Per-sample flip alignment.  The reference aligns the two views with
+ *   with FixRandomSeed(seed): torch.stack([TensorRandomFlip(axis=[1, 2], threshold=0.8)(x) for x in batch])
+ * (semi_seg/epocher.py:121,148-149,160-161,264-266; dc2:deepclustering2/augment/tensor_augment.py:17-41),
+ * i.e. per sample a clone and up to two flips, then a stack.  Here the flags are drawn once on the host
+ * (same generator, same order) and passed as one byte per sample: IIC_FLIP_H = axis 1 of the (C,H,W)
+ * sample, IIC_FLIP_W = axis 2.
+ *   iic_flip_batch        out[n,c,h,w] = in[n,c, H-1-h if H-flag else h, W-1-w if W-flag else w]; one launch,
+ *                         one pass; (outer, C, H, W) contiguous float32, out != in.  Its own adjoint.
+ *   iic_uda_flip_forward  iic_uda_forward(prob, flip(target)) without materialising flip(target): the UDA
+ *   iic_uda_flip_backward term of semi_seg/epocher.py:221-224 on `unlabel_tf_logits` and the unflipped
+ *                         `unlabel_logits` (epocher.py:160-161 fused away).  kind / eps / from_logits as for
+ *                         iic_uda_forward (no class weights, no simplex pass); C <= 8.  workspace >=
+ *                         iic_uda_flip_workspace_bytes, zero-initialised once by the caller.
+ * ---------------------------------------------------------------------------------------------- */
+#define IIC_FLIP_H 1
+#define IIC_FLIP_W 2
+int iic_flip_batch(const float* in, float* out, const unsigned char* flips, long long outer, int C, int H, int W,
+                   void* stream);
+size_t iic_uda_flip_workspace_bytes(int device, long long outer);
+int iic_uda_flip_forward(const float* prob, const float* target, const unsigned char* flips, long long outer,
+                         int C, int H, int W, int kind, double eps, int from_logits, float* loss_out, int* flags,
+                         void* workspace, void* stream);
+int iic_uda_flip_backward(const float* prob, const float* target, const unsigned char* flips, long long outer,
+                          int C, int H, int W, int kind, double eps, int from_logits, const float* grad_loss,
+                          float* grad_prob, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Joint exchange over NVLink peer memory (multi-GPU, one process per GPU).  The path's only collective

@@ -3,7 +3,8 @@
 Import as ``iic_b200`` (the importable alias at the repo root); this directory carries the name the
 project layout asks for, which is not a valid Python identifier.
 """
-from . import _lib, checks, ops  # noqa: F401
+from . import _lib, augment, checks, ops  # noqa: F401
+from .augment import TensorRandomFlip, draw_flip_flags, flip_stack  # noqa: F401
 from .checks import check_mode, get_check_mode, raise_if_flagged, set_check_mode  # noqa: F401
 from .losses.iic_loss import (IIDLoss, IIDSegmentationLoss, IIDSegmentationSmallPathLoss, compute_joint,  # noqa: F401
                               patch_generator)
@@ -12,5 +13,5 @@ from .ops import set_data_parallel, data_parallel_transport  # noqa: F401
 from .semi_seg._utils import IICLossWrapper  # noqa: F401
 
 __all__ = ["IIDLoss", "IIDSegmentationLoss", "IIDSegmentationSmallPathLoss", "compute_joint", "patch_generator",
-           "KL_div", "MSELoss", "uda_from_logits", "sup_kl_from_logits", "dice_from_counts", "IICLossWrapper", "set_check_mode", "get_check_mode",
+           "KL_div", "MSELoss", "uda_from_logits", "sup_kl_from_logits", "dice_from_counts", "TensorRandomFlip", "draw_flip_flags", "flip_stack", "IICLossWrapper", "set_check_mode", "get_check_mode",
            "check_mode", "raise_if_flagged", "set_data_parallel", "data_parallel_transport"]

@@ -10,11 +10,13 @@ import os
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libiic_b200.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 FLAG_NAN_LOSS = 1
 FLAG_NOT_SIMPLEX = 2
 FLAG_BAD_LABEL = 4
 UNSUPPORTED = 3
+FLIP_H = 1      # axis 1 of a (C, H, W) sample
+FLIP_W = 2      # axis 2
 
 _p = C.c_void_p
 _ll = C.c_longlong
@@ -51,6 +53,10 @@ PROTOTYPES = {
     "iic_sup_workspace_bytes": (_sz, [_i, _ll]),
     "iic_sup_forward": (_i, [_p, _p, _ll, _i, _ll, _d, _p, _p, _p, _p, _p, _p]),
     "iic_sup_backward": (_i, [_p, _p, _ll, _i, _ll, _d, _p, _p, _p, _p]),
+    "iic_flip_batch": (_i, [_p, _p, _p, _ll, _i, _i, _i, _p]),
+    "iic_uda_flip_workspace_bytes": (_sz, [_i, _ll]),
+    "iic_uda_flip_forward": (_i, [_p, _p, _p, _ll, _i, _i, _i, _i, _d, _i, _p, _p, _p, _p]),
+    "iic_uda_flip_backward": (_i, [_p, _p, _p, _ll, _i, _i, _i, _i, _d, _i, _p, _p, _p]),
     "iic_xchg_buffer_bytes": (_sz, [_i, _ll]),
     "iic_xchg_create": (_i, [_i, _ll, _p]),
     "iic_xchg_export": (_i, [_p, _p]),

@@ -11,64 +11,15 @@
 // A thread owns V consecutive pixels of one sample (V = 4 with 16-byte loads when the rows allow it) and keeps NC
 // channels in registers: NC = C for the usual 2..4 classes (no padded work), NC = 8 with run-time guards otherwise.
 #include "common.cuh"
+#include "pixel_common.cuh"
 
 namespace iic {
-
-constexpr int SUP_CMAX = 8;
 
 struct SupWorkspace {
   unsigned int ticket;   // self-resetting arrival counter
   unsigned int pad_;
   // followed by double partial[gridDim.x * gridDim.y]
 };
-
-template <int V, int NC>
-__device__ __forceinline__ void sup_load(const float* __restrict__ src, long long inner, int C,
-                                         float (&v)[NC][V]) {
-#pragma unroll
-  for (int c = 0; c < NC; ++c) {
-    if (c < C) {
-      if (V == 4) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(src + (long long)c * inner));
-        v[c][0] = t.x; v[c][1 % V] = t.y; v[c][2 % V] = t.z; v[c][3 % V] = t.w;
-      } else {
-        v[c][0] = __ldg(src + (long long)c * inner);
-      }
-    } else {
-#pragma unroll
-      for (int e = 0; e < V; ++e) v[c][e] = -INFINITY;
-    }
-  }
-}
-
-template <int V>
-__device__ __forceinline__ void sup_load_labels(const long long* __restrict__ src, long long (&l)[V]) {
-  if (V == 4) {
-    const longlong2 a = __ldg(reinterpret_cast<const longlong2*>(src));
-    const longlong2 b = __ldg(reinterpret_cast<const longlong2*>(src) + 1);
-    l[0] = a.x; l[1 % V] = a.y; l[2 % V] = b.x; l[3 % V] = b.y;
-  } else {
-    l[0] = __ldg(src);
-  }
-}
-
-// softmax over the channels of pixel e, in place; returns the index of the first maximal logit
-template <int V, int NC>
-__device__ __forceinline__ int sup_softmax(float (&v)[NC][V], int e) {
-  float mx = v[0][e];
-  int arg = 0;
-#pragma unroll
-  for (int c = 1; c < NC; ++c) {
-    if (v[c][e] > mx) { mx = v[c][e]; arg = c; }
-  }
-  float s = 0.f;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) { v[c][e] = __expf(v[c][e] - mx); s += v[c][e]; }   // exp(-inf) = 0 pads
-  const float inv = 1.f / s;
-#pragma unroll
-  for (int c = 0; c < NC; ++c) v[c][e] *= inv;
-  return arg;
-}
 
 // grid (gx, outer): blockIdx.y = sample, so the Dice counters of a CTA belong to one sample
 template <int V, int NC>
@@ -219,19 +170,6 @@ __global__ void __launch_bounds__(256, NC <= 4 ? 3 : 2) sup_bwd_kernel(const flo
   }
 }
 
-// CTAs per sample for one resident wave (launch bounds: 3 CTAs per SM for C <= 4, else 2) with every thread
-// walking the same number of pixel groups: k = iterations per thread, then just enough CTAs for k.
-static int sup_ctas_per_sample(long long outer, long long groups, int C) {
-  int sms = sm_count_cached(current_device());
-  if (sms <= 0) sms = 148;
-  long long cap = ((long long)sms * (C <= 4 ? 3 : 2)) / outer;     // total CTAs <= max(sms*3, outer)
-  if (cap < 1) cap = 1;
-  const long long k = (groups + 256 * cap - 1) / (256 * cap);
-  long long gx = (groups + 256 * k - 1) / (256 * k);
-  if (gx < 1) gx = 1;
-  return (int)gx;
-}
-
 static bool sup_vec_ok(const void* a, const void* b, const void* c, long long inner) {
   if (inner % 4 != 0) return false;
   return ((reinterpret_cast<uintptr_t>(a) | reinterpret_cast<uintptr_t>(b) | reinterpret_cast<uintptr_t>(c)) & 15) == 0;
@@ -261,7 +199,7 @@ extern "C" int iic_sup_forward(const float* logits, const long long* labels, lon
   if (dice_out) IIC_CHECK_CUDA(cudaMemsetAsync(dice_out, 0, (size_t)2 * outer * C * sizeof(long long), st));
   const double denom = (double)outer * (double)inner;
   const bool vec = sup_vec_ok(logits, labels, logits, inner);
-  const dim3 grid(sup_ctas_per_sample(outer, vec ? inner / 4 : inner, C), (unsigned)outer);
+  const dim3 grid(pixel_ctas_per_sample(outer, vec ? inner / 4 : inner, C <= 4 ? 3 : 2), (unsigned)outer);
 #define IIC_SUP_FWD(VV, NN)                                                                                      \
   sup_fwd_kernel<VV, NN><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, denom, loss_out,    \
                                                dice_out, flags, (SupWorkspace*)workspace)
@@ -283,7 +221,7 @@ extern "C" int iic_sup_backward(const float* logits, const long long* labels, lo
   cudaStream_t st = (cudaStream_t)stream;
   const float inv_denom = (float)(1.0 / ((double)outer * (double)inner));
   const bool vec = sup_vec_ok(logits, labels, grad_logits, inner);
-  const dim3 grid(sup_ctas_per_sample(outer, vec ? inner / 4 : inner, C), (unsigned)outer);
+  const dim3 grid(pixel_ctas_per_sample(outer, vec ? inner / 4 : inner, C <= 4 ? 3 : 2), (unsigned)outer);
 #define IIC_SUP_BWD(VV, NN)                                                                                      \
   sup_bwd_kernel<VV, NN><<<grid, 256, 0, st>>>(logits, labels, C, inner, (float)eps, weight, inv_denom,          \
                                                grad_loss, grad_logits)

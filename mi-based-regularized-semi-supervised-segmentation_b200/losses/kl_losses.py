@@ -18,7 +18,7 @@ import torch
 from torch import Tensor, nn
 
 from .. import checks
-from ..ops import SupervisedKLFunction, UDAFunction
+from ..ops import SupervisedKLFunction, UDAFlipFunction, UDAFunction
 
 _KIND = {"mse": 0, "kl": 1}
 
@@ -86,10 +86,19 @@ class MSELoss(nn.Module):
         return loss
 
 
-def uda_from_logits(student_logits: Tensor, teacher_logits: Tensor, kind: str = "mse", eps: float = 1e-16) -> Tensor:
+def uda_from_logits(student_logits: Tensor, teacher_logits: Tensor, kind: str = "mse", eps: float = 1e-16,
+                    teacher_flips: Optional[Tensor] = None) -> Tensor:
     """criterion(softmax(student_logits, 1), softmax(teacher_logits, 1).detach()) in one kernel each way
-    (semi_seg/epocher.py:221-224); the gradient is returned w.r.t. ``student_logits``."""
+    (semi_seg/epocher.py:221-224); the gradient is returned w.r.t. ``student_logits``.
+
+    ``teacher_flips`` (uint8 per sample, ``augment.draw_flip_flags``): the teacher is read through those flips, i.e.
+    ``teacher_logits`` is the UNflipped ``unlabel_logits`` and the ``torch.stack([T(x) for x in unlabel_logits])`` of
+    semi_seg/epocher.py:160-161 is folded into the loss kernels."""
     assert student_logits.shape == teacher_logits.shape
+    if teacher_flips is not None:
+        return UDAFlipFunction.apply(student_logits, teacher_logits.detach(),
+                                     teacher_flips.to(student_logits.device, non_blocking=True), _KIND[kind],
+                                     float(eps), True)
     return UDAFunction.apply(student_logits, teacher_logits.detach(), _KIND[kind], float(eps), None, True, False)
 
 

@@ -32,6 +32,10 @@ _LIBDEF.define("uda_forward(Tensor prob, Tensor target, int kind, float eps, Ten
 _LIBDEF.define("uda_backward(Tensor prob, Tensor target, int kind, float eps, Tensor? weight, bool from_logits, "
                "Tensor grad) -> Tensor")
 _LIBDEF.define("simplex_check(Tensor t, int axis) -> ()")
+_LIBDEF.define("flip_batch(Tensor x, Tensor flips) -> Tensor")
+_LIBDEF.define("uda_flip_forward(Tensor prob, Tensor target, Tensor flips, int kind, float eps, bool from_logits) -> Tensor")
+_LIBDEF.define("uda_flip_backward(Tensor prob, Tensor target, Tensor flips, int kind, float eps, bool from_logits, "
+               "Tensor grad) -> Tensor")
 _LIBDEF.define("sup_forward(Tensor logits, Tensor labels, float eps, Tensor? weight, bool want_dice) -> (Tensor, Tensor)")
 _LIBDEF.define("sup_backward(Tensor logits, Tensor labels, float eps, Tensor? weight, Tensor grad) -> Tensor")
 
@@ -46,6 +50,13 @@ class _StreamState:
         self.uda_ws = torch.zeros(lib.iic_uda_workspace_bytes(device.index or 0), dtype=torch.uint8, device=device)
         self.epi_ws = {}
         self.sup_ws = None
+        self.flip_ws = None
+
+    def uda_flip_ws(self, outer: int, device) -> torch.Tensor:
+        nbytes = _lib.load().iic_uda_flip_workspace_bytes(device.index or 0, outer)
+        if self.flip_ws is None or self.flip_ws.numel() < nbytes:
+            self.flip_ws = torch.zeros(nbytes, dtype=torch.uint8, device=device)
+        return self.flip_ws
 
     def supervised_ws(self, outer: int, device) -> torch.Tensor:
         nbytes = _lib.load().iic_sup_workspace_bytes(device.index or 0, outer)
@@ -346,6 +357,59 @@ def _simplex_check(t, axis):
     _lib.check(rc, "iic_simplex_check")
 
 
+def _flip_args(name, x, flips):
+    _require_cuda_f32(name, x)
+    if x.dim() != 4:
+        raise ValueError(f"iic_b200.{name}: expected a (B, C, H, W) tensor, got {tuple(x.shape)}")
+    if flips.dtype != torch.uint8 or flips.device != x.device or flips.shape != x.shape[:1]:
+        raise TypeError(f"iic_b200.{name}: flips must be a uint8 tensor of shape ({x.shape[0]},) on {x.device}, got "
+                        f"{flips.dtype} {tuple(flips.shape)} on {flips.device}")
+    return x.contiguous(), flips.contiguous()
+
+
+def _flip_batch(x, flips):
+    lib = _lib.load()
+    x, flips = _flip_args("flip_batch", x, flips)
+    B, C, H, W = x.shape
+    out = torch.empty_like(x)
+    with torch.cuda.device(x.device):
+        rc = lib.iic_flip_batch(x.data_ptr(), out.data_ptr(), flips.data_ptr(), B, C, H, W, _stream(x.device))
+    _lib.check(rc, "iic_flip_batch")
+    return out
+
+
+def _uda_flip_forward(prob, target, flips, kind, eps, from_logits):
+    lib = _lib.load()
+    prob, flips = _flip_args("uda_flip_forward", prob, flips)
+    _require_cuda_f32("target", target)
+    if prob.shape != target.shape:
+        raise ValueError(f"iic_b200.uda_flip_forward: shapes {tuple(prob.shape)} vs {tuple(target.shape)}")
+    target = target.contiguous()
+    B, C, H, W = prob.shape
+    st = _state(prob.device)
+    loss = torch.empty((), dtype=torch.float32, device=prob.device)
+    with torch.cuda.device(prob.device):
+        rc = lib.iic_uda_flip_forward(prob.data_ptr(), target.data_ptr(), flips.data_ptr(), B, C, H, W, kind, float(eps),
+                                      int(from_logits), loss.data_ptr(), st.flags.data_ptr(),
+                                      st.uda_flip_ws(B, prob.device).data_ptr(), _stream(prob.device))
+    _lib.check(rc, "iic_uda_flip_forward")
+    return loss
+
+
+def _uda_flip_backward(prob, target, flips, kind, eps, from_logits, grad):
+    lib = _lib.load()
+    prob, flips = _flip_args("uda_flip_backward", prob, flips)
+    target = target.contiguous()
+    B, C, H, W = prob.shape
+    out = torch.empty_like(prob)
+    grad = grad.to(torch.float32).reshape(())
+    with torch.cuda.device(prob.device):
+        rc = lib.iic_uda_flip_backward(prob.data_ptr(), target.data_ptr(), flips.data_ptr(), B, C, H, W, kind, float(eps),
+                                       int(from_logits), grad.data_ptr(), out.data_ptr(), _stream(prob.device))
+    _lib.check(rc, "iic_uda_flip_backward")
+    return out
+
+
 def _sup_args(logits, labels, weight):
     _require_cuda_f32("logits", logits)
     if labels.dtype != torch.int64 or labels.device != logits.device:
@@ -390,6 +454,9 @@ def _sup_backward(logits, labels, eps, weight, grad):
 
 
 _LIBIMPL = torch.library.Library("iic_b200", "IMPL", "CUDA")
+_LIBIMPL.impl("flip_batch", _flip_batch)
+_LIBIMPL.impl("uda_flip_forward", _uda_flip_forward)
+_LIBIMPL.impl("uda_flip_backward", _uda_flip_backward)
 _LIBIMPL.impl("sup_forward", _sup_forward)
 _LIBIMPL.impl("sup_backward", _sup_backward)
 _LIBIMPL.impl("local_joint", _local_joint)
@@ -415,7 +482,8 @@ def _cpu_refusal(name):
 
 _LIBCPU = torch.library.Library("iic_b200", "IMPL", "CPU")
 for _n in ("local_joint", "local_epilogue", "local_backward", "local_joint_logits", "local_backward_logits", "global_joint", "global_epilogue",
-           "global_backward", "uda_forward", "uda_backward", "simplex_check", "sup_forward", "sup_backward"):
+           "global_backward", "uda_forward", "uda_backward", "simplex_check", "sup_forward", "sup_backward",
+           "flip_batch", "uda_flip_forward", "uda_flip_backward"):
     _LIBCPU.impl(_n, _cpu_refusal(_n))
 
 ops = torch.ops.iic_b200
@@ -632,3 +700,36 @@ class SupervisedKLFunction(torch.autograd.Function):
         logits, labels, weight = ctx.saved_tensors
         g = ops.sup_backward(logits, labels, ctx.eps, weight, grad.contiguous())
         return g, None, None, None, None
+
+
+class FlipBatchFunction(torch.autograd.Function):
+    """Per-sample flips of a (B, C, H, W) batch in one launch (semi_seg/epocher.py:148-149,160-161,264-266).  A flip
+    is a permutation and its own inverse, so the backward is the same kernel on the incoming gradient."""
+
+    @staticmethod
+    def forward(ctx, x, flips):
+        ctx.save_for_backward(flips)
+        return ops.flip_batch(x, flips)
+
+    @staticmethod
+    def backward(ctx, grad):
+        (flips,) = ctx.saved_tensors
+        return ops.flip_batch(grad.contiguous(), flips), None
+
+
+class UDAFlipFunction(torch.autograd.Function):
+    """UDAFunction with the target read through per-sample flips (the flipped copy is never materialised)."""
+
+    @staticmethod
+    def forward(ctx, prob, target, flips, kind, eps, from_logits):
+        loss = ops.uda_flip_forward(prob, target, flips, kind, eps, from_logits)
+        ctx.save_for_backward(prob, target, flips)
+        ctx.cfg = (kind, eps, from_logits)
+        return loss
+
+    @staticmethod
+    def backward(ctx, grad):
+        prob, target, flips = ctx.saved_tensors
+        kind, eps, from_logits = ctx.cfg
+        g = ops.uda_flip_backward(prob, target, flips, kind, eps, from_logits, grad.contiguous())
+        return g, None, None, None, None, None

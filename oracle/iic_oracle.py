@@ -343,3 +343,49 @@ def dice_counts(logits, labels):
     tgt = class2one_hot(labels, C)
     axes = tuple(range(2, z.ndim))
     return (pred * tgt).sum(axis=axes), (pred + tgt).sum(axis=axes)
+
+
+# --------------------------------------------------------------------------------------------
+# per-sample flip alignment
+# --------------------------------------------------------------------------------------------
+FLIP_H, FLIP_W = 1, 2     # axis 1 / axis 2 of a (C, H, W) sample
+
+
+def draw_flip_flags(seed: int, batch: int, axis=(1, 2), threshold: float = 0.8):
+    """The draws of ``[TensorRandomFlip(axis, threshold)(x) for x in batch]`` under ``FixRandomSeed(seed)``
+    (semi_seg/epocher.py:121,148-149; dc2:augment/tensor_augment.py:31-41; dc2:decorator/decorator.py:196-212):
+    ``random.seed(seed)``, then per sample one ``random.random() < threshold`` per axis, in axis order."""
+    import random
+    rng = random.Random()
+    rng.seed(seed)
+    out = np.zeros(batch, dtype=np.uint8)
+    for n in range(batch):
+        for a in axis:
+            if rng.random() < threshold:
+                out[n] ^= FLIP_H if a == 1 else FLIP_W
+    return out
+
+
+def flip_stack(batch, flags):
+    """``torch.stack([T(x) for x in batch])`` for the flips in ``flags`` (one (C, H, W) sample at a time)."""
+    x = np.asarray(batch)
+    out = np.empty_like(x)
+    for n, f in enumerate(np.asarray(flags)):
+        s = x[n]
+        if f & FLIP_H:
+            s = s[:, ::-1, :]
+        if f & FLIP_W:
+            s = s[:, :, ::-1]
+        out[n] = s
+    return out
+
+
+def uda_from_logits_flipped(student_logits, teacher_logits, flags, kind: str = "mse", with_grads: bool = False):
+    """semi_seg/epocher.py:160-161 + 221-224: criterion(softmax(student), softmax(flip_stack(teacher)).detach());
+    the gradient goes back through the student's softmax."""
+    p, t = softmax(student_logits, axis=1), softmax(flip_stack(teacher_logits, flags), axis=1)
+    fn = mse_loss if kind == "mse" else kl_div
+    if not with_grads:
+        return fn(p, t)
+    loss, gp = fn(p, t, with_grads=True)
+    return loss, softmax_backward(p, gp, axis=1)

@@ -163,6 +163,41 @@ def make_sup(ns):
         print(name, res["loss_f64"], res["loss_f32"], res["dice"])
 
 
+def make_flip(ns):
+    """Flip-alignment fixtures: the reference's seeded per-sample loop (semi_seg/epocher.py:148-149,160-161) and
+    its UDA term on the flipped teacher logits (epocher.py:221-224)."""
+    torch = ns.torch
+    TensorRandomFlip, FixRandomSeed = ref_loader.load_flip()
+    T = TensorRandomFlip(axis=[1, 2], threshold=0.8)          # semi_seg/epocher.py:121
+    rng = np.random.default_rng(20260120)
+    for name, shape, seed, kind in (("f_8x4x6x8_mse", (8, 4, 6, 8), 3, "mse"),        # 16-byte rows
+                                    ("f_6x4x5x7_kl", (6, 4, 5, 7), 11, "kl"),         # ragged rows
+                                    ("f_5x2x12x12_kl", (5, 2, 12, 12), 12345, "kl"),
+                                    ("f_7x8x4x4_mse", (7, 8, 4, 4), 0, "mse")):
+        student = torch.from_numpy((rng.standard_normal(shape) * 2).astype(np.float32))
+        teacher = torch.from_numpy((rng.standard_normal(shape) * 2).astype(np.float32))
+        with FixRandomSeed(seed):
+            teacher_tf = torch.stack([T(x) for x in teacher], dim=0)
+        with FixRandomSeed(seed):                              # the draws themselves, for the flag fixture
+            import random as _random
+            draws = [[_random.random() < 0.8 for _ in range(2)] for _ in range(shape[0])]
+        flags = np.asarray([(1 if h else 0) | (2 if w else 0) for h, w in draws], dtype=np.uint8)
+        out = {}
+        for tag, dt in (("f64", torch.float64), ("f32", torch.float32)):
+            s = student.to(dt).clone().requires_grad_(True)
+            crit = torch.nn.MSELoss() if kind == "mse" else ns.KL_div(verbose=False)
+            loss = crit(s.softmax(1), teacher_tf.to(dt).softmax(1).detach())
+            (g,) = torch.autograd.grad(loss, (s,))
+            out[f"loss_{tag}"] = loss.item()
+            if tag == "f64":
+                out["g_f64"] = g.numpy()
+            else:
+                out["gerr_f32"] = _relmax(g.numpy(), out["g_f64"])
+        np.savez_compressed(os.path.join(OUT, f"{name}.npz"), kind=kind, seed=seed, student=student.numpy(),
+                            teacher=teacher.numpy(), teacher_tf=teacher_tf.numpy(), flags=flags, **out)
+        print(name, flags.tolist(), out["loss_f64"], out["loss_f32"])
+
+
 def main():
     ns = ref_loader.load()
     torch = ns.torch
@@ -170,6 +205,9 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if "--sup-only" in sys.argv:
         make_sup(ns)
+        return
+    if "--flip-only" in sys.argv:
+        make_flip(ns)
         return
     rng = np.random.default_rng(20260118)
 
@@ -267,6 +305,7 @@ def main():
     print("simplex verdicts", verdicts)
 
     make_sup(ns)
+    make_flip(ns)
 
 
 if __name__ == "__main__":

@@ -167,3 +167,30 @@ def load_dice():
                 sys.modules[k] = v
     _cache["dice"] = dice.UniversalDice
     return dice.UniversalDice
+
+
+def load_flip():
+    """The reference's unmodified ``TensorRandomFlip`` (dc2:augment/tensor_augment.py:17-41) and ``FixRandomSeed``
+    (dc2:decorator/decorator.py:196-212), loaded by path; returns ``(TensorRandomFlip, FixRandomSeed)``."""
+    if "flip" in _cache:
+        return _cache["flip"]
+    ns = load()
+    a = ns._assertion
+    names = ("deepclustering2", "deepclustering2.utils")
+    saved = {k: sys.modules.get(k) for k in names}
+    try:
+        mods = {k: types.ModuleType(k) for k in names}
+        for m in mods.values():
+            m.__path__ = []
+        mods["deepclustering2.utils"].assert_list = a.assert_list
+        sys.modules.update(mods)
+        aug = _load_by_path("_ref_dc2_tensor_augment", _extract_wheel_member("deepclustering2/augment/tensor_augment.py"))
+        dec = _load_by_path("_ref_dc2_decorator", _extract_wheel_member("deepclustering2/decorator/decorator.py"))
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache["flip"] = (aug.TensorRandomFlip, dec.FixRandomSeed)
+    return _cache["flip"]

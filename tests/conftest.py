@@ -27,6 +27,8 @@ def golden_names(kind):
             out.append(n)
         elif kind == "sup" and n.startswith("s_"):
             out.append(n)
+        elif kind == "flip" and n.startswith("f_"):
+            out.append(n)
     return out
 
 

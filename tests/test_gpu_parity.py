@@ -383,6 +383,51 @@ def test_supervised_matches_probability_path_and_flags_bad_labels(iic, cuda_devi
 
 
 # ---------------------------------------------------------------------------------------------------
+# per-sample flip alignment: batched flip and UDA through the flips
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names("flip"))
+def test_flip_golden(iic, cuda_device, name):
+    g = load_golden(name)
+    seed, kind = int(g["seed"]), str(g["kind"])
+    teacher = torch.from_numpy(g["teacher"]).to(cuda_device)
+    tf = iic.flip_stack(teacher, seed)                                   # == the reference's seeded per-sample loop
+    assert np.array_equal(tf.cpu().numpy(), g["teacher_tf"])             # a permutation: bit-exact
+    student = torch.from_numpy(g["student"]).to(cuda_device).requires_grad_(True)
+    flags = iic.draw_flip_flags(seed, len(teacher))
+    loss = iic.uda_from_logits(student, teacher, kind, teacher_flips=flags)
+    loss.backward()
+    assert abs(loss.item() - float(g["loss_f64"])) <= LOSS_RTOL * abs(float(g["loss_f64"]))
+    assert relmax(student.grad.cpu().numpy(), g["g_f64"]) <= GRAD_RTOL
+    # and it is the same number as the unfused sequence on the materialised flip
+    s2 = torch.from_numpy(g["student"]).to(cuda_device).requires_grad_(True)
+    l2 = iic.uda_from_logits(s2, tf, kind)
+    assert abs(l2.item() - loss.item()) <= 1e-6 * abs(loss.item())
+
+
+@pytest.mark.parametrize("kind", ["mse", "kl"])
+@pytest.mark.parametrize("shape", [(8, 4, 224, 224), (5, 4, 37, 53), (4, 8, 9, 12), (6, 3, 16, 20), (4, 2, 7, 8)])
+def test_flip_vs_oracle(iic, cuda_device, kind, shape):
+    rng = np.random.default_rng(300 + shape[1] + shape[3])
+    B = shape[0]
+    ls = (rng.standard_normal(shape) * 2).astype(np.float32)
+    lt = (rng.standard_normal(shape) * 2).astype(np.float32)
+    flags = np.asarray([n % 4 for n in range(B)], dtype=np.uint8)        # none / H / W / both
+    fd = torch.from_numpy(flags)
+    td = torch.from_numpy(lt).to(cuda_device).requires_grad_(True)
+    out = iic.flip_stack(td, fd)
+    assert np.array_equal(out.detach().cpu().numpy(), O.flip_stack(lt, flags))
+    up = torch.from_numpy(rng.standard_normal(shape).astype(np.float32)).to(cuda_device)
+    out.backward(up)                                                     # the adjoint of a flip is the same flip
+    assert np.array_equal(td.grad.cpu().numpy(), O.flip_stack(up.cpu().numpy(), flags))
+    sd = torch.from_numpy(ls).to(cuda_device).requires_grad_(True)
+    loss = iic.uda_from_logits(sd, td.detach(), kind, teacher_flips=fd)
+    (2.0 * loss).backward()
+    ol, og = O.uda_from_logits_flipped(ls, lt, flags, kind, with_grads=True)
+    assert abs(loss.item() - ol) <= LOSS_RTOL * abs(ol)
+    assert relmax(sd.grad.cpu().numpy(), 2.0 * og) <= GRAD_RTOL
+
+
+# ---------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE config-2 size (32 x 10 x 224 x 224, padding 1)
 # ---------------------------------------------------------------------------------------------------
 def test_full_size_properties(iic, cuda_device):

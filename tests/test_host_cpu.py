@@ -32,7 +32,7 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"libiic_b200.so does not export {name}"
     assert declared == set(built._lib.PROTOTYPES), declared ^ set(built._lib.PROTOTYPES)
-    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 4
+    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 5
 
 
 def test_patch_count_matches_reference_windows(built):
@@ -91,6 +91,28 @@ def test_no_cpu_fallback(built):
         built.MSELoss()(x, x.detach())
     with pytest.raises(Exception) as ei:
         built.sup_kl_from_logits(torch.randn(2, 4, 8, 8, requires_grad=True), torch.zeros(2, 8, 8, dtype=torch.int64))
+    assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
+
+
+def test_flip_flags_replay_the_reference_draws(built):
+    """draw_flip_flags == the draws of the reference's seeded per-sample loop (golden fixtures made by running it)."""
+    from conftest import golden_names
+    names = golden_names("flip")
+    assert names
+    for name in names:
+        g = load_golden(name)
+        flags = built.draw_flip_flags(int(g["seed"]), len(g["teacher"]))
+        assert flags.dtype == torch.uint8 and flags.tolist() == g["flags"].tolist(), name
+    assert built.draw_flip_flags(5, 4, axis=None).tolist() == [0, 0, 0, 0]
+    assert built.TensorRandomFlip(axis=[1, 2], threshold=0.8).flags(3, 8).tolist() == load_golden("f_8x4x6x8_mse")["flags"].tolist()
+    with pytest.raises(ValueError):
+        built.draw_flip_flags(0, 2, axis=[0])
+    import random
+    state = random.getstate()
+    built.draw_flip_flags(123, 16)
+    assert random.getstate() == state          # like FixRandomSeed, the module-level generator is left alone
+    with pytest.raises(Exception) as ei:       # no CPU path for the kernels themselves
+        built.flip_stack(torch.zeros(2, 1, 4, 4), 0)
     assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
 
 

@@ -82,6 +82,18 @@ def test_supervised_oracle_rejects_bad_labels():
         O.class2one_hot(np.array([[[0, 4]]]), 4)
 
 
+@pytest.mark.parametrize("name", golden_names("flip"))
+def test_flip_oracle_matches_reference(name):
+    """semi_seg/epocher.py:148-149,160-161,221-224 as run by oracle/make_golden.py::make_flip."""
+    g = load_golden(name)
+    flags = O.draw_flip_flags(int(g["seed"]), len(g["teacher"]))
+    assert np.array_equal(flags, g["flags"])
+    assert np.array_equal(O.flip_stack(g["teacher"], flags), g["teacher_tf"])
+    loss, grad = O.uda_from_logits_flipped(g["student"], g["teacher"], flags, str(g["kind"]), with_grads=True)
+    assert abs(loss - g["loss_f64"]) <= 1e-12 * max(1.0, abs(g["loss_f64"]))
+    assert relmax(grad, g["g_f64"]) < 1e-11
+
+
 def test_patch_windows_match_reference():
     g = load_golden("patch_windows")
     for key, wins in g.items():
@@ -180,3 +192,16 @@ def test_live_reference_supervised_branch():
     inter, union = O.dice_counts(lg.detach().numpy(), tgt.numpy()[:, 0])
     assert np.array_equal(meter._intersections[0].numpy(), inter)
     assert np.array_equal(meter._unions[0].numpy(), union)
+
+
+@pytest.mark.skipif(not ref_loader.available(), reason="/root/reference not mounted (GPU box)")
+def test_live_reference_flip_draws():
+    ns = ref_loader.load()
+    torch = ns.torch
+    TensorRandomFlip, FixRandomSeed = ref_loader.load_flip()
+    T = TensorRandomFlip(axis=[1, 2], threshold=0.8)
+    x = torch.arange(9 * 2 * 3 * 5, dtype=torch.float32).reshape(9, 2, 3, 5)
+    for seed in (0, 1, 7, 2**31 - 1):
+        with FixRandomSeed(seed):
+            ref = torch.stack([T(s) for s in x], dim=0)
+        assert np.array_equal(O.flip_stack(x.numpy(), O.draw_flip_flags(seed, 9)), ref.numpy()), seed
