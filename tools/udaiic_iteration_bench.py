@@ -12,7 +12,13 @@ changes between the arms is the loss path only:
   b200    iic_b200 drop-in modules on softmax maps (checks deferred to one read per iteration)
   fused   iic_b200 with the head softmax fused (IIDSegmentationSmallPathLoss.from_logits, uda_from_logits)
 
-    python tools/udaiic_iteration_bench.py [--K 10 --paddings 1 1 --unlabeled 10 --iters 20]
+    python tools/udaiic_iteration_bench.py [--K 10 --paddings 1 1 --unlabeled 10 --iters 20] [--per-sample-flips]
+
+--per-sample-flips (added after the round's last GPU run -- not measured yet): the views are aligned with the
+reference's seeded per-sample random flips instead of one fixed W flip.  The torch arm then runs the reference's
+Python loops (clone/flip per sample + stack, semi_seg/epocher.py:148-149,160-161,264-266) and its supervised
+KL_div on a `long` one-hot (epocher.py:165-166); the b200 / fused arms use draw_flip_flags + flip_stack, the UDA
+term read through the flips and sup_kl_from_logits.
 
 The UNet below has the reference's topology and channel widths (contrastyou/arch/unet.py:43-133:
 5 levels, 16..256 channels, double 3x3 conv+BN+ReLU blocks, nearest-upsample + conv decoders) with
@@ -105,6 +111,7 @@ def main():
     ap.add_argument("--unlabeled", type=int, default=10)
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--arms", nargs="+", default=["torch", "b200", "fused"])
+    ap.add_argument("--per-sample-flips", action="store_true")
     a = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.backends.cudnn.allow_tf32 = False
@@ -130,7 +137,72 @@ def main():
     l2 = iic_b200.IIDSegmentationSmallPathLoss(padding=a.paddings[1], patch_size=1024)
     mse = iic_b200.MSELoss()
 
+    def ref_flip_stack(batch, flags):
+        """The reference's loop: per sample a clone and up to two flips, then a stack."""
+        out = []
+        for x, f in zip(batch, flags):
+            x = x.clone()
+            if f & 1:
+                x = x.flip(1)
+            if f & 2:
+                x = x.flip(2)
+            out.append(x)
+        return torch.stack(out, dim=0)
+
+    step_no = [0]
+
+    def iteration_flips(arm):
+        """Same iteration with seeded per-sample flips and the fused supervised branch (see the module docstring)."""
+        step_no[0] += 1
+        flags = iic_b200.draw_flip_flags(step_no[0], nu)
+        if arm == "torch":
+            fl = flags.tolist()
+            align = lambda t: ref_flip_stack(t, fl)                                  # noqa: E731
+        else:
+            fdev = flags.to(dev, non_blocking=True)
+            align = lambda t: iic_b200.flip_stack(t, fdev)                           # noqa: E731
+        img_u_tf = align(img_u)
+        logits, conv5, up3, up2 = net(torch.cat((img_l, img_u, img_u_tf)))
+        if arm == "torch":
+            onehot = F.one_hot(tgt_l, 4).permute(0, 3, 1, 2)                          # class2one_hot: a `long` tensor
+            p = logits[:nl].softmax(1)
+            sup = (-onehot * torch.log((p + 1e-16) / (onehot + 1e-16))).sum(1).mean()
+        else:
+            sup = iic_b200.sup_kl_from_logits(logits[:nl], tgt_l)
+        lu, lu_tf = logits[nl:nl + nu], logits[nl + nu:]
+        f5 = conv5[nl:].mean((2, 3))
+        f3a, f3b = align(up3[nl:nl + nu]), up3[nl + nu:]
+        f2a, f2b = align(up2[nl:nl + nu]), up2[nl + nu:]
+        iic_terms = []
+        for s in range(S):
+            e = enc_heads[s](f5).softmax(1)
+            ea, eb = e[:nu], e[nu:]
+            z3a, z3b = dec3_heads[s](f3a), dec3_heads[s](f3b)
+            z2a, z2b = dec2_heads[s](f2a), dec2_heads[s](f2b)
+            if arm == "torch":
+                t = torch_global_iic(ea, eb) + 0.5 * torch_local_iic(z3a.softmax(1), z3b.softmax(1), a.paddings[0]) \
+                    + 0.5 * torch_local_iic(z2a.softmax(1), z2b.softmax(1), a.paddings[1])
+            elif arm == "b200":
+                t = g_loss(ea, eb)[0] + 0.5 * l3(z3a.softmax(1), z3b.softmax(1)) + 0.5 * l2(z2a.softmax(1), z2b.softmax(1))
+            else:
+                t = g_loss(ea, eb)[0] + 0.5 * l3.from_logits(z3a, z3b) + 0.5 * l2.from_logits(z2a, z2b)
+            iic_terms.append(t)
+        iic = sum(iic_terms) / S / 2.0
+        if arm == "torch":
+            uda = F.mse_loss(lu_tf.softmax(1), align(lu).softmax(1).detach())
+        else:
+            uda = iic_b200.uda_from_logits(lu_tf, lu, "mse", teacher_flips=fdev)
+        total = sup + 5.0 * uda + 0.1 * iic
+        opt.zero_grad(set_to_none=True)
+        total.backward()
+        opt.step()
+        if arm != "torch":
+            iic_b200.raise_if_flagged(dev)
+        return total
+
     def iteration(arm):
+        if a.per_sample_flips:
+            return iteration_flips(arm)
         img_u_tf = img_u.flip(3)
         logits, conv5, up3, up2 = net(torch.cat((img_l, img_u, img_u_tf)))
         sup = F.cross_entropy(logits[:nl], tgt_l)
@@ -169,7 +241,7 @@ def main():
 
     out = {"config": {"K": K, "subheads": S, "paddings": a.paddings, "labeled": nl, "unlabeled": nu, "size": 224,
                       "layers": ["Conv5 (global)", "Up_conv3 112^2", "Up_conv2 224^2"], "optimizer": "Adam",
-                      "data": "synthetic", "iters": a.iters}}
+                      "data": "synthetic", "iters": a.iters, "per_sample_flips": a.per_sample_flips}}
     for arm in a.arms:
         try:
             for _ in range(3):
