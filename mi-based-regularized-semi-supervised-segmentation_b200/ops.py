@@ -570,6 +570,22 @@ def set_data_parallel(enabled: bool, group=None, peer_memory=None):
         _xchg = None
 
 
+def ddp_loss_scale(group=None) -> float:
+    """Factor for the IIC terms of a loss that is back-propagated under ``DistributedDataParallel``.
+
+    With the joint exchange on, every rank holds the IIC loss L of the GLOBAL batch and its backward yields
+    dL/d(activations of the local shard); the parameter gradient of L is therefore the SUM of the ranks' gradients
+    ("DDP semantics").  Stock DDP averages gradients, which is right for the per-rank means
+    (supervised, UDA) and a factor world_size too small for L: multiply the IIC terms by this value.  1.0 when the
+    exchange is off or no process group is up."""
+    if not _dist_enabled:
+        return 1.0
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1.0
+    return float(dist.get_world_size(group if group is not None else _process_group))
+
+
 def data_parallel_transport() -> str:
     """'peer_memory', 'nccl' or 'off' -- what _maybe_allreduce will use."""
     if not _dist_enabled:
