@@ -116,6 +116,26 @@ def test_flip_flags_replay_the_reference_draws(built):
     assert "CPU" in str(ei.value) or "CUDA" in str(ei.value)
 
 
+def test_flip_flags_against_live_reference(built):
+    """Many seeds and batch sizes against the reference's own TensorRandomFlip loop (build container only)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ref_loader
+    if not ref_loader.available():
+        pytest.skip("/root/reference not mounted (GPU box)")
+    TensorRandomFlip, FixRandomSeed = ref_loader.load_flip()
+    for axis, thr in (([1, 2], 0.8), ([2], 0.5), ([1], 0.3), ([2, 1], 0.8)):
+        T = TensorRandomFlip(axis=axis, threshold=thr)
+        for seed in (0, 1, 2, 17, 4242, 2**31 - 1):
+            for B in (1, 5, 10):
+                x = torch.arange(B * 2 * 3 * 4, dtype=torch.float32).reshape(B, 2, 3, 4)
+                with FixRandomSeed(seed):
+                    ref = torch.stack([T(s) for s in x], dim=0)
+                flags = built.draw_flip_flags(seed, B, axis, thr).tolist()
+                mine = torch.stack([s.flip([d for d, bit in ((1, 1), (2, 2)) if f & bit]) if f else s
+                                    for s, f in zip(x, flags)], dim=0)
+                assert torch.equal(mine, ref), (axis, thr, seed, B)
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(PKG):
         for f in files:
