@@ -1,15 +1,18 @@
 """Loss plumbing of the reference's ``semi_seg/_utils.py`` that sits on the hot path.
 
 ``IIDLoss`` (semi_seg/_utils.py:12-15) returns the loss only; ``IICLossWrapper`` (:189-224) picks the
-global loss for encoder features and the small-patch local loss for decoder features.  The UNet block
+global loss for encoder features and the small-patch local loss for decoder features.
+``average_iter`` / ``weighted_average_iter`` (contrastyou/helper/utils.py:46-47,54-56) are the two reductions the
+epocher applies to those losses (semi_seg/epocher.py:275,277); ``combine_iic_losses`` does both in three launches.  The UNet block
 names come from contrastyou/arch/unet.py:185-194 and are restated here so this module does not need
 the backbone.
 """
 from __future__ import annotations
 
 from itertools import repeat
-from typing import List, Union
+from typing import List, Sequence, Union
 
+import torch
 from torch import Tensor, nn
 
 from ..losses.iic_loss import IIDLoss as _IIDLoss
@@ -67,3 +70,36 @@ class IICLossWrapper(nn.Module):
     @property
     def feature_names(self):
         return self._encoder_features + self._decoder_features
+
+
+def average_iter(a_list):
+    """Mean over the sub-heads of one layer (contrastyou/helper/utils.py:46-47; semi_seg/epocher.py:275)."""
+    a_list = list(a_list)
+    return sum(a_list) / float(len(a_list))
+
+
+def weighted_average_iter(a_list, weight_list):
+    """sum_l w_l a_l / (sum_l w_l + 1e-16) over the feature layers (contrastyou/helper/utils.py:54-56;
+    semi_seg/epocher.py:277; the weights are the normalised feature importances of semi_seg/trainer.py:46-49)."""
+    a_list, weight_list = list(a_list), list(weight_list)
+    assert len(a_list) == len(weight_list), (len(a_list), len(weight_list))
+    return sum(a * w for a, w in zip(a_list, weight_list)) / (sum(weight_list) + 1e-16)
+
+
+def combine_iic_losses(losses_per_layer: Sequence[Sequence[Tensor]], feature_importance: Sequence[float]):
+    """``weighted_average_iter([average_iter(heads) for heads in losses_per_layer], feature_importance)`` -- the value
+    ``IICTrainEpocher.regularization`` returns (semi_seg/epocher.py:274-277) -- as ONE stack, one weighted sum and one
+    division instead of ~2*S*L scalar kernels.  Also returns the per-layer means (for the ``individual_mis`` meter,
+    epocher.py:279-282) as one tensor, so they can be read with a single host transfer."""
+    assert len(losses_per_layer) == len(feature_importance), (len(losses_per_layer), len(feature_importance))
+    counts = [len(h) for h in losses_per_layer]
+    assert all(c > 0 for c in counts), counts
+    flat = torch.stack([l for heads in losses_per_layer for l in heads])
+    # weight of one sub-head loss: importance of its layer / number of sub-heads of that layer
+    w = torch.tensor([float(fi) / c for fi, c in zip(feature_importance, counts) for _ in range(c)],
+                     dtype=flat.dtype).to(flat.device, non_blocking=True)
+    total = (flat * w).sum() / (float(sum(feature_importance)) + 1e-16)
+    seg = torch.tensor([1.0 / c for c in counts for _ in range(c)], dtype=flat.dtype).to(flat.device, non_blocking=True)
+    index = torch.tensor([i for i, c in enumerate(counts) for _ in range(c)]).to(flat.device, non_blocking=True)
+    per_layer = torch.zeros(len(counts), dtype=flat.dtype, device=flat.device).index_add(0, index, flat * seg)
+    return total, per_layer

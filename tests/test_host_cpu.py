@@ -136,6 +136,25 @@ def test_flip_flags_against_live_reference(built):
                 assert torch.equal(mine, ref), (axis, thr, seed, B)
 
 
+def test_sub_head_and_layer_reductions(built):
+    """A7 of SURVEY.md section 8a: the epocher's two reductions and their batched form."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import iic_oracle as O
+    from iic_b200.semi_seg._utils import average_iter, combine_iic_losses, weighted_average_iter
+    torch.manual_seed(0)
+    layers = [[torch.randn((), dtype=torch.float64, requires_grad=True) for _ in range(n)] for n in (5, 5, 3)]
+    imp = [0.5, 0.3, 0.2]
+    means = [average_iter(h) for h in layers]
+    ref = weighted_average_iter(means, imp)
+    want = O.weighted_average_iter([O.average_iter([float(l.detach()) for l in h]) for h in layers], imp)
+    assert abs(float(ref) - want) < 1e-14
+    total, per_layer = combine_iic_losses(layers, imp)
+    assert abs(float(total) - want) < 1e-14
+    assert torch.allclose(per_layer, torch.stack([m.detach() for m in means]), atol=1e-15)
+    total.backward()                                   # d total / d loss = importance / (sum + 1e-16) / heads
+    assert abs(float(layers[2][1].grad) - 0.2 / (1.0 + 1e-16) / 3) < 1e-15
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(PKG):
         for f in files:
