@@ -147,9 +147,9 @@ def test_sub_head_and_layer_reductions(built):
     means = [average_iter(h) for h in layers]
     ref = weighted_average_iter(means, imp)
     want = O.weighted_average_iter([O.average_iter([float(l.detach()) for l in h]) for h in layers], imp)
-    assert abs(float(ref) - want) < 1e-14
+    assert abs(ref.item() - want) < 1e-14
     total, per_layer = combine_iic_losses(layers, imp)
-    assert abs(float(total) - want) < 1e-14
+    assert abs(total.item() - want) < 1e-14
     assert torch.allclose(per_layer, torch.stack([m.detach() for m in means]), atol=1e-15)
     total.backward()                                   # d total / d loss = importance / (sum + 1e-16) / heads
     assert abs(float(layers[2][1].grad) - 0.2 / (1.0 + 1e-16) / 3) < 1e-15
