@@ -31,7 +31,7 @@ extern "C" {
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
 #define IIC_FLAG_NOT_SIMPLEX 2   /* dc2:utils/assertion.py:56-65 -> AssertionError on the host */
-#define IIC_FLAG_BAD_LABEL 4     /* dc2:utils/general.py class2one_hot `assert sset(seg, range(C))` -> AssertionError */
+#define IIC_FLAG_BAD_LABEL 4     /* dc2:utils/assertion.py:101-116 class2one_hot `assert sset(seg, range(C))` -> AssertionError */
 
 /* return code of the *_from_logits entry points for shapes their fused kernels do not cover */
 #define IIC_UNSUPPORTED 3

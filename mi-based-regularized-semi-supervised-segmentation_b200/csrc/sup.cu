@@ -1,7 +1,7 @@
 // Supervised branch of the udaiic iteration: one streaming pass each way (HBM-bound).
 //   loss : sup_loss = KL_div()(label_logits.softmax(1), class2one_hot(labeled_target.squeeze(1), C))
 //          semi_seg/epocher.py:165-166; dc2:deepclustering2/loss/kl_losses.py:107-126 (reduction "mean");
-//          dc2:deepclustering2/utils/general.py class2one_hot (a `long` one-hot; its sset assert -> BAD_LABEL flag)
+//          dc2:deepclustering2/utils/assertion.py:101-116 class2one_hot (a `long` one-hot; its sset assert -> BAD_LABEL flag)
 //   dice : the tensors UniversalDice.add appends for (label_logits.max(1)[1], labeled_target.squeeze(1))
 //          semi_seg/epocher.py:183-184; dc2:deepclustering2/meters2/individual_meters/general_dice_meter.py:41-95
 //          (_intersaction = sum(pred*target), _union = sum(pred+target) over the pixels of one sample)
