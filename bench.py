@@ -472,6 +472,39 @@ def run_b200(args):
         del f1, f2
     except Exception as e:  # noqa: BLE001
         extra["flip_error"] = f"{type(e).__name__}: {e}"
+    try:
+        # the same two terms with inputs rotating over 4 sets per graph replay (> 126 MB L2 in flight), i.e. from HBM.
+        # Written after the round's last GPU run: a failure here is recorded and leaves the entries above untouched.
+        NR = 4
+        gr = torch.Generator(device=dev).manual_seed(399 + rank)
+        rs = [(torch.randn(B, 4, H, W, device=dev, generator=gr) * 2).requires_grad_(True) for _ in range(NR)]
+        rt = [torch.randn(B, 4, H, W, device=dev, generator=gr) * 2 for _ in range(NR)]
+        rl = [torch.randint(0, 4, (B, H, W), device=dev, generator=gr) for _ in range(NR)]
+        rf = iic_b200.draw_flip_flags(4321, B).to(dev)
+
+        def sup_rot():
+            for a_, l_ in zip(rs, rl):
+                torch.autograd.grad(iic_b200.sup_kl_from_logits(a_, l_, return_dice=True)[0], (a_,))
+
+        def flip_uda_rot():
+            for a_, t_ in zip(rs, rt):
+                torch.autograd.grad(iic_b200.uda_from_logits(a_, t_, "mse", teacher_flips=rf), (a_,))
+
+        def flip_rot():
+            for t_ in rt:
+                iic_b200.flip_stack(t_, rf)
+
+        px_ = B * H * W
+        ms_a, ms_b, ms_c = timed_graph(sup_rot) / NR, timed_graph(flip_uda_rot) / NR, timed_graph(flip_rot) / NR
+        extra["section_8f_kernels_from_hbm"] = {
+            "what": "supervised KL + Dice (12*C+16 B/px), UDA through flips (20*C B/px) and flip_stack (8*C B/px) at "
+                    "(B,4,H,W), fwd+bwd, inputs rotating over 4 sets inside one graph replay so they come from HBM",
+            "supervised_ms": round(ms_a, 4), "supervised_hbm_frac": round(64.0 * px_ / (ms_a * 1e-3) / 1e9 / hbm_peak, 4),
+            "uda_flip_ms": round(ms_b, 4), "uda_flip_hbm_frac": round(80.0 * px_ / (ms_b * 1e-3) / 1e9 / hbm_peak, 4),
+            "flip_stack_ms": round(ms_c, 4), "flip_stack_hbm_frac": round(32.0 * px_ / (ms_c * 1e-3) / 1e9 / hbm_peak, 4)}
+        del rs, rt, rl
+    except Exception as e:  # noqa: BLE001
+        extra["section_8f_from_hbm_error"] = f"{type(e).__name__}: {e}"
 
     # ---- end to end through the public API with HOST buffers ----
     hx, hy, hgx, hgy = (t.detach().cpu().pin_memory() for t in sets[0])
