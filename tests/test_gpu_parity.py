@@ -517,3 +517,48 @@ def test_modules_are_parameter_free(iic):
         assert len(m.state_dict()) == 0
     assert repr(iic.IIDSegmentationSmallPathLoss(padding=3, patch_size=32)) == \
         "IIDSegmentationSmallPathLoss with patch_size=(32, 32) and padding=3."
+
+
+# ---------------------------------------------------------------------------------------------------
+# KEEP LAST IN THIS FILE.  Batched cluster heads (iic_b200.trainer): their outputs are channel-block views of one
+# tensor, i.e. inputs whose SAMPLE stride is not K*H*W.  The C ABI takes the strides, but no earlier GPU test passes
+# such views; this one was written after the round's last GPU run, hence non-strict xfail and last position.
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.xfail(strict=False, reason="first GPU run of strided (channel-block) inputs pending")
+def test_batched_heads_feed_strided_views(iic, cuda_device):
+    from iic_b200.trainer import ClusterHead, LocalClusterHead
+    torch.manual_seed(4)
+    S, K, B = 3, 10, 2
+    head = LocalClusterHead(16, num_clusters=K, num_subheads=S).to(cuda_device)
+    feats = torch.randn(2 * B, 16, 32, 48, device=cuda_device) * 2
+    crit = iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=1024)
+    for maps, fn in ((head(feats), crit), (head.logits(feats), crit.from_logits)):
+        for m in maps:
+            a, b = torch.chunk(m, 2, 0)
+            assert a.stride(0) == S * K * 32 * 48
+            a, b = a.detach().requires_grad_(True), b.detach().requires_grad_(True)   # detach keeps the strides
+            assert a.stride(0) == S * K * 32 * 48
+            loss = fn(a, b)
+            loss.backward()
+            pa, pb = a.detach().cpu().numpy(), b.detach().cpu().numpy()
+            if fn is not crit:
+                ol, oga, ogb = O.iid_segmentation_small_path_loss(O.softmax(pa).astype(np.float32),
+                                                                  O.softmax(pb).astype(np.float32), 1, 1024,
+                                                                  with_grads=True)
+                assert _loss_close(loss.item(), ol)
+            else:
+                ol, oga, ogb = O.iid_segmentation_small_path_loss(pa, pb, 1, 1024, with_grads=True)
+                assert _loss_close(loss.item(), ol)
+                assert relmax(a.grad.cpu().numpy(), oga) <= GRAD_RTOL and relmax(b.grad.cpu().numpy(), ogb) <= GRAD_RTOL
+    enc = ClusterHead(32, num_clusters=K, num_subheads=S).to(cuda_device)
+    rows = enc(torch.randn(2 * 16, 32, 7, 7, device=cuda_device))
+    for r in rows:
+        a, b = torch.chunk(r, 2, 0)
+        assert a.stride(0) == S * K
+        a, b = a.detach().requires_grad_(True), b.detach().requires_grad_(True)
+        l1, _, _ = iic.IIDLoss()(a, b)
+        l1.backward()
+        o1, _, _ = O.iid_loss(a.detach().cpu().numpy(), b.detach().cpu().numpy())
+        ox, oy = O.iid_loss_grads(a.detach().cpu().numpy(), b.detach().cpu().numpy())
+        assert _loss_close(l1.item(), o1)
+        assert relmax(a.grad.cpu().numpy(), ox) <= GRAD_RTOL and relmax(b.grad.cpu().numpy(), oy) <= GRAD_RTOL

@@ -155,6 +155,42 @@ def test_sub_head_and_layer_reductions(built):
     assert abs(float(layers[2][1].grad) - 0.2 / (1.0 + 1e-16) / 3) < 1e-15
 
 
+def test_batched_cluster_heads_match_reference(built):
+    """iic_b200.trainer heads load the reference heads' state_dict (strict) and give the same maps and gradients
+    (contrastyou/trainer/_utils.py:96-168, loaded by path in the build container)."""
+    import importlib.util
+    path = "/root/reference/contrastyou/trainer/_utils.py"
+    if not os.path.isfile(path):
+        pytest.skip("/root/reference not mounted (GPU box)")
+    spec = importlib.util.spec_from_file_location("_ref_trainer_utils", path)
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    from iic_b200.trainer import ClusterHead, LocalClusterHead
+    torch.manual_seed(0)
+    for kw in (dict(head_type="linear", num_clusters=10, num_subheads=5, T=1, normalize=False),
+               dict(head_type="linear", num_clusters=7, num_subheads=3, T=0.5, normalize=True),
+               dict(head_type="mlp", num_clusters=6, num_subheads=2, T=1, normalize=False)):
+        for ref_cls, cls, shape in ((ref.LocalClusterHead, LocalClusterHead, (4, 16, 12, 10)),
+                                    (ref.ClusterHead, ClusterHead, (6, 16, 5, 5))):
+            r, m = ref_cls(16, **kw).double(), cls(16, **kw).double()
+            m.load_state_dict(r.state_dict(), strict=True)
+            f1 = torch.randn(*shape, dtype=torch.float64, requires_grad=True)
+            f2 = f1.detach().clone().requires_grad_(True)
+            o1, o2 = r(f1), m(f2)
+            assert len(o1) == len(o2) == kw["num_subheads"]
+            assert max((a - b).abs().max().item() for a, b in zip(o1, o2)) < 1e-14
+            w = [torch.randn_like(o) for o in o1]
+            sum((a * c).sum() for a, c in zip(o1, w)).backward()
+            sum((a * c).sum() for a, c in zip(o2, w)).backward()
+            assert (f1.grad - f2.grad).abs().max().item() < 1e-13
+            assert max((p.grad - q.grad).abs().max().item() for p, q in zip(r.parameters(), m.parameters())) < 1e-12
+            lg = m.logits(f2.detach())
+            assert all(torch.allclose(torch.softmax((torch.nn.functional.normalize(z, p=2, dim=1) if kw["normalize"]
+                                                     else z) / kw["T"], 1), o.detach(), atol=1e-14)
+                       for z, o in zip(lg, o2)) or kw["normalize"]
+            assert all(o.stride(-1) == 1 for o in o2)          # what the loss kernels require of their inputs
+
+
 def test_product_never_imports_oracle():
     for dirpath, _, files in os.walk(PKG):
         for f in files:
