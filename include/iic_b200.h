@@ -26,12 +26,13 @@
 extern "C" {
 #endif
 
-#define IIC_B200_ABI_VERSION 5
+#define IIC_B200_ABI_VERSION 6
 
 /* flag bits written (OR-ed) into the int* `flags` words by the kernels */
 #define IIC_FLAG_NAN_LOSS 1      /* iic_loss.py:147-148,184-185 -> RuntimeError on the host  */
 #define IIC_FLAG_NOT_SIMPLEX 2   /* dc2:utils/assertion.py:56-65 -> AssertionError on the host */
 #define IIC_FLAG_BAD_LABEL 4     /* dc2:utils/assertion.py:101-116 class2one_hot `assert sset(seg, range(C))` -> AssertionError */
+#define IIC_FLAG_XCHG_TIMEOUT 8  /* multi-GPU: a peer never published its joints within xchg_timeout_ms -> RuntimeError */
 
 /* return code of the *_from_logits entry points for shapes their fused kernels do not cover */
 #define IIC_UNSUPPORTED 3
@@ -40,6 +41,13 @@ int iic_b200_abi_version(void);
 const char* iic_b200_last_error(void);
 /* number of SMs of `device` (148 on B200); <0 on error */
 int iic_b200_sm_count(int device);
+/* Dispatch switches.  The library reads IIC_B200_* environment variables ONCE (at first use) as defaults; after that
+ * only these calls change them.  Names: "no_tma", "no_tc", "no_tc10", "no_fast" (skip a kernel family), "tcp_p1",
+ * "tcrb_p1", "tc10_force" (force a tensor-core kernel outside the shapes it is normally chosen for), "no_fused_epilogue",
+ * "xchg_timeout_ms".  Results are the same whatever the switches; only the kernel that runs changes (the parity tests
+ * use them to reach every dispatch branch).  set: 0 = ok; get: the value, -1 for an unknown name. */
+int iic_b200_set_option(const char* name, int value);
+int iic_b200_get_option(const char* name);
 
 /* ------------------------------------------------------------------------------------------------
  * simplex assertion: flags |= IIC_FLAG_NOT_SIMPLEX unless |sum_c t[o,c,i] - 1| <= 2e-4 everywhere
@@ -78,7 +86,27 @@ int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_
                     int patch_h, int patch_w, int step_h, int step_w,
                     double* J_out, void* workspace, size_t workspace_bytes, int* flags, void* stream);
 
-/* number of floats in each of the Wx / Wy coefficient buffers written by iic_local_epilogue */
+/* iic_local_joint without the cross-CTA reduction: the joint kernel's per-CTA partial sums stay in `workspace`
+ * (same size as for iic_local_joint) and *info_host says how they are laid out; iic_finish (below) reduces them -- for
+ * many loss terms at once -- and runs the epilogues.  Everything else as iic_local_joint. */
+typedef struct iic_slot_info {
+  int layout;              /* opaque: pass through to iic_finish_item */
+  int n_slots;             /* per-CTA slots per patch */
+  long long slot_stride;   /* floats between slots */
+  int nb;
+} iic_slot_info;
+int iic_local_joint_partials(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                             const float* y, long long y_sn, long long y_sc, long long y_sh,
+                             const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                             int B, int K, int H, int W, int pad,
+                             int patch_h, int patch_w, int step_h, int step_w,
+                             void* workspace, size_t workspace_bytes, int* flags,
+                             iic_slot_info* info_host, void* stream);
+
+/* number of floats in each of the Wx / Wy buffers: the coefficient tensor [patch][cin][tap][K rounded up to 4] written
+ * by iic_local_epilogue, followed (for the (K, pad) the tensor-core backward kernels cover, one patch) by scratch in
+ * which iic_local_backward lays the coefficients out in MMA operand order.  The caller owns both buffers from the
+ * epilogue to the end of the backward; there is no hidden allocation inside the library. */
 size_t iic_local_coeff_floats(int K, int pad, int n_patches);
 
 /* From the (all-reduced) joint: min-shift, per-displacement normalise, symmetrise, marginals, entropy
@@ -97,13 +125,14 @@ int iic_local_epilogue(const double* J, int K, int pad, int n_patches, double la
  *   gx[n,i,a,b] (+)= g * mask * sum_{d,j} dL/dJ[d,i,j] * (mask*y)[n,j,a-dy+pad,b-dx+pad]
  *   gy[n,j,u,v] (+)= g * mask * sum_{d,i} dL/dJ[d,i,j] * (mask*x)[n,i,u+dy-pad,v+dx-pad]
  * g = *grad_loss (device scalar; NULL means 1).  gx/gy are dense NCHW (B,K,H,W); with more than one
- * patch the caller zero-fills them first and every patch accumulates. */
+ * patch the caller zero-fills them first and every patch accumulates.  Wx / Wy are the buffers of iic_local_epilogue
+ * (iic_local_coeff_floats floats each); their scratch tail may be overwritten. */
 int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long x_sh,
                        const float* y, long long y_sn, long long y_sc, long long y_sh,
                        const float* mask, long long m_sn, long long m_sc, long long m_sh,
                        int B, int K, int H, int W, int pad,
                        int patch_h, int patch_w, int step_h, int step_w,
-                       const float* Wx, const float* Wy, const float* grad_loss,
+                       float* Wx, float* Wy, const float* grad_loss,
                        float* gx, float* gy, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
@@ -114,12 +143,14 @@ int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long
  * and the backward returns the gradients with respect to the logits.  Between the two calls the caller
  * runs iic_local_epilogue exactly as for the probability path.  Covered shapes: padding 1, K == 10,
  * W % 4 == 0, W <= 248, 16-byte aligned rows; anything else returns IIC_UNSUPPORTED (apply the softmax
- * and use the probability entry points).  workspace: iic_b200_sm_count() * 9*K*K floats.
+ * and use the probability entry points).  workspace: iic_b200_sm_count() * 9*K*K floats.  info_host (nullable): when
+ * given, the per-CTA slots are left in `workspace` for iic_finish and described there; J_out is then unused.
  * ---------------------------------------------------------------------------------------------- */
 int iic_local_joint_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
                                 const float* ly, long long y_sn, long long y_sc, long long y_sh,
                                 int B, int K, int H, int W, int pad, float inv_temperature,
-                                double* J_out, void* workspace, size_t workspace_bytes, void* stream);
+                                double* J_out, void* workspace, size_t workspace_bytes,
+                                iic_slot_info* info_host, void* stream);
 int iic_local_backward_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
                                    const float* ly, long long y_sn, long long y_sc, long long y_sh,
                                    int B, int K, int H, int W, int pad, float inv_temperature,
@@ -148,6 +179,48 @@ int iic_global_backward(const float* x, long long x_sn, const float* y, long lon
                         long long N, int K, const double* J, double lamb, int symmetric,
                         const float* g_loss, const float* g_no_lamb, const float* gP,
                         float* gx, float* gy, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * iic_finish: ONE launch between the joint kernels and the backward kernels of one or many IIC terms -- the (layer,
+ * sub-head) calls of one iteration, semi_seg/epocher.py:249-284.  It reduces the per-CTA slots of every local term
+ * (iic_local_joint_partials) into its joint in fp64 in a fixed order, computes the joints of the global terms straight
+ * from their (N, K) rows (iic_loss.py:88-89, both simplex assertions fused), and -- multi-GPU -- sums ALL joints over the
+ * ranks with ONE exchange over the peer buffers of iic_xchg_create (same protocol and bit-identical results as
+ * iic_xchg_allreduce).  With want_epilogue it then runs every term's epilogue (iic_local_epilogue /
+ * iic_global_epilogue arithmetic) in the same launch when all K <= 32, else as one extra launch per term.
+ *   J_all        E_total doubles: the terms' joints back to back in batch order (term i: n_patches*T*T*K*K or K*K);
+ *                kept by the caller for the global terms' backward (iic_global_backward's J)
+ *   workspace    >= iic_finish_workspace_bytes(), zero-initialised once by the caller, one per stream
+ *   xchg_bufs_host, rank, world, xchg_capacity   as for iic_xchg_allreduce; world == 1 means no exchange
+ * At most 32 terms per call.
+ * ---------------------------------------------------------------------------------------------- */
+#define IIC_ITEM_LOCAL 0
+#define IIC_ITEM_GLOBAL_ROWS 1
+typedef struct iic_finish_item {
+  int kind;                       /* IIC_ITEM_LOCAL or IIC_ITEM_GLOBAL_ROWS */
+  int K;
+  double lamda;                   /* lamda of IIDSegmentationLoss / lamb of IIDLoss */
+  /* local term: the slots left by iic_local_joint_partials and its geometry */
+  const float* slots;
+  int layout, n_slots, nb;
+  long long slot_stride;
+  int pad, n_patches;
+  void* epilogue_workspace;       /* iic_local_epilogue_workspace_bytes; only used when K > 32 (may be NULL otherwise) */
+  /* global term: the rows */
+  const float* x; long long x_sn;
+  const float* y; long long y_sn;
+  long long N;
+  int symmetric, check_simplex;
+  /* outputs: local loss_out[1], Wx, Wy (iic_local_coeff_floats each); global loss_out[2], P_out (K,K; nullable) */
+  float* loss_out;
+  float* Wx;
+  float* Wy;
+  float* P_out;
+} iic_finish_item;
+size_t iic_finish_workspace_bytes(void);
+int iic_finish(const iic_finish_item* items_host, int n_items, double* J_all, long long E_total, int* flags,
+               void* workspace, void* const* xchg_bufs_host, int rank, int world, long long xchg_capacity,
+               int want_epilogue, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * UDA consistency on (outer, C, inner) contiguous maps.  kind 0 = torch.nn.MSELoss() mean over all
@@ -226,7 +299,9 @@ int iic_uda_flip_backward(const float* prob, const float* target, const unsigned
  *   iic_xchg_import      map a peer's buffer from its handle
  *   iic_xchg_release     cudaFree (imported = 0) or cudaIpcCloseMemHandle (imported = 1)
  *   iic_xchg_allreduce   J[0..E) <- sum over ranks, in place; bufs_host[r] = this process's pointer to rank
- *                        r's buffer (host array of `world` device pointers)
+ *                        r's buffer (host array of `world` device pointers); flags (nullable) receives
+ *                        IIC_FLAG_XCHG_TIMEOUT when a peer does not arrive within the xchg_timeout_ms option
+ *                        (the wait is bounded but long: a slow peer is not an error)
  * ---------------------------------------------------------------------------------------------- */
 size_t iic_xchg_buffer_bytes(int world, long long capacity);
 int iic_xchg_create(int world, long long capacity, void** buf_out);
@@ -234,7 +309,7 @@ int iic_xchg_export(void* buf, void* handle64_host);
 int iic_xchg_import(const void* handle64_host, void** peer_out);
 int iic_xchg_release(void* buf, int imported);
 int iic_xchg_allreduce(double* J, long long E, long long capacity, void* const* bufs_host, int rank,
-                       int world, void* stream);
+                       int world, int* flags, void* stream);
 
 #ifdef __cplusplus
 }

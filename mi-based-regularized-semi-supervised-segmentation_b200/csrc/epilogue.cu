@@ -350,8 +350,15 @@ static int global_grid(int device, long long N, long long* rows_per_cta) {
 using namespace iic;
 
 extern "C" size_t iic_local_coeff_floats(int K, int pad, int n_patches) {
-  const int T = 2 * pad + 1, Kp = (K + 3) & ~3;
-  return (size_t)n_patches * K * T * T * Kp;
+  if (K <= 0 || pad < 0 || n_patches <= 0) return 0;
+  size_t img = 0;
+  if (n_patches == 1) {
+    img = local_bwd_tc_image_bytes(K, pad);
+    const size_t rb = local_bwd_tcrb_image_bytes(K, pad);
+    if (rb > img) img = rb;
+  }
+  if (img == 0) return local_coeff_base_floats(K, pad, n_patches);
+  return local_coeff_image_offset(K, pad, n_patches) + (img + 3) / 4;
 }
 
 extern "C" size_t iic_local_epilogue_workspace_bytes(int K, int pad, int n_patches) {

@@ -167,11 +167,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) local_bwd_kernel(const LocalBw
 template <int T, int OCB>
 static int launch_bwd(const LocalBwdParams& P, dim3 grid, size_t smem, cudaStream_t st) {
   auto kern = local_bwd_kernel<T, OCB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(kern), (int)(200 * 1024)));
   kern<<<grid, BWD_WARPS * 32, smem, st>>>(P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -208,10 +204,10 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
                        const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
                        int from_logits, float inv_temp, cudaStream_t st);
 int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
-                     long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                     long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
                      const float* grad_loss, float* gx, float* gy, cudaStream_t st);
 int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
-                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
                        const float* grad_loss, float* gx, float* gy, cudaStream_t st);
 int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
@@ -224,7 +220,7 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
                                   const float* mask, long long m_sn, long long m_sc, long long m_sh,
                                   int B, int K, int H, int W, int pad,
                                   int patch_h, int patch_w, int step_h, int step_w,
-                                  const float* Wx, const float* Wy, const float* grad_loss,
+                                  float* Wx, float* Wy, const float* grad_loss,
                                   float* gx, float* gy, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IIC_REQUIRE(x && y && Wx && Wy && gx && gy, "iic_local_backward: null pointer");
@@ -239,14 +235,14 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
   IIC_REQUIRE(sms > 0, "iic_local_backward: no device");
 
   // fast path: one patch, no mask, TMA-describable rows, small window (local_bwd_tma.cu)
-  if (n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
+  if (n_patches == 1 && mask == nullptr && !options().no_tma) {
     // wide cluster heads (K = 128): tcgen05 3xTF32 sweeps (local_bwd_tc.cu)
-    if (!getenv("IIC_B200_NO_TC")) {
+    if (!options().no_tc) {
       const int rc_tc = local_bwd_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                          gx, gy, st);
       if (rc_tc >= 0) return rc_tc;
       // 10 clusters, padding 1 (config 2): row-block tensor-core sweeps with the leftover-slot MMA (local_bwd_tcrb10.cu)
-      if (!getenv("IIC_B200_NO_TC10")) {
+      if (!options().no_tc10) {
         const int rc_10 = local_bwd_tcrb10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                                gx, gy, st);
         if (rc_10 >= 0) return rc_10;
@@ -259,7 +255,7 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
         if (rc_rb >= 0) return rc_rb;
       }
     }
-    int rc = getenv("IIC_B200_NO_FAST") ? -1
+    int rc = options().no_fast ? -1
                  : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
                                       grad_loss, gx, gy, sms, 0, 1.f, st);
     if (rc < 0)

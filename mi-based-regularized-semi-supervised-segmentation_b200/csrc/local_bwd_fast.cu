@@ -287,11 +287,7 @@ template <int KB, int T, int NWARPS, int STAGES, int CB, bool FROM_LOGITS>
 static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const BwdFastParams& P, dim3 grid,
                            size_t smem, cudaStream_t st) {
   auto kern = local_bwd_fast_kernel<KB, T, NWARPS, STAGES, CB, FROM_LOGITS>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(kern), (int)(226 * 1024)));
   kern<<<grid, (NWARPS + 1) * 32, smem, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;

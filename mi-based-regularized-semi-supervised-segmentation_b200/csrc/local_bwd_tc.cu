@@ -295,30 +295,15 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int H, int W, l
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// per-device scratch for the two weight images (2 x 1.18 MB), allocated on first use -- but never while the stream
-// is being captured into a CUDA graph (cudaMalloc would invalidate the capture): the caller then takes the FFMA2 path
-static float* weight_scratch(int device, cudaStream_t st) {
-  static float* buf[64] = {nullptr};
-  if (device < 0 || device >= 64) return nullptr;
-  if (!buf[device]) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    if (cudaMalloc(&buf[device], 2 * (size_t)NSL * 9 * W_TILE) != cudaSuccess) {
-      cudaGetLastError();
-      buf[device] = nullptr;
-    }
-  }
-  return buf[device];
-}
-
 }  // namespace bwdtc
+
+size_t local_bwd_tc_image_bytes(int K, int pad) {
+  return (K == bwdtc::KC && pad == 1) ? (size_t)bwdtc::NSL * 9 * bwdtc::W_TILE : 0;
+}
 
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
 int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
-                     long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                     long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
                      const float* grad_loss, float* gx, float* gy, cudaStream_t st) {
   using namespace bwdtc;
   if (K != KC || pad != 1 || W % 4 != 0 || W > MAXW || W < 8) return -1;
@@ -328,22 +313,17 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
   const int device = current_device();
   const int sms = sm_count_cached(device);
   if (sms <= 0) return -1;
-  float* img = weight_scratch(device, st);
-  if (!img) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  // the weight image lives in the tail of the caller's coefficient buffer (common.cuh)
+  float* img_x = Wx + local_coeff_image_offset(K, pad, 1);
+  float* img_y = Wy + local_coeff_image_offset(K, pad, 1);
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tc_kernel), (int)(SMEM_BYTES)));
   const int n_items = B * ((H + 1) / 2);
   const int grid = n_items < sms ? n_items : sms;
   const int wthreads = NSL * 9 * KC;
-  float* img_x = img;
-  float* img_y = img + (size_t)NSL * 9 * (W_TILE / 4);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y);
   IIC_CHECK_CUDA(cudaGetLastError());
-  const int dbg = getenv("IIC_TC_DBG") ? atoi(getenv("IIC_TC_DBG")) : 0;
+  const int dbg = tc::bringup_env("IIC_TC_DBG", 0);
   Params Pgx{B, H, W, n_items, img_x, grad_loss, gx, dbg};     // dL/dx from y
   local_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(my, Pgx);
   Params Pgy{B, H, W, n_items, img_y, grad_loss, gy, dbg};     // dL/dy from x

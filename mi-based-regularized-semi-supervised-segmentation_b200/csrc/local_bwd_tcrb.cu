@@ -323,31 +323,9 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-constexpr size_t SCRATCH_BYTES = 2 * 3 * 75264 + 4096;     // two weight images, K <= 24, T <= 7
-static float* weight_scratch(int device, cudaStream_t st) {
-  static float* buf[64] = {nullptr};
-  if (device < 0 || device >= 64) return nullptr;
-  if (!buf[device]) {
-    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
-    if (cudaStreamIsCapturing(st, &cs) != cudaSuccess || cs != cudaStreamCaptureStatusNone) {
-      cudaGetLastError();
-      return nullptr;
-    }
-    if (cudaMalloc(&buf[device], SCRATCH_BYTES) != cudaSuccess) {
-      cudaGetLastError();
-      buf[device] = nullptr;
-    }
-  }
-  return buf[device];
-}
-
 template <int T>
 static int launch(const CUtensorMap& m, const Params& P, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_bwd_tcrb_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb_kernel<T>), (int)(SMEM_LIMIT)));
   local_bwd_tcrb_kernel<T><<<grid, NTHREADS, smem, st>>>(m, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -355,9 +333,15 @@ static int launch(const CUtensorMap& m, const Params& P, int grid, size_t smem, 
 
 }  // namespace bwdrb
 
+size_t local_bwd_tcrb_image_bytes(int K, int pad) {
+  if (K < 16 || K > 24 || (pad != 1 && pad != 3)) return 0;
+  const int T = 2 * pad + 1, KP = (K + 7) & ~7;
+  return (size_t)(KP / bwdrb::SL) * 64 * T * T * KP;
+}
+
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
 int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
-                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                       long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
                        const float* grad_loss, float* gx, float* gy, cudaStream_t st) {
   using namespace bwdrb;
   if (K < 16 || K > 24 || (pad != 1 && pad != 3) || W % 4 != 0 || W < 8) return -1;
@@ -380,23 +364,21 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
   while (nraw < NRAW_MAX && spare >= (long long)na * A_ROW + (long long)(nraw + 1) * RAW_MAX) ++nraw;
   while (na < NA_MAX && spare >= (long long)(na + 1) * A_ROW + (long long)nraw * RAW_MAX) ++na;
   const size_t smem = (size_t)2 * ((wslice + 127) & ~127) + (size_t)na * A_ROW + (size_t)nraw * RAW_MAX + 1024;
-  if ((size_t)2 * NS * wslice + 4096 > SCRATCH_BYTES) return -1;
   CUtensorMap mx, my;
   if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, PW + 8)) return -1;
   if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh, PW + 8)) return -1;
   const int device = current_device();
   const int sms = sm_count_cached(device);
   if (sms <= 0) return -1;
-  float* img = weight_scratch(device, st);
-  if (!img) return -1;
   const int nblk = (H + R - 1) / R;
   const int n_items = B * nblk * npanel;
   // 3 x 3 window: the FFMA2 kernel is as fast unless there are enough row blocks to keep every SM busy (measured:
   // (32,20,224,224) 0.32 ms vs 0.42 ms, (8,20,112,112) no gain)
-  if (pad == 1 && n_items < 2 * sms && !getenv("IIC_B200_TCRB_P1")) return -1;
+  if (pad == 1 && n_items < 2 * sms && !options().tcrb_p1) return -1;
   const int grid = n_items < sms ? n_items : sms;
-  float* img_x = img;
-  float* img_y = img + ((size_t)NS * wslice + 1023) / 1024 * 256;      // 1 KB aligned second image
+  // the weight image lives in the tail of the caller's coefficient buffer (common.cuh)
+  float* img_x = Wx + local_coeff_image_offset(K, pad, 1);
+  float* img_y = Wy + local_coeff_image_offset(K, pad, 1);
   const int wthreads = NS * T * T * KP;
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x, K, Kp4, KP, NS, T);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y, K, Kp4, KP, NS, T);

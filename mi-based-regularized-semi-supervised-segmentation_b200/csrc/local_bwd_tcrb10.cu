@@ -366,15 +366,11 @@ int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long lo
   const int device = current_device();
   const int sms = sm_count_cached(device);
   if (sms <= 0) return -1;
-  if ((long long)B * H < 8LL * sms && !getenv("IIC_B200_TC10_FORCE")) return -1;   // too few rows to fill the SMs: FFMA2 is faster
+  if ((long long)B * H < 8LL * sms && !options().tc10_force) return -1;   // too few rows to fill the SMs: FFMA2 is faster
   CUtensorMap mx, my;
   if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh)) return -1;
   if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh)) return -1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_bwd_tcrb10_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10_kernel), (int)(SMEM_BYTES)));
   const int Kp4 = (K + 3) & ~3;
   Params P{B, H, W, K, {Wx, Wy}, Kp4, grad_loss, {gx, gy}};
   // one launch, two sweeps per CTA: dL/dx from y (sweep 0), then dL/dy from x (sweep 1)

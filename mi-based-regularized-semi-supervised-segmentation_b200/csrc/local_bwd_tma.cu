@@ -191,11 +191,7 @@ template <int T, int OCB>
 static int launch_bwd_tma(const CUtensorMap& mx, const CUtensorMap& my, const BwdTmaParams& P, int grid,
                           size_t smem, cudaStream_t st) {
   auto kern = local_bwd_tma_kernel<T, OCB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(kern), (int)(226 * 1024)));
   kern<<<grid, BT_WARPS * 32, smem, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;

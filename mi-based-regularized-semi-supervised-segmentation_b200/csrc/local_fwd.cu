@@ -340,11 +340,7 @@ static bool make_fwd_plan(int device, int B, int K, const PatchGrid& g, int pad,
 template <int T, int IT, int JT, int DYB>
 static int launch_fwd(const LocalFwdParams& P, dim3 grid, int nthreads, size_t smem, cudaStream_t st) {
   auto kern = local_joint_kernel<T, IT, JT, DYB>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(kern), (int)(200 * 1024)));
   kern<<<grid, nthreads, smem, st>>>(P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -396,18 +392,20 @@ int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long
 size_t local_joint_tcp_slot_floats(int K, int pad);
 int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                         long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial,
-                        size_t partial_floats, double* J_out, cudaStream_t st);
+                        size_t partial_floats, double* J_out, SlotInfo* info, cudaStream_t st);
 }
 
-extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
-                               const float* y, long long y_sn, long long y_sc, long long y_sh,
-                               const float* mask, long long m_sn, long long m_sc, long long m_sh,
-                               int B, int K, int H, int W, int pad,
-                               int patch_h, int patch_w, int step_h, int step_w,
-                               double* J_out, void* workspace, size_t workspace_bytes, int* flags,
-                               void* stream) {
+// info == nullptr: the per-CTA slots are reduced into J_out (fp64, fixed order) by a second launch.
+// info != nullptr: the slots are left in `workspace` and described in *info (for iic_finish); J_out is unused.
+static int local_joint_impl(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                            const float* y, long long y_sn, long long y_sc, long long y_sh,
+                            const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                            int B, int K, int H, int W, int pad,
+                            int patch_h, int patch_w, int step_h, int step_w,
+                            double* J_out, void* workspace, size_t workspace_bytes, int* flags,
+                            SlotInfo* info, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  IIC_REQUIRE(x && y && J_out, "iic_local_joint: null pointer");
+  IIC_REQUIRE(x && y && (J_out || info), "iic_local_joint: null pointer");
   IIC_REQUIRE(!flags || x_sh == W, "iic_local_joint: the fused simplex assertion needs dense rows (x_sh == W)");
   IIC_REQUIRE(B > 0 && K > 0, "iic_local_joint: empty batch or channel dimension (B=%d K=%d)", B, K);
   IIC_REQUIRE(pad >= 0 && pad <= 7, "iic_local_joint: padding %d unsupported (0..7)", pad);
@@ -430,34 +428,35 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   };
 
   // fast path: one patch, no mask, TMA-describable rows -> pipelined FFMA2 kernel (local_fwd_tma.cu)
-  if (pl.n_patches == 1 && mask == nullptr && !getenv("IIC_B200_NO_TMA")) {
+  if (pl.n_patches == 1 && mask == nullptr && !options().no_tma) {
     int ncta = 0, checked = 0;
     // the reference's default cluster count (16 <= K <= 24), padding 3: packed tensor-core joint (local_fwd_tcp.cu);
     // padding 1 stays on the FFMA2 kernel unless IIC_B200_TCP_P1 is set
-    if (!getenv("IIC_B200_NO_TC") && (pad == 3 || getenv("IIC_B200_TCP_P1"))) {
+    if (!options().no_tc && (pad == 3 || options().tcp_p1)) {
       const int rc_p = local_joint_tcp_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
-                                           workspace_bytes / sizeof(float), J_out, st);
+                                           workspace_bytes / sizeof(float), J_out, info, st);
       if (rc_p > 0) return rc_p;
       if (rc_p == 0) return simplex_pass();
     }
     // wide cluster heads (K = 128): tcgen05 3xTF32 contraction (local_fwd_tc.cu)
-    if (!getenv("IIC_B200_NO_TC")) {
+    if (!options().no_tc) {
       const int rc_tc = local_joint_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
                                            pl.slots_per_patch, &ncta, st);
       if (rc_tc > 0) return rc_tc;
       if (rc_tc == 0) {
         if (int e = simplex_pass()) return e;
+        if (info) { *info = SlotInfo{SLOT_TC128, ncta, (long long)E, 0}; return 0; }
         dim3 rgrid((unsigned)((E + 31) / 32), 1);
         reduce_partials_kernel<true><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
         IIC_CHECK_CUDA(cudaGetLastError());
         return 0;
       }
     }
-    int rc = getenv("IIC_B200_NO_FAST") ? -1
+    int rc = options().no_fast ? -1
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                         (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, 0, 1.f, st);
     if (rc == 0 && checked) flags = nullptr;       // done inside the joint kernel
-    if (rc < 0 && !getenv("IIC_B200_NO_FAST"))
+    if (rc < 0 && !options().no_fast)
       rc = local_joint_fast7_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace,
                                  pl.slots_per_patch, &ncta, st);
     if (rc < 0)
@@ -466,6 +465,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
     if (rc > 0) return rc;
     if (rc == 0) {
       if (int e = simplex_pass()) return e;
+      if (info) { *info = SlotInfo{SLOT_STD, ncta, (long long)E, 0}; return 0; }
       dim3 rgrid((unsigned)((E + 31) / 32), 1);
       reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
       IIC_CHECK_CUDA(cudaGetLastError());
@@ -522,6 +522,7 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
       if (rc) return rc;
     }
   }
+  if (info) { *info = SlotInfo{SLOT_STD, pl.ctas_per_patch, (long long)E, 0}; return 0; }
   {
     dim3 rgrid((unsigned)((E + 31) / 32), pl.n_patches);
     reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, pl.ctas_per_patch,
@@ -531,14 +532,46 @@ extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, l
   return 0;
 }
 
+extern "C" int iic_local_joint(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                               const float* y, long long y_sn, long long y_sc, long long y_sh,
+                               const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                               int B, int K, int H, int W, int pad,
+                               int patch_h, int patch_w, int step_h, int step_w,
+                               double* J_out, void* workspace, size_t workspace_bytes, int* flags,
+                               void* stream) {
+  IIC_REQUIRE(J_out, "iic_local_joint: null pointer");
+  return local_joint_impl(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, mask, m_sn, m_sc, m_sh, B, K, H, W, pad, patch_h,
+                          patch_w, step_h, step_w, J_out, workspace, workspace_bytes, flags, nullptr, stream);
+}
+
+extern "C" int iic_local_joint_partials(const float* x, long long x_sn, long long x_sc, long long x_sh,
+                                        const float* y, long long y_sn, long long y_sc, long long y_sh,
+                                        const float* mask, long long m_sn, long long m_sc, long long m_sh,
+                                        int B, int K, int H, int W, int pad,
+                                        int patch_h, int patch_w, int step_h, int step_w,
+                                        void* workspace, size_t workspace_bytes, int* flags,
+                                        iic_slot_info* info_host, void* stream) {
+  IIC_REQUIRE(info_host, "iic_local_joint_partials: null pointer");
+  SlotInfo info{SLOT_STD, 0, 0, 0};
+  const int rc = local_joint_impl(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, mask, m_sn, m_sc, m_sh, B, K, H, W, pad,
+                                  patch_h, patch_w, step_h, step_w, nullptr, workspace, workspace_bytes, flags, &info,
+                                  stream);
+  if (rc) return rc;
+  info_host->layout = info.layout;
+  info_host->n_slots = info.n_slots;
+  info_host->slot_stride = info.slot_stride;
+  info_host->nb = info.nb;
+  return 0;
+}
+
 // Fused cluster-head softmax + local joint: only the shapes the fast kernel covers
 extern "C" int iic_local_joint_from_logits(const float* lx, long long x_sn, long long x_sc, long long x_sh,
                                            const float* ly, long long y_sn, long long y_sc, long long y_sh,
                                            int B, int K, int H, int W, int pad, float inv_temperature,
                                            double* J_out, void* workspace, size_t workspace_bytes,
-                                           void* stream) {
+                                           iic_slot_info* info_host, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
-  IIC_REQUIRE(lx && ly && J_out && workspace, "iic_local_joint_from_logits: null pointer");
+  IIC_REQUIRE(lx && ly && (J_out || info_host) && workspace, "iic_local_joint_from_logits: null pointer");
   IIC_REQUIRE(B > 0 && K > 0 && H > 0 && W > 0, "iic_local_joint_from_logits: empty input");
   const int device = current_device();
   const int sms = sm_count_cached(device);
@@ -556,6 +589,13 @@ extern "C" int iic_local_joint_from_logits(const float* lx, long long x_sn, long
     return IIC_UNSUPPORTED;
   }
   if (rc > 0) return rc;
+  if (info_host) {          // leave the slots for iic_finish
+    info_host->layout = SLOT_STD;
+    info_host->n_slots = ncta;
+    info_host->slot_stride = (long long)E;
+    info_host->nb = 0;
+    return 0;
+  }
   dim3 rgrid((unsigned)((E + 31) / 32), 1);
   reduce_partials_kernel<false><<<rgrid, RED_GROUPS * 32, 0, st>>>((const float*)workspace, ncta, (long long)E, J_out);
   IIC_CHECK_CUDA(cudaGetLastError());

@@ -239,12 +239,7 @@ int local_joint_fast7_try(const float* x, long long x_sn, long long x_sc, long l
   if (gx < 1) gx = 1;
   if (gx > items) gx = (int)items;
   *ncta = gx;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_fast7_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(STAGES * STAGE_BYTES)));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_joint_fast7_kernel), (int)((int)(STAGES * STAGE_BYTES))));
   local_joint_fast7_kernel<<<dim3(gx, ny), NTHREADS, STAGES * STAGE_BYTES, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;

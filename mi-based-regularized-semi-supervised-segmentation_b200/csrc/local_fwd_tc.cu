@@ -313,13 +313,9 @@ int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long
   if (gx > max_ctas) gx = max_ctas;
   if (gx > nkb) gx = (int)nkb;
   if (gx < 1) gx = 1;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
-  Params P{B, H, W, W / PXB, partial, getenv("IIC_TC_SEG") ? atoi(getenv("IIC_TC_SEG")) : SEG_KB_DEFAULT,
-           getenv("IIC_TC_DBG") ? atoi(getenv("IIC_TC_DBG")) : 0};
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_joint_tc_kernel), (int)(SMEM_BYTES)));
+  Params P{B, H, W, W / PXB, partial, tc::bringup_env("IIC_TC_SEG", SEG_KB_DEFAULT),
+           tc::bringup_env("IIC_TC_DBG", 0)};
   local_joint_tc_kernel<<<dim3(gx, 3), NTHREADS, SMEM_BYTES, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   *ncta = gx;

@@ -56,10 +56,8 @@ struct Params {
   float* partial;               // [gridDim.x][slot_floats]
 };
 
-// slot element of (row tile mt, accumulator row m, accumulator column c): chunks of 8 columns, float4-interleaved over rows
-__host__ __device__ inline size_t slot_index(int mt, int m, int c, int nb) {
-  return ((((size_t)mt * (nb / 8) + c / 8) * 2 + (c % 8) / 4) * 128 + m) * 4 + (c % 4);
-}
+using iic::packed_slot_index;
+__host__ __device__ inline size_t slot_index(int mt, int m, int c, int nb) { return packed_slot_index(mt, m, c, nb); }
 
 template <int T>
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -316,11 +314,7 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, i
 
 template <int T>
 static int launch(const CUtensorMap& mx, const CUtensorMap& my, const Params& P, int grid, size_t smem, cudaStream_t st) {
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(local_joint_tcp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_joint_tcp_kernel<T>), (int)(SMEM_LIMIT)));
   local_joint_tcp_kernel<T><<<grid, NTHREADS, smem, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -338,7 +332,7 @@ size_t local_joint_tcp_slot_floats(int K, int pad) {
 // Returns 0 when launched (J_out written), < 0 when the shape is not covered, > 0 on error.
 int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                         long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial,
-                        size_t partial_floats, double* J_out, cudaStream_t st) {
+                        size_t partial_floats, double* J_out, SlotInfo* info, cudaStream_t st) {
   using namespace fwdtcp;
   const size_t slot_floats = local_joint_tcp_slot_floats(K, pad);
   if (slot_floats == 0 || W % PXB != 0) return -1;
@@ -358,14 +352,15 @@ int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long lon
   const int raw_bytes = (3072 + KPC * T * 64 + 1023) & ~1023;
   int nop = (SMEM_LIMIT - 1024 - NRAW * raw_bytes) / op_bytes;
   if (nop > 8) nop = 8;
-  if (getenv("IIC_TC_NOP") && atoi(getenv("IIC_TC_NOP")) < nop) nop = atoi(getenv("IIC_TC_NOP"));   // experiments
+  if (tc::bringup_env("IIC_TC_NOP", nop) < nop) nop = tc::bringup_env("IIC_TC_NOP", nop);   // experiments (bring-up builds only)
   if (nop < 2) return -1;
   const size_t smem = (size_t)nop * op_bytes + (size_t)NRAW * raw_bytes + 1024;
   Params P{B, H, W, K, W / PXB, nmt, nb, op_bytes, raw_bytes, nop,
-           getenv("IIC_TC_SEG") ? atoi(getenv("IIC_TC_SEG")) : SEG_KB_DEFAULT,
-           getenv("IIC_TC_DBG") ? atoi(getenv("IIC_TC_DBG")) : 0, partial};
+           tc::bringup_env("IIC_TC_SEG", SEG_KB_DEFAULT),
+           tc::bringup_env("IIC_TC_DBG", 0), partial};
   const int rc = T == 3 ? launch<3>(mx, my, P, (int)grid, smem, st) : launch<7>(mx, my, P, (int)grid, smem, st);
   if (rc) return rc;
+  if (info) { *info = SlotInfo{SLOT_PACKED, (int)grid, (long long)slot_floats, nb}; return 0; }
   const int E = T * T * K * K;
   reduce_packed_kernel<<<(E + 31) / 32, 1024, 0, st>>>(partial, (int)grid, (int)slot_floats, T, K, nb, J_out);
   IIC_CHECK_CUDA(cudaGetLastError());

@@ -191,11 +191,7 @@ template <int T, int JT>
 static int launch_fwd_tma(const CUtensorMap& mx, const CUtensorMap& my, const FwdTmaParams& P, int grid,
                           size_t smem, cudaStream_t st) {
   auto kern = local_joint_tma_kernel<T, JT>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
-  }
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(kern), (int)(220 * 1024)));
   kern<<<grid, (P.nconsumers + 1) * 32, smem, st>>>(mx, my, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;

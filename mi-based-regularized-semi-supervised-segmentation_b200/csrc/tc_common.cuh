@@ -6,11 +6,24 @@
 #pragma once
 #include <cuda_bf16.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "tma.cuh"
 
 namespace iic {
 namespace tc {
+
+// Bring-up knobs (IIC_TC_DBG ablates loads / transforms / stores and therefore produces WRONG results, IIC_TC_SEG and
+// IIC_TC_NOP change accumulation-run lengths): only a build with -DIIC_TC_BRINGUP (the harnesses under tools/) reads
+// them; in the product library they are compile-time defaults.
+#ifdef IIC_TC_BRINGUP
+inline int bringup_env(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+#else
+inline int bringup_env(const char*, int dflt) { return dflt; }
+#endif
 
 // K-major, SWIZZLE_64B: 64-byte rows, 8-row groups 512 bytes apart
 __device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {

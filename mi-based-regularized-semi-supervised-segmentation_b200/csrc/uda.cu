@@ -6,40 +6,9 @@
 // A thread owns one pixel (o, i) and walks its C channels (stride `inner`), so a warp reads 32
 // consecutive floats per channel: fully coalesced.  With from_logits the two channel softmaxes of
 // epocher.py:222-223 are computed in registers and never touch HBM.
-#include <stdarg.h>
-
 #include "common.cuh"
 
 namespace iic {
-
-// ---- error plumbing ----------------------------------------------------------------------------------
-static thread_local char g_err[512] = "";
-void set_error(const char* fmt, ...) {
-  va_list ap;
-  va_start(ap, fmt);
-  vsnprintf(g_err, sizeof(g_err), fmt, ap);
-  va_end(ap);
-}
-const char* get_error() { return g_err; }
-
-int current_device() {
-  int d = -1;
-  if (cudaGetDevice(&d) != cudaSuccess) return -1;
-  return d;
-}
-int sm_count_cached(int device) {
-  static int cache[64];
-  if (device < 0 || device >= 64) return -1;
-  if (cache[device] > 0) return cache[device];
-  int v = 0;
-  if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) != cudaSuccess) {
-    set_error("cudaDeviceGetAttribute(MultiProcessorCount, %d) failed: %s", device,
-              cudaGetErrorString(cudaGetLastError()));
-    return -1;
-  }
-  cache[device] = v;
-  return v;
-}
 
 // ---- simplex ---------------------------------------------------------------------------------------
 __global__ void simplex_kernel(const float* __restrict__ t, long long outer, int C, long long inner,
@@ -332,9 +301,6 @@ static int uda_grid(long long total) {
 
 using namespace iic;
 
-extern "C" int iic_b200_abi_version(void) { return IIC_B200_ABI_VERSION; }
-extern "C" const char* iic_b200_last_error(void) { return get_error(); }
-extern "C" int iic_b200_sm_count(int device) { return sm_count_cached(device); }
 
 extern "C" int iic_simplex_check(const float* t, long long outer, int C, long long inner,
                                  long long s_outer, long long s_c, int* flags, void* stream) {

@@ -14,35 +14,13 @@
 //
 // Buffer layout (per rank, cudaMalloc'd by iic_xchg_create so that the IPC handle maps the allocation from offset 0):
 //   [header: flags[2][MAXR] u64, seq u64, arrive u32, done u32][pad to 1 KB][data: 2 parities x world x capacity doubles]
-#include "common.cuh"
+#include "xchg.cuh"
 
 namespace iic {
 
-constexpr int XCHG_MAXR = 16;
-constexpr size_t XCHG_HDR_BYTES = 1024;
-
-struct XchgHeader {
-  unsigned long long flags[2][XCHG_MAXR];
-  unsigned long long seq;
-  unsigned int arrive;
-  unsigned int done;
-};
-
-struct XchgPeers {
-  unsigned char* base[XCHG_MAXR];
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-
 __global__ void __launch_bounds__(256)
-xchg_allreduce_kernel(double* __restrict__ J, long long E, long long capacity, XchgPeers peers, int rank, int world) {
+xchg_allreduce_kernel(double* __restrict__ J, long long E, long long capacity, XchgPeers peers, int rank, int world,
+                      unsigned long long timeout_ns, int* __restrict__ flags) {
   XchgHeader* hdr = reinterpret_cast<XchgHeader*>(peers.base[rank]);
   __shared__ unsigned long long seq_s;
   __shared__ int last_s;
@@ -75,11 +53,10 @@ xchg_allreduce_kernel(double* __restrict__ J, long long E, long long capacity, X
   }
   // 3. wait for every rank's slot
   if (threadIdx.x < world) {
-    unsigned long long spins = 0;
-    while (ld_acquire_sys(&hdr->flags[par][threadIdx.x]) < seq) {
-      __nanosleep(64);
-      if (++spins > (1ull << 26)) __trap();          // a peer never arrived: fault instead of hanging the GPU
-    }
+    // a peer that is only slow (checkpointing, validation) is waited for; the bound (options: xchg_timeout_ms, ten
+    // minutes by default) only stops a dead peer from hanging the GPU, and is reported through the flag word
+    // (IIC_FLAG_XCHG_TIMEOUT -> RuntimeError on the host) instead of a sticky context fault
+    if (!xchg_wait_flag(hdr, par, threadIdx.x, seq, timeout_ns) && flags) atomicOr(flags, IIC_FLAG_XCHG_TIMEOUT);
   }
   __syncthreads();
   // 4. fixed-order sum (ld.cg: the slots were written by peers, L1 must not serve them)
@@ -154,7 +131,7 @@ extern "C" int iic_xchg_release(void* buf, int imported) {
 /* J[e] <- sum over ranks of their J[e], e < E <= capacity, in place, fp64, rank order.  bufs_host[r] = this process's
  * mapping of rank r's buffer (bufs_host[rank] = the local one). */
 extern "C" int iic_xchg_allreduce(double* J, long long E, long long capacity, void* const* bufs_host, int rank,
-                                  int world, void* stream) {
+                                  int world, int* flags, void* stream) {
   IIC_REQUIRE(J && bufs_host, "iic_xchg_allreduce: null pointer");
   IIC_REQUIRE(world >= 1 && world <= XCHG_MAXR && rank >= 0 && rank < world, "iic_xchg_allreduce: bad rank %d / world %d", rank, world);
   IIC_REQUIRE(E >= 0 && E <= capacity, "iic_xchg_allreduce: %lld elements exceed the buffer capacity %lld", E, capacity);
@@ -164,9 +141,29 @@ extern "C" int iic_xchg_allreduce(double* J, long long E, long long capacity, vo
   for (int r = 0; r < world; ++r) IIC_REQUIRE(peers.base[r], "iic_xchg_allreduce: buffer of rank %d is not mapped", r);
   long long ctas = (E + 255) / 256;
   const int sms = sm_count_cached(current_device());
-  const long long cap = sms > 0 ? sms : 64;            // all CTAs must be resident: they wait on one another's arrival
+  // every CTA waits for the LAST CTA of the same launch to publish, so all of them must be resident at once: at most
+  // half the SMs' worth of 256-thread CTAs (they fit beside anything that leaves 8 warps per SM free), one for small E
+  long long cap = sms > 0 ? sms / 2 : 32;
+  if (E <= 4096) cap = 1;
   if (ctas > cap) ctas = cap;
-  xchg_allreduce_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(J, E, capacity, peers, rank, world);
+  const unsigned long long timeout_ns = (unsigned long long)options().xchg_timeout_ms * 1000000ull;
+  if (ctas > 1) {
+    // cooperative launch: the driver starts the grid only when every CTA can be resident, whatever runs on other streams
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)ctas);
+    cfg.blockDim = dim3(256);
+    cfg.stream = (cudaStream_t)stream;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeCooperative;
+    attr.val.cooperative = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaLaunchKernelEx(&cfg, xchg_allreduce_kernel, J, E, capacity, peers, rank, world, timeout_ns, flags) == cudaSuccess)
+      return 0;
+    cudaGetLastError();          // e.g. a driver that cannot capture cooperative launches: plain launch below
+  }
+  xchg_allreduce_kernel<<<(unsigned)ctas, 256, 0, (cudaStream_t)stream>>>(J, E, capacity, peers, rank, world, timeout_ns,
+                                                                          flags);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -21,8 +21,8 @@ import torch
 from torch import Tensor, nn
 
 from .. import checks
-from ..ops import (FusedShapeUnsupported, GlobalIICFunction, JointFunction, LocalIICFunction,
-                   LocalIICLogitsFunction)
+from ..ops import (FusedShapeUnsupported, GlobalIICFunction, GlobalTerm, JointFunction, LocalIICFunction,
+                   LocalIICLogitsFunction, LocalTerm, iic_terms)
 
 
 def _pair(x):
@@ -141,3 +141,48 @@ class IIDSegmentationSmallPathLoss(IIDSegmentationLoss):
             except FusedShapeUnsupported:
                 pass
         return self((logits_out / T).softmax(1), (logits_tf_out / T).softmax(1))
+
+
+def iic_losses(calls):
+    """Evaluate many loss calls of one iteration TOGETHER: ``calls`` is a sequence of ``(criterion, x_out, x_tf_out)`` or
+    ``(criterion, x_out, x_tf_out, mask)`` with ``criterion`` an :class:`IIDLoss`, :class:`IIDSegmentationLoss` or
+    :class:`IIDSegmentationSmallPathLoss` instance; the result is the list ``[criterion(x_out, x_tf_out), ...]`` -- same
+    values, same autograd behaviour -- but computed with one joint kernel per call and ONE finish launch for all of
+    them (csrc/finish.cu): one slot reduction, one epilogue and, under ``set_data_parallel(True)``, ONE exchange of all
+    joints.  This is the batched form of the (feature layer x sub-head) loop of ``IICTrainEpocher.regularization``
+    (semi_seg/epocher.py:249-277), where the reference issues S x L separate calls."""
+    terms, post = [], []
+    for c in calls:
+        crit, x, y = c[0], c[1], c[2]
+        mask = c[3] if len(c) > 3 else None
+        if isinstance(crit, IIDSegmentationLoss):
+            assert x.requires_grad and y.requires_grad                   # iic_loss.py:110
+            if mask is not None:
+                assert not mask.requires_grad                            # :112
+            assert x.shape == y.shape                                    # :114
+            h, w = x.shape[2], x.shape[3]
+            if isinstance(crit, IIDSegmentationSmallPathLoss):
+                patch, step = crit._patch_size, crit._step_size
+            else:
+                patch, step = (h, w), (h, w)
+            terms.append(LocalTerm(x, y, mask, crit.padding, patch, step, crit.lamda))
+            post.append(None)
+        elif isinstance(crit, IIDLoss):
+            assert x.dim() == 2 and y.shape == x.shape, (x.shape, y.shape)
+            terms.append(GlobalTerm(x, y, crit.lamb, True))
+            post.append(crit)
+        else:
+            raise TypeError(f"iic_losses: unsupported criterion {type(crit).__name__}")
+    if not terms:
+        return []
+    res = iic_terms(terms, checks.want_simplex_kernels())
+    out = []
+    for r, crit in zip(res, post):
+        if crit is None:
+            out.append(r)
+        else:
+            # semi_seg/_utils.py:12-15: the epocher's IIDLoss wrapper returns the loss only
+            out.append(r[0] if getattr(crit, "_returns_loss_only", False) else r)
+    checks.finish(terms[0].x.device, out[0] if not isinstance(out[0], tuple) else out[0][0],
+                  "x_out / x_tf_out is not a simplex over dim 1")
+    return out

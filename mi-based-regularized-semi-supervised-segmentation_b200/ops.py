@@ -51,6 +51,7 @@ class _StreamState:
         self.epi_ws = {}
         self.sup_ws = None
         self.flip_ws = None
+        self.fin_ws = torch.zeros(lib.iic_finish_workspace_bytes(), dtype=torch.uint8, device=device)
 
     def uda_flip_ws(self, outer: int, device) -> torch.Tensor:
         nbytes = _lib.load().iic_uda_flip_workspace_bytes(device.index or 0, outer)
@@ -221,7 +222,7 @@ def _local_joint_logits(lx, ly, pad, inv_temperature):
         rc = lib.iic_local_joint_from_logits(lx.data_ptr(), lx.stride(0), lx.stride(1), lx.stride(2),
                                              ly.data_ptr(), ly.stride(0), ly.stride(1), ly.stride(2),
                                              B, K, H, W, pad, float(inv_temperature), J.data_ptr(), ws.data_ptr(),
-                                             ws.numel(), _stream(lx.device))
+                                             ws.numel(), None, _stream(lx.device))
     if rc == _lib.UNSUPPORTED:
         raise FusedShapeUnsupported(lib.iic_b200_last_error().decode())
     _lib.check(rc, "iic_local_joint_from_logits")
@@ -493,39 +494,86 @@ ops = torch.ops.iic_b200
 _process_group = None
 _dist_enabled = False
 _xchg = None          # PeerExchange, when the NVLink peer-memory exchange is set up
-XCHG_CAPACITY = 9 * 128 * 128     # doubles per rank slot: the local joint at K = 128, padding 1 (config 5)
+XCHG_CAPACITY = 1 << 18          # doubles per rank slot (2 MB): every joint of one iteration, e.g. config 3's 15 terms at K = 20
+                                 # (118 k) or config 5's local + global joint at K = 128 (164 k)
 
 
 class PeerExchange:
-    """Exchange buffers of all ranks mapped into this process with CUDA IPC (csrc/xchg.cu).  Built collectively."""
+    """Exchange buffers of all ranks mapped into this process with CUDA IPC (csrc/xchg.cu).  Built collectively.
 
-    def __init__(self, group, device: torch.device, capacity: int = XCHG_CAPACITY):
+    Every rank runs the SAME sequence of collectives whatever fails locally (an allocation, an IPC import without peer
+    access): local errors are recorded, the agreement all-reduce at the end decides for everybody, and a rank that
+    failed releases what it had mapped.  ``ok`` tells whether the exchange is usable on ALL ranks."""
+
+    def __init__(self, group, device: torch.device, capacity: int = None):
         import ctypes as C
         import torch.distributed as dist
         lib = _lib.load()
+        capacity = XCHG_CAPACITY if capacity is None else capacity
         self.group, self.device, self.capacity = group, device, int(capacity)
         self.rank, self.world = dist.get_rank(group), dist.get_world_size(group)
+        self.ptrs = (C.c_void_p * self.world)()
+        self._owned, self._imported, self.error = None, [], None
+        handle = C.create_string_buffer(64)
         with torch.cuda.device(device):
-            buf = C.c_void_p()
-            _lib.check(lib.iic_xchg_create(self.world, self.capacity, C.byref(buf)), "iic_xchg_create")
-            handle = C.create_string_buffer(64)
-            _lib.check(lib.iic_xchg_export(buf, handle), "iic_xchg_export")
+            # phase 1 (local): allocate and export
+            try:
+                buf = C.c_void_p()
+                _lib.check(lib.iic_xchg_create(self.world, self.capacity, C.byref(buf)), "iic_xchg_create")
+                self._owned = buf.value
+                _lib.check(lib.iic_xchg_export(buf, handle), "iic_xchg_export")
+                mine = bytes(handle.raw)
+            except Exception as e:  # noqa: BLE001
+                self.error, mine = e, None
+            # collective 1: everybody takes part, failed ranks contribute None
             handles = [None] * self.world
-            dist.all_gather_object(handles, bytes(handle.raw), group=group)
-            self.ptrs = (C.c_void_p * self.world)()
-            for r, h in enumerate(handles):
-                if r == self.rank:
-                    self.ptrs[r] = buf.value
-                else:
-                    peer = C.c_void_p()
-                    _lib.check(lib.iic_xchg_import(C.create_string_buffer(h, 64), C.byref(peer)), f"iic_xchg_import(rank {r})")
-                    self.ptrs[r] = peer.value
-        dist.barrier(group=group)     # every rank has mapped every buffer before the first exchange
+            dist.all_gather_object(handles, mine, group=group)
+            # phase 2 (local): import the peers' buffers
+            if self.error is None and all(h is not None for h in handles):
+                try:
+                    for r, h in enumerate(handles):
+                        if r == self.rank:
+                            self.ptrs[r] = self._owned
+                        else:
+                            peer = C.c_void_p()
+                            _lib.check(lib.iic_xchg_import(C.create_string_buffer(h, 64), C.byref(peer)),
+                                       f"iic_xchg_import(rank {r})")
+                            self._imported.append(peer.value)
+                            self.ptrs[r] = peer.value
+                except Exception as e:  # noqa: BLE001
+                    self.error = e
+            elif self.error is None:
+                self.error = RuntimeError("a peer could not create its exchange buffer")
+            # collective 2: agreement (doubles as the barrier "every rank has mapped every buffer")
+            ok = torch.tensor([0 if self.error is not None else 1], device=device)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
+            self.ok = bool(int(ok.item()))
+        if not self.ok:
+            self.close()
+
+    def close(self):
+        """Unmap the peers' buffers and free the own one (idempotent)."""
+        lib = _lib.load()
+        with torch.cuda.device(self.device):
+            for p in self._imported:
+                lib.iic_xchg_release(p, 1)
+            self._imported = []
+            if self._owned is not None:
+                torch.cuda.synchronize(self.device)
+                lib.iic_xchg_release(self._owned, 0)
+                self._owned = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
 
     def allreduce_(self, J: torch.Tensor) -> torch.Tensor:
-        assert J.dtype == torch.float64 and J.is_contiguous() and J.device == self.device
+        assert self.ok and J.dtype == torch.float64 and J.is_contiguous() and J.device == self.device
         lib = _lib.load()
         _lib.check(lib.iic_xchg_allreduce(J.data_ptr(), J.numel(), self.capacity, self.ptrs, self.rank, self.world,
+                                          _state(self.device).flags.data_ptr(),
                                           torch.cuda.current_stream(self.device).cuda_stream), "iic_xchg_allreduce")
         return J
 
@@ -543,6 +591,8 @@ def set_data_parallel(enabled: bool, group=None, peer_memory=None):
     global _process_group, _dist_enabled, _xchg
     _dist_enabled = bool(enabled)
     _process_group = group
+    if _xchg is not None:
+        _xchg.close()            # a previous call's buffers and IPC mappings
     _xchg = None
     if not _dist_enabled or peer_memory is False:
         return
@@ -555,19 +605,13 @@ def set_data_parallel(enabled: bool, group=None, peer_memory=None):
                  or dist.get_world_size(group) > 16
                  or int(os.environ.get("LOCAL_WORLD_SIZE", dist.get_world_size(group))) != dist.get_world_size(group)):
         return
-    try:
-        _xchg = PeerExchange(group, torch.device("cuda", torch.cuda.current_device()))
-    except Exception:
-        _xchg = None
-        if not auto:
-            raise
-    # all ranks must agree, or some would wait in the exchange kernel while others sit in NCCL
-    ok = torch.tensor([1 if _xchg is not None else 0], device="cuda")
-    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)
-    if int(ok.item()) == 0:
-        if not auto:
-            raise RuntimeError("iic_b200: the peer-memory exchange could not be set up on every rank")
-        _xchg = None
+    # PeerExchange runs the same collectives on every rank whatever fails locally and ends with an agreement step,
+    # so either all ranks use peer memory or all of them fall back to NCCL
+    px = PeerExchange(group, torch.device("cuda", torch.cuda.current_device()))
+    if px.ok:
+        _xchg = px
+    elif not auto:
+        raise RuntimeError(f"iic_b200: the peer-memory exchange could not be set up on every rank ({px.error})")
 
 
 def ddp_loss_scale(group=None) -> float:
@@ -603,18 +647,248 @@ def _maybe_allreduce(J: torch.Tensor) -> torch.Tensor:
     return J
 
 
+# ---- one or many IIC terms through ONE finish launch (csrc/finish.cu) ------------------------------------
+class LocalTerm:
+    """One local IIC call: IIDSegmentationLoss / IIDSegmentationSmallPathLoss on (x, y[, mask]); `logits` = the inputs are
+    the cluster head's logits and the softmax is fused into the kernels (one patch, no mask)."""
+    __slots__ = ("x", "y", "mask", "pad", "patch", "step", "lamda", "logits", "inv_temperature")
+
+    def __init__(self, x, y, mask, pad, patch, step, lamda, logits=False, inv_temperature=1.0):
+        self.x, self.y, self.mask = x, y, mask
+        self.pad, self.patch, self.step, self.lamda = int(pad), (int(patch[0]), int(patch[1])), (int(step[0]), int(step[1])), float(lamda)
+        self.logits, self.inv_temperature = bool(logits), float(inv_temperature)
+
+
+class GlobalTerm:
+    """One global IIC call: IIDLoss / compute_joint on (N, K) rows."""
+    __slots__ = ("x", "y", "lamb", "symmetric", "want_losses")
+
+    def __init__(self, x, y, lamb=1.0, symmetric=True, want_losses=True):
+        self.x, self.y, self.lamb, self.symmetric, self.want_losses = x, y, float(lamb), bool(symmetric), bool(want_losses)
+
+
+MAX_TERMS_PER_FINISH = 32
+GLOBAL_ROWS_MAX = 4096          # larger (N, K) inputs take the multi-CTA global joint kernel instead of iic_finish
+
+
+def _world():
+    if _dist_enabled:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_world_size(_process_group)
+    return 1
+
+
+def _finish_terms(terms, check_simplex):
+    """Joint kernels of every term, then ONE iic_finish launch (slot reduction, the multi-GPU exchange of ALL joints,
+    the epilogues).  Returns per term a dict of what its backward needs and its outputs."""
+    import ctypes as C
+    lib = _lib.load()
+    assert 0 < len(terms) <= MAX_TERMS_PER_FINISH
+    for t in terms:                      # before any device state is touched: CPU tensors are refused loudly
+        _require_cuda_f32("x_out", t.x)
+        _require_cuda_f32("x_tf_out", t.y)
+    dev = terms[0].x.device
+    st = _state(dev)
+    flags = st.flags.data_ptr()
+    items = (_lib.FinishItem * len(terms))()
+    keep, recs, E_total = [], [], 0
+    n_loss = sum(1 if isinstance(t, LocalTerm) else 2 for t in terms)
+    loss_buf = torch.empty(n_loss, dtype=torch.float32, device=dev)
+    lo = 0
+    with torch.cuda.device(dev):
+        for i, t in enumerate(terms):
+            it = items[i]
+            if isinstance(t, LocalTerm):
+                _require_cuda_f32("x_out", t.x)
+                _require_cuda_f32("x_tf_out", t.y)
+                if t.x.dim() != 4 or t.x.shape != t.y.shape:
+                    raise ValueError(f"iic_b200: local term shapes {tuple(t.x.shape)} vs {tuple(t.y.shape)}")
+                x, y = _w_contig(t.x), _w_contig(t.y)
+                B, K, H, W = x.shape
+                info = _lib.SlotInfo()
+                if t.logits:
+                    nbytes = max(lib.iic_b200_sm_count(dev.index or 0) * 9 * K * K * 4, 4)
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    rc = lib.iic_local_joint_from_logits(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
+                                                         y.data_ptr(), y.stride(0), y.stride(1), y.stride(2),
+                                                         B, K, H, W, t.pad, t.inv_temperature, None, ws.data_ptr(), nbytes,
+                                                         C.byref(info), _stream(dev))
+                    if rc == _lib.UNSUPPORTED:
+                        raise FusedShapeUnsupported(lib.iic_b200_last_error().decode())
+                    _lib.check(rc, "iic_local_joint_from_logits")
+                    npatch, m = 1, None
+                else:
+                    m, msn, msc, msh = _mask_args(t.mask, x)
+                    npatch = lib.iic_local_num_patches(H, W, t.patch[0], t.patch[1], t.step[0], t.step[1])
+                    if npatch <= 0:
+                        _lib.check(1, "iic_local_num_patches")
+                    nbytes = lib.iic_local_joint_workspace_bytes(dev.index or 0, B, K, H, W, t.pad, t.patch[0], t.patch[1],
+                                                                 t.step[0], t.step[1])
+                    if nbytes == 0:
+                        _lib.check(1, "iic_local_joint_workspace_bytes")
+                    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                    fl = None
+                    if check_simplex:
+                        if x.stride(2) == W:
+                            fl = flags
+                        else:
+                            _simplex_check(x, 1)
+                    _lib.check(lib.iic_local_joint_partials(
+                        x.data_ptr(), x.stride(0), x.stride(1), x.stride(2), y.data_ptr(), y.stride(0), y.stride(1),
+                        y.stride(2), _ptr(m), msn, msc, msh, B, K, H, W, t.pad, t.patch[0], t.patch[1], t.step[0], t.step[1],
+                        ws.data_ptr(), nbytes, fl, C.byref(info), _stream(dev)), "iic_local_joint_partials")
+                T = 2 * t.pad + 1
+                ncoef = lib.iic_local_coeff_floats(K, t.pad, npatch)
+                Wx = torch.empty(ncoef, dtype=torch.float32, device=dev)
+                Wy = torch.empty(ncoef, dtype=torch.float32, device=dev)
+                it.kind, it.K, it.lamda = _lib.ITEM_LOCAL, K, t.lamda
+                it.slots, it.layout, it.n_slots, it.nb, it.slot_stride = ws.data_ptr(), info.layout, info.n_slots, info.nb, info.slot_stride
+                it.pad, it.n_patches = t.pad, npatch
+                it.epilogue_workspace = st.epilogue_ws(K, t.pad, npatch, dev).data_ptr() if K > 32 else None
+                it.loss_out, it.Wx, it.Wy = loss_buf[lo:].data_ptr(), Wx.data_ptr(), Wy.data_ptr()
+                E = npatch * T * T * K * K
+                recs.append(dict(kind="local", x=x, y=y, mask=m, Wx=Wx, Wy=Wy, loss=loss_buf[lo], K=K, T=T, npatch=npatch,
+                                 joff=E_total, E=E))
+                keep.append(ws)
+                lo += 1
+            else:
+                _require_cuda_f32("x_out", t.x)
+                _require_cuda_f32("x_tf_out", t.y)
+                if t.x.dim() != 2 or t.x.shape != t.y.shape:
+                    raise ValueError(f"iic_b200: global term shapes {tuple(t.x.shape)} vs {tuple(t.y.shape)}")
+                x, y = _w_contig(t.x), _w_contig(t.y)
+                N, K = x.shape
+                P = torch.empty((K, K), dtype=torch.float32, device=dev)
+                it.kind, it.K, it.lamda = _lib.ITEM_GLOBAL_ROWS, K, t.lamb
+                it.x, it.x_sn, it.y, it.y_sn, it.N = x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N
+                it.symmetric, it.check_simplex = int(t.symmetric), int(bool(check_simplex))
+                it.loss_out, it.P_out = loss_buf[lo:].data_ptr(), P.data_ptr()
+                E = K * K
+                recs.append(dict(kind="global", x=x, y=y, P=P, loss=loss_buf[lo], loss_nl=loss_buf[lo + 1], K=K, joff=E_total,
+                                 E=E))
+                lo += 2
+            E_total += E
+        J_all = torch.empty(E_total, dtype=torch.float64, device=dev)
+        world = _world()
+        fused_xchg = world > 1 and _xchg is not None and E_total <= _xchg.capacity
+        if world > 1 and not fused_xchg:
+            # NCCL transport (or joints larger than the peer slots): reduce here, all-reduce, then the epilogue launches
+            _lib.check(lib.iic_finish(items, len(terms), J_all.data_ptr(), E_total, flags, st.fin_ws.data_ptr(), None, 0, 1, 0,
+                                      0, _stream(dev)), "iic_finish")
+            import torch.distributed as dist
+            dist.all_reduce(J_all, op=dist.ReduceOp.SUM, group=_process_group)
+            for i, (t, r) in enumerate(zip(terms, recs)):
+                Jv = J_all[r["joff"]:r["joff"] + r["E"]]
+                if r["kind"] == "local":
+                    _lib.check(lib.iic_local_epilogue(Jv.data_ptr(), r["K"], t.pad, r["npatch"], t.lamda, items[i].loss_out, None,
+                                                      r["Wx"].data_ptr(), r["Wy"].data_ptr(), None, flags,
+                                                      st.epilogue_ws(r["K"], t.pad, r["npatch"], dev).data_ptr(), _stream(dev)),
+                               "iic_local_epilogue")
+                else:
+                    _lib.check(lib.iic_global_epilogue(Jv.data_ptr(), r["K"], t.lamb, int(t.symmetric), items[i].loss_out,
+                                                       r["P"].data_ptr(), flags, _stream(dev)), "iic_global_epilogue")
+        else:
+            _lib.check(lib.iic_finish(items, len(terms), J_all.data_ptr(), E_total, flags, st.fin_ws.data_ptr(),
+                                      _xchg.ptrs if fused_xchg else None, _xchg.rank if fused_xchg else 0,
+                                      world if fused_xchg else 1, _xchg.capacity if fused_xchg else 0, 1, _stream(dev)),
+                       "iic_finish")
+    del keep
+    for r in recs:
+        r["J"] = J_all[r["joff"]:r["joff"] + r["E"]]
+    return recs
+
+
+class IICTermsFunction(torch.autograd.Function):
+    """The losses of one or many IIC terms -- local (iic_loss.py:107-149,171-186) and global (iic_loss.py:43-94) -- from
+    ONE finish launch.  apply(terms, check_simplex, *tensors): `terms` carries the geometry, `tensors` the differentiable
+    inputs (x, y of every term in order).  Outputs per local term: loss; per global term: loss, loss_no_lamb, P."""
+
+    @staticmethod
+    def forward(ctx, terms, check_simplex, *tensors):
+        recs = _finish_terms(terms, check_simplex)
+        outs, saved = [], []
+        for r in recs:
+            if r["kind"] == "local":
+                outs.append(r["loss"])
+                saved += [r["x"], r["y"], r["Wx"], r["Wy"]] + ([r["mask"]] if r["mask"] is not None else [])
+            else:
+                outs += [r["loss"], r["loss_nl"], r["P"]]
+                saved += [r["x"], r["y"], r["J"]]
+        ctx.save_for_backward(*saved)
+        ctx.meta = [(t.__class__, getattr(t, "pad", None), getattr(t, "patch", None), getattr(t, "step", None),
+                     getattr(t, "logits", False), getattr(t, "inv_temperature", 1.0), getattr(t, "lamb", None),
+                     getattr(t, "symmetric", True), r.get("mask") is not None) for t, r in zip(terms, recs)]
+        ctx.set_materialize_grads(False)
+        return tuple(outs)
+
+    @staticmethod
+    def backward(ctx, *grads):
+        sv = list(ctx.saved_tensors)
+        res, gi, si = [], 0, 0
+        for cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask in ctx.meta:
+            if cls is LocalTerm:
+                x, y, Wx, Wy = sv[si:si + 4]
+                si += 4
+                mask = None
+                if has_mask:
+                    mask = sv[si]
+                    si += 1
+                g = grads[gi]
+                gi += 1
+                if g is None:
+                    res += [None, None]
+                elif logits:
+                    res += list(ops.local_backward_logits(x, y, Wx, Wy, g.contiguous(), pad, inv_t))
+                else:
+                    res += list(ops.local_backward(x, y, mask, Wx, Wy, g.contiguous(), pad, patch[0], patch[1], step[0], step[1]))
+            else:
+                x, y, J = sv[si:si + 3]
+                si += 3
+                g1, g2, gP = grads[gi:gi + 3]
+                gi += 3
+                if g1 is None and g2 is None and gP is None:
+                    res += [None, None]
+                else:
+                    res += list(ops.global_backward(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP))
+        return (None, None, *res)
+
+
+def iic_terms(terms, check_simplex=False):
+    """Evaluate many IIC terms together; returns a list with, per term, the loss (LocalTerm) or the tuple
+    (loss, loss_no_lamb, P) (GlobalTerm).  Global terms with more than GLOBAL_ROWS_MAX rows and batches beyond
+    MAX_TERMS_PER_FINISH are split off transparently."""
+    terms = list(terms)
+    out = [None] * len(terms)
+    batch = [i for i, t in enumerate(terms) if isinstance(t, LocalTerm) or t.x.shape[0] <= GLOBAL_ROWS_MAX]
+    for i, t in enumerate(terms):
+        if i not in batch:
+            out[i] = _GlobalIICMultiCTAFunction.apply(t.x, t.y, t.lamb, t.symmetric, check_simplex)
+    for c0 in range(0, len(batch), MAX_TERMS_PER_FINISH):
+        idx = batch[c0:c0 + MAX_TERMS_PER_FINISH]
+        sub = [terms[i] for i in idx]
+        flat = [v for t in sub for v in (t.x, t.y)]
+        res = list(IICTermsFunction.apply(sub, check_simplex, *flat))
+        for i, t in zip(idx, sub):
+            if isinstance(t, LocalTerm):
+                out[i] = res.pop(0)
+            else:
+                out[i] = (res.pop(0), res.pop(0), res.pop(0))
+    return out
+
+
 # ---- autograd ------------------------------------------------------------------------------------------
 class LocalIICFunction(torch.autograd.Function):
-    """loss = mean over patches of the shifted-window IIC loss (iic_loss.py:107-149, 171-186)."""
+    """loss = mean over patches of the shifted-window IIC loss (iic_loss.py:107-149, 171-186): joint kernel, one finish
+    launch (slot reduction [+ exchange] + epilogue), and in backward one gradient kernel."""
 
     @staticmethod
     def forward(ctx, x, y, mask, pad, patch_h, patch_w, step_h, step_w, lamda, check_simplex=False):
-        J = ops.local_joint(x, y, mask, pad, patch_h, patch_w, step_h, step_w, check_simplex)
-        J = _maybe_allreduce(J)
-        loss, Wx, Wy = ops.local_epilogue(J, x.shape[1], pad, lamda)
-        ctx.save_for_backward(x, y, mask, Wx, Wy)
+        t = LocalTerm(x, y, mask, pad, (patch_h, patch_w), (step_h, step_w), lamda)
+        (r,) = _finish_terms([t], check_simplex)
+        ctx.save_for_backward(r["x"], r["y"], r["mask"], r["Wx"], r["Wy"])
         ctx.geom = (pad, patch_h, patch_w, step_h, step_w)
-        return loss
+        return r["loss"]
 
     @staticmethod
     def backward(ctx, grad):
@@ -630,12 +904,11 @@ class LocalIICLogitsFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, lx, ly, pad, lamda, inv_temperature):
-        J = ops.local_joint_logits(lx, ly, pad, inv_temperature)
-        J = _maybe_allreduce(J)
-        loss, Wx, Wy = ops.local_epilogue(J, lx.shape[1], pad, lamda)
-        ctx.save_for_backward(lx, ly, Wx, Wy)
+        t = LocalTerm(lx, ly, None, pad, lx.shape[2:], lx.shape[2:], lamda, logits=True, inv_temperature=inv_temperature)
+        (r,) = _finish_terms([t], False)
+        ctx.save_for_backward(r["x"], r["y"], r["Wx"], r["Wy"])
         ctx.cfg = (pad, inv_temperature)
-        return loss
+        return r["loss"]
 
     @staticmethod
     def backward(ctx, grad):
@@ -644,17 +917,41 @@ class LocalIICLogitsFunction(torch.autograd.Function):
         return gx, gy, None, None, None
 
 
+class _GlobalIICMultiCTAFunction(torch.autograd.Function):
+    """(loss, loss_no_lamb, P) of IIDLoss.forward (iic_loss.py:43-71) for LARGE N: multi-CTA joint, exchange, epilogue."""
+
+    @staticmethod
+    def forward(ctx, x, y, lamb, symmetric=True, check_simplex=False):
+        J = _maybe_allreduce(ops.global_joint(x, y, check_simplex))
+        losses, P = ops.global_epilogue(J, lamb, symmetric, True)
+        ctx.save_for_backward(x, y, J)
+        ctx.cfg = (lamb, symmetric)
+        ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero tensors
+        return losses[0], losses[1], P
+
+    @staticmethod
+    def backward(ctx, g1, g2, gP):
+        x, y, J = ctx.saved_tensors
+        gx, gy = ops.global_backward(x, y, J, ctx.cfg[0], ctx.cfg[1], g1, g2, gP)
+        return gx, gy, None, None, None
+
+
 class GlobalIICFunction(torch.autograd.Function):
-    """(loss, loss_no_lamb, P) of IIDLoss.forward (iic_loss.py:43-71)."""
+    """(loss, loss_no_lamb, P) of IIDLoss.forward (iic_loss.py:43-71): for the udaiic sizes (N <= 4096 rows) ONE launch --
+    iic_finish computes the joint from the rows, exchanges it under data parallelism and runs the epilogue."""
 
     @staticmethod
     def forward(ctx, x, y, lamb, check_simplex=False):
-        J = _maybe_allreduce(ops.global_joint(x, y, check_simplex))
-        losses, P = ops.global_epilogue(J, lamb, True, True)
-        ctx.save_for_backward(x, y, J)
-        ctx.lamb = lamb
         ctx.set_materialize_grads(False)     # unused outputs arrive as None, not as zero tensors
-        return losses[0], losses[1], P
+        ctx.lamb = lamb
+        if x.dim() == 2 and x.shape[0] > GLOBAL_ROWS_MAX:
+            J = _maybe_allreduce(ops.global_joint(x, y, check_simplex))
+            losses, P = ops.global_epilogue(J, lamb, True, True)
+            ctx.save_for_backward(x, y, J)
+            return losses[0], losses[1], P
+        (r,) = _finish_terms([GlobalTerm(x, y, lamb, True)], check_simplex)
+        ctx.save_for_backward(r["x"], r["y"], r["J"].view(r["K"], r["K"]))
+        return r["loss"], r["loss_nl"], r["P"]
 
     @staticmethod
     def backward(ctx, g1, g2, gP):

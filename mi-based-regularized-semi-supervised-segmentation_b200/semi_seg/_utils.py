@@ -16,7 +16,7 @@ import torch
 from torch import Tensor, nn
 
 from ..losses.iic_loss import IIDLoss as _IIDLoss
-from ..losses.iic_loss import IIDSegmentationSmallPathLoss
+from ..losses.iic_loss import IIDSegmentationSmallPathLoss, iic_losses
 
 # contrastyou/arch/unet.py:185-194
 ENCODER_NAMES = ["Conv1", "Conv2", "Conv3", "Conv4", "Conv5"]
@@ -24,6 +24,8 @@ DECODER_NAMES = ["Up5", "Up_conv5", "Up4", "Up_conv4", "Up3", "Up_conv3", "Up2",
 
 
 class IIDLoss(_IIDLoss):
+    _returns_loss_only = True        # semi_seg/_utils.py:14-15; iic_losses() honours it too
+
     def forward(self, x_out: Tensor, x_tf_out: Tensor):
         return super().forward(x_out, x_tf_out)[0]
 
@@ -103,3 +105,24 @@ def combine_iic_losses(losses_per_layer: Sequence[Sequence[Tensor]], feature_imp
     index = torch.tensor([i for i, c in enumerate(counts) for _ in range(c)]).to(flat.device, non_blocking=True)
     per_layer = torch.zeros(len(counts), dtype=flat.dtype, device=flat.device).index_add(0, index, flat * seg)
     return total, per_layer
+
+
+def iic_regularization(prob_pairs_per_layer: Sequence[Sequence], criteria: Sequence[nn.Module],
+                       feature_importance: Sequence[float]):
+    """The value ``IICTrainEpocher.regularization`` computes (semi_seg/epocher.py:249-277) from the cluster heads' outputs:
+    ``prob_pairs_per_layer[l]`` is the list of ``(prob1, prob2)`` pairs of layer ``l`` (one per sub-head, epocher.py:
+    269-273), ``criteria[l]`` that layer's loss module (``IICLossWrapper[l]``).  All S x L loss calls go through
+    :func:`iic_losses` -- one finish launch, one multi-GPU exchange -- and are combined by :func:`combine_iic_losses`
+    (``average_iter`` over sub-heads, ``weighted_average_iter`` over layers).  Returns ``(reg_loss, per_layer_losses)``."""
+    assert len(prob_pairs_per_layer) == len(criteria) == len(feature_importance)
+    calls, counts = [], []
+    for pairs, crit in zip(prob_pairs_per_layer, criteria):
+        pairs = list(pairs)
+        counts.append(len(pairs))
+        calls += [(crit, a, b) for a, b in pairs]
+    flat = iic_losses(calls)
+    per_layer, k = [], 0
+    for c in counts:
+        per_layer.append([l[0] if isinstance(l, tuple) else l for l in flat[k:k + c]])
+        k += c
+    return combine_iic_losses(per_layer, feature_importance)

@@ -22,9 +22,24 @@ import tempfile
 import types
 import zipfile
 
-REFERENCE_ROOT = os.environ.get("IIC_REFERENCE_ROOT", "/root/reference")
 _WHEEL = "deepclustering2-2.0.0-py3-none-any.whl"
+_LOCAL_COPY = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref", "reference")   # oracle/make_ref.py
 _cache = {}
+
+
+def _pick_root() -> str:
+    """IIC_REFERENCE_ROOT if set, else /root/reference (the build container), else the verbatim copy that
+    oracle/make_ref.py laid out under oracle/_ref/ (the GPU box, where /root/reference does not exist)."""
+    env = os.environ.get("IIC_REFERENCE_ROOT")
+    if env:
+        return env
+    for cand in ("/root/reference", _LOCAL_COPY):
+        if os.path.isfile(os.path.join(cand, "contrastyou", "losses", "iic_loss.py")):
+            return cand
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _pick_root()
 
 
 def available() -> bool:
@@ -39,6 +54,9 @@ def _load_by_path(name: str, path: str):
 
 
 def _extract_wheel_member(member: str) -> str:
+    unpacked = os.path.join(REFERENCE_ROOT, member)          # oracle/_ref: the wheel is already extracted
+    if os.path.isfile(unpacked):
+        return unpacked
     out_dir = os.path.join(tempfile.gettempdir(), "iic_b200_dc2_extract")
     out = os.path.join(out_dir, member)
     if not os.path.isfile(out):

@@ -32,7 +32,32 @@ def test_library_exports_every_declared_symbol(built):
     for name in declared:
         assert hasattr(lib, name), f"libiic_b200.so does not export {name}"
     assert declared == set(built._lib.PROTOTYPES), declared ^ set(built._lib.PROTOTYPES)
-    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == 5
+    declared_abi = int(re.search(r"#define IIC_B200_ABI_VERSION (\d+)", hdr).group(1))
+    assert built._lib.load().iic_b200_abi_version() == built._lib.ABI_VERSION == declared_abi
+
+
+def test_options_are_read_once_and_settable(built):
+    """The dispatch switches are a table inside the library (csrc/runtime.cu): environment defaults are read once,
+    iic_b200_set_option changes them afterwards, unknown names are errors."""
+    L = built._lib
+    lib = L.load()
+    assert lib.iic_b200_get_option(b"tcrb_p1") in (0, 1)
+    old = L.set_option("tcrb_p1", 1)
+    try:
+        assert lib.iic_b200_get_option(b"tcrb_p1") == 1
+        os.environ["IIC_B200_TCRB_P1"] = "0"          # too late: the environment was read at first use
+        assert lib.iic_b200_get_option(b"tcrb_p1") == 1
+    finally:
+        os.environ.pop("IIC_B200_TCRB_P1", None)
+        L.set_option("tcrb_p1", old)
+    assert lib.iic_b200_get_option(b"xchg_timeout_ms") > 0
+    assert lib.iic_b200_set_option(b"no_such_switch", 1) != 0
+    assert lib.iic_b200_get_option(b"no_such_switch") == -1
+    # the coefficient buffers carry the tensor-core weight images: no hidden allocation in the backward
+    assert lib.iic_local_coeff_floats(10, 1, 1) == 10 * 9 * 12
+    assert lib.iic_local_coeff_floats(20, 3, 1) > 20 * 49 * 20
+    assert lib.iic_local_coeff_floats(128, 1, 1) > 128 * 9 * 128
+    assert lib.iic_local_coeff_floats(20, 3, 4) == 4 * 20 * 49 * 20       # several patches: generic kernels only
 
 
 def test_patch_count_matches_reference_windows(built):
