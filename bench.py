@@ -217,11 +217,15 @@ def build_step(wl, B, crits, iic_losses, uda_fn, torch):
         calls, spans = [], []
         for gi, (kind, S, K, H, W, pad, patch, w) in enumerate(wl["groups"]):
             x, y = tensors[2 * gi], tensors[2 * gi + 1]
+            spans.append((len(calls), S, w))
+            if S == 1:
+                calls.append((crits[gi], x, y))
+                continue
+            # the S sub-heads are channel blocks of ONE head output, as the batched cluster heads emit them
             if kind == "local":
                 xv, yv = x.view(B, S, K, H, W), y.view(B, S, K, H, W)
             else:
                 xv, yv = x.view(B, S, K), y.view(B, S, K)
-            spans.append((len(calls), S, w))
             calls += [(crits[gi], xv[:, s], yv[:, s]) for s in range(S)]
         losses = iic_losses(calls)
         flat = [l[0] if isinstance(l, tuple) else l for l in losses]

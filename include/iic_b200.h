@@ -43,7 +43,8 @@ const char* iic_b200_last_error(void);
 int iic_b200_sm_count(int device);
 /* Dispatch switches.  The library reads IIC_B200_* environment variables ONCE (at first use) as defaults; after that
  * only these calls change them.  Names: "no_tma", "no_tc", "no_tc10", "no_fast" (skip a kernel family), "tcp_p1",
- * "tcrb_p1", "tc10_force" (force a tensor-core kernel outside the shapes it is normally chosen for), "no_fused_epilogue",
+ * "tcrb_p1", "tc10_force" (force a tensor-core kernel outside the shapes it is normally chosen for), "tc10_tf32" (the
+ * tf32 + bf16-correction form of the K = 10 backward instead of the fp16-split one), "no_fused_epilogue",
  * "xchg_timeout_ms".  Results are the same whatever the switches; only the kernel that runs changes (the parity tests
  * use them to reach every dispatch branch).  set: 0 = ok; get: the value, -1 for an unknown name. */
 int iic_b200_set_option(const char* name, int value);
@@ -124,8 +125,10 @@ int iic_local_epilogue(const double* J, int K, int pad, int n_patches, double la
 /* Both input gradients (what autograd's convolution_backward yields for iic_loss.py:123):
  *   gx[n,i,a,b] (+)= g * mask * sum_{d,j} dL/dJ[d,i,j] * (mask*y)[n,j,a-dy+pad,b-dx+pad]
  *   gy[n,j,u,v] (+)= g * mask * sum_{d,i} dL/dJ[d,i,j] * (mask*x)[n,i,u+dy-pad,v+dx-pad]
- * g = *grad_loss (device scalar; NULL means 1).  gx/gy are dense NCHW (B,K,H,W); with more than one
- * patch the caller zero-fills them first and every patch accumulates.  Wx / Wy are the buffers of iic_local_epilogue
+ * g = *grad_loss (device scalar; NULL means 1).  gx/gy are (B,K,H,W) with dense rows and channel planes and the sample
+ * strides gx_sn / gy_sn in elements (0 = K*H*W, a fully dense tensor): a sub-head's gradient can be written straight
+ * into its channel block of the gradient of the whole (B, S*K, H, W) head output (contrastyou/trainer/_utils.py:
+ * 137-168), no gather pass.  With more than one patch the caller zero-fills them first and every patch accumulates.  Wx / Wy are the buffers of iic_local_epilogue
  * (iic_local_coeff_floats floats each); their scratch tail may be overwritten. */
 int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long x_sh,
                        const float* y, long long y_sn, long long y_sc, long long y_sh,
@@ -133,7 +136,7 @@ int iic_local_backward(const float* x, long long x_sn, long long x_sc, long long
                        int B, int K, int H, int W, int pad,
                        int patch_h, int patch_w, int step_h, int step_w,
                        float* Wx, float* Wy, const float* grad_loss,
-                       float* gx, float* gy, void* stream);
+                       float* gx, float* gy, long long gx_sn, long long gy_sn, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Cluster-head softmax fused into the local term.  lx, ly are the LOGITS of LocalClusterHead
@@ -155,7 +158,7 @@ int iic_local_backward_from_logits(const float* lx, long long x_sn, long long x_
                                    const float* ly, long long y_sn, long long y_sc, long long y_sh,
                                    int B, int K, int H, int W, int pad, float inv_temperature,
                                    const float* Wx, const float* Wy, const float* grad_loss,
-                                   float* g_lx, float* g_ly, void* stream);
+                                   float* g_lx, float* g_ly, long long gx_sn, long long gy_sn, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Global IIC on (N,K) simplex rows.  Replaces compute_joint (iic_loss.py:74-94) and IIDLoss.forward
@@ -174,11 +177,12 @@ int iic_global_epilogue(const double* J, int K, double lamb, int symmetric,
                         float* losses_out, float* P_out, int* flags, void* stream);
 /* gradients of  g_loss*loss + g_no_lamb*loss_no_lamb + <gP, P>  w.r.t. x and y, from the saved J.
  * g_loss, g_no_lamb (device scalars) and gP ((K,K) float32) are the upstream gradients of the three
- * outputs of IIDLoss.forward; each is nullable and NULL means "no gradient flows into that output". */
+ * outputs of IIDLoss.forward; each is nullable and NULL means "no gradient flows into that output".
+ * gx_sn / gy_sn: row strides of the (N, K) gradient tensors in elements (0 = K, dense). */
 int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
                         long long N, int K, const double* J, double lamb, int symmetric,
                         const float* g_loss, const float* g_no_lamb, const float* gP,
-                        float* gx, float* gy, void* stream);
+                        float* gx, float* gy, long long gx_sn, long long gy_sn, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * iic_finish: ONE launch between the joint kernels and the backward kernels of one or many IIC terms -- the (layer,
@@ -205,7 +209,8 @@ typedef struct iic_finish_item {
   int layout, n_slots, nb;
   long long slot_stride;
   int pad, n_patches;
-  void* epilogue_workspace;       /* iic_local_epilogue_workspace_bytes; only used when K > 32 (may be NULL otherwise) */
+  void* epilogue_workspace;       /* iic_local_epilogue_workspace_bytes; used when the epilogue is not fused (K > 32, very
+                                     many patches, or the no_fused_epilogue switch) */
   /* global term: the rows */
   const float* x; long long x_sn;
   const float* y; long long y_sn;

@@ -43,7 +43,7 @@ PROTOTYPES = {
     "iic_local_epilogue_workspace_bytes": (_sz, [_i, _i, _i]),
     "iic_local_epilogue": (_i, [_p, _i, _i, _i, _d, _p, _p, _p, _p, _p, _p, _p, _p]),
     "iic_local_backward": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
-                                _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+                                _i, _i, _i, _i, _i, _i, _i, _i, _i, _p, _p, _p, _p, _p, _ll, _ll, _p]),
     "iic_local_joint_from_logits": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, C.c_float,
                                          _p, _p, _sz, _p, _p]),
     "iic_local_joint_partials": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _p, _ll, _ll, _ll,
@@ -51,11 +51,11 @@ PROTOTYPES = {
     "iic_finish_workspace_bytes": (_sz, []),
     "iic_finish": (_i, [_p, _i, _p, _ll, _p, _p, _p, _i, _i, _ll, _i, _p]),
     "iic_local_backward_from_logits": (_i, [_p, _ll, _ll, _ll, _p, _ll, _ll, _ll, _i, _i, _i, _i, _i, C.c_float,
-                                            _p, _p, _p, _p, _p, _p]),
+                                            _p, _p, _p, _p, _p, _ll, _ll, _p]),
     "iic_global_joint_workspace_bytes": (_sz, [_i, _ll, _i]),
     "iic_global_joint": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _p, _sz, _p, _p]),
     "iic_global_epilogue": (_i, [_p, _i, _d, _i, _p, _p, _p, _p]),
-    "iic_global_backward": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _d, _i, _p, _p, _p, _p, _p, _p]),
+    "iic_global_backward": (_i, [_p, _ll, _p, _ll, _ll, _i, _p, _d, _i, _p, _p, _p, _p, _p, _ll, _ll, _p]),
     "iic_uda_workspace_bytes": (_sz, [_i]),
     "iic_uda_forward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _i, _p, _p]),
     "iic_uda_backward": (_i, [_p, _p, _ll, _i, _ll, _i, _d, _p, _i, _p, _p, _p]),

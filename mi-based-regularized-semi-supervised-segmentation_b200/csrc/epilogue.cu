@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
     const float* __restrict__ x, long long x_sn, const float* __restrict__ y, long long y_sn, long long N,
     int K, const double* __restrict__ J, double lamb, int symmetric, const float* __restrict__ g_loss,
     const float* __restrict__ g_no_lamb, const float* __restrict__ gP, float* __restrict__ gx,
-    float* __restrict__ gy,
+    float* __restrict__ gy, long long gx_sn, long long gy_sn,
     long long rows_per_cta) {
   extern __shared__ __align__(16) double sm[];
   double* scratch = sm;            // 33
@@ -330,8 +330,8 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
       ax = fmaf(GJ[(size_t)c * K + q], yr[q], ax);
       ay = fmaf(GJ[(size_t)q * K + c], xr[q], ay);
     }
-    gx[n * K + c] = ax;
-    gy[n * K + c] = ay;
+    gx[n * gx_sn + c] = ax;
+    gy[n * gy_sn + c] = ay;
   }
 }
 
@@ -432,7 +432,7 @@ extern "C" int iic_global_epilogue(const double* J, int K, double lamb, int symm
 extern "C" int iic_global_backward(const float* x, long long x_sn, const float* y, long long y_sn,
                                    long long N, int K, const double* J, double lamb, int symmetric,
                                    const float* g_loss, const float* g_no_lamb, const float* gP, float* gx,
-                                   float* gy, void* stream) {
+                                   float* gy, long long gx_sn, long long gy_sn, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
   IIC_REQUIRE(x && y && J && gx && gy, "iic_global_backward: null pointer");
   IIC_REQUIRE(N > 0 && K > 0 && K <= 128, "iic_global_backward: bad sizes N=%lld K=%d", N, K);
@@ -443,7 +443,9 @@ extern "C" int iic_global_backward(const float* x, long long x_sn, const float* 
   if (smem > 48 * 1024) {
     IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   }
-  kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy, rpc);
+  if (gx_sn <= 0) gx_sn = K;            // 0 = dense rows
+  if (gy_sn <= 0) gy_sn = K;
+  kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy, gx_sn, gy_sn, rpc);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -23,7 +23,8 @@ constexpr int BWD_TW = 32 * BWD_PXT;
 struct LocalBwdParams {
   View4 in;                 // staged input of this sweep (y for gx, x for gy)
   View4 m;                  // optional mask
-  float* out;               // dense (B,K,H,W) gradient
+  float* out;               // (B,K,H,W) gradient, rows and channel planes dense
+  long long out_sn;         // its sample stride in elements (K*H*W when the whole tensor is dense)
   const float* W;           // [patch][K][T*T][Kp]
   const float* grad_loss;   // device scalar or nullptr
   int B, K, Kp, H, Wd, pad;
@@ -135,7 +136,7 @@ __global__ void __launch_bounds__(BWD_WARPS * 32) local_bwd_kernel(const LocalBw
         for (int c = 0; c < OCB; ++c) {
           const int oc = oc0 + c;
           if (oc < P.K) {
-            float* dst = P.out + (((size_t)n * P.K + oc) * P.H + gh) * P.Wd + gw;
+            float* dst = P.out + (size_t)n * P.out_sn + ((size_t)oc * P.H + gh) * P.Wd + gw;
             float v[PXT];
 #pragma unroll
             for (int q = 0; q < PXT; ++q) v[q] = acc[c][q];
@@ -197,21 +198,24 @@ static int dispatch_ocb(int ocb, const LocalBwdParams& P, dim3 grid, size_t smem
 namespace iic {
 int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                      const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                      cudaStream_t st);
+                      const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, long long gx_sn,
+                      long long gy_sn, int sms, cudaStream_t st);
 int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                       int from_logits, float inv_temp, cudaStream_t st);
+                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, long long gx_sn,
+                       long long gy_sn, int sms, int from_logits, float inv_temp, cudaStream_t st);
 int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                      long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
-                     const float* grad_loss, float* gx, float* gy, cudaStream_t st);
+                     const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
 int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                        long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
-                       const float* grad_loss, float* gx, float* gy, cudaStream_t st);
+                       const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
+int local_bwd_tcrb10h_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
+                          const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
 int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
-                         const float* grad_loss, float* gx, float* gy, cudaStream_t st);
+                         const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
 }
 using namespace iic;
 
@@ -221,8 +225,10 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
                                   int B, int K, int H, int W, int pad,
                                   int patch_h, int patch_w, int step_h, int step_w,
                                   float* Wx, float* Wy, const float* grad_loss,
-                                  float* gx, float* gy, void* stream) {
+                                  float* gx, float* gy, long long gx_sn, long long gy_sn, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (gx_sn <= 0) gx_sn = (long long)K * H * W;          // 0 = the gradient tensor is dense
+  if (gy_sn <= 0) gy_sn = (long long)K * H * W;
   IIC_REQUIRE(x && y && Wx && Wy && gx && gy, "iic_local_backward: null pointer");
   IIC_REQUIRE(B > 0 && K > 0, "iic_local_backward: empty batch or channel dimension");
   IIC_REQUIRE(pad >= 0 && pad <= 7, "iic_local_backward: padding %d unsupported (0..7)", pad);
@@ -239,28 +245,31 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
     // wide cluster heads (K = 128): tcgen05 3xTF32 sweeps (local_bwd_tc.cu)
     if (!options().no_tc) {
       const int rc_tc = local_bwd_tc_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                         gx, gy, st);
+                                         gx, gy, gx_sn, gy_sn, st);
       if (rc_tc >= 0) return rc_tc;
       // 10 clusters, padding 1 (config 2): row-block tensor-core sweeps with the leftover-slot MMA (local_bwd_tcrb10.cu)
       if (!options().no_tc10) {
-        const int rc_10 = local_bwd_tcrb10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                               gx, gy, st);
+        // fp16-split variant (6 MMAs per source row and tile) by default; tc10_tf32 selects the tf32 + bf16 one (8 MMAs)
+        const int rc_10 = options().tc10_tf32 ? local_bwd_tcrb10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
+                                                                      grad_loss, gx, gy, gx_sn, gy_sn, st)
+                                              : local_bwd_tcrb10h_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
+                                               gx, gy, gx_sn, gy_sn, st);
         if (rc_10 >= 0) return rc_10;
       }
       // the reference's default cluster count (16 <= K <= 24), padding 1 or 3: row-block tensor-core sweeps
       // (local_bwd_tcrb.cu; at padding 1 only when the map has enough row blocks to fill the SMs, decided inside)
       {
         const int rc_rb = local_bwd_tcrb_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                             gx, gy, st);
+                                             gx, gy, gx_sn, gy_sn, st);
         if (rc_rb >= 0) return rc_rb;
       }
     }
     int rc = options().no_fast ? -1
                  : local_bwd_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
-                                      grad_loss, gx, gy, sms, 0, 1.f, st);
+                                      grad_loss, gx, gy, gx_sn, gy_sn, sms, 0, 1.f, st);
     if (rc < 0)
       rc = local_bwd_tma_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                             gx, gy, sms, st);
+                             gx, gy, gx_sn, gy_sn, sms, st);
     if (rc >= 0) return rc;
   }
 
@@ -292,8 +301,8 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
   dim3 grid((unsigned)per, n_patches);
 
   for (int sweep = 0; sweep < 2; ++sweep) {
-    if (sweep == 0) { P.in = {y, y_sn, y_sc, y_sh}; P.out = gx; P.W = Wx; }
-    else            { P.in = {x, x_sn, x_sc, x_sh}; P.out = gy; P.W = Wy; }
+    if (sweep == 0) { P.in = {y, y_sn, y_sc, y_sh}; P.out = gx; P.out_sn = gx_sn; P.W = Wx; }
+    else            { P.in = {x, x_sn, x_sc, x_sh}; P.out = gy; P.out_sn = gy_sn; P.W = Wy; }
     int rc;
     switch (T) {
       case 1:  rc = dispatch_ocb<1>(ocb, P, grid, smem, st); break;
@@ -315,13 +324,15 @@ extern "C" int iic_local_backward_from_logits(const float* lx, long long x_sn, l
                                               const float* ly, long long y_sn, long long y_sc, long long y_sh,
                                               int B, int K, int H, int W, int pad, float inv_temperature,
                                               const float* Wx, const float* Wy, const float* grad_loss,
-                                              float* g_lx, float* g_ly, void* stream) {
+                                              float* g_lx, float* g_ly, long long gx_sn, long long gy_sn, void* stream) {
   cudaStream_t st = (cudaStream_t)stream;
+  if (gx_sn <= 0) gx_sn = (long long)K * H * W;
+  if (gy_sn <= 0) gy_sn = (long long)K * H * W;
   IIC_REQUIRE(lx && ly && Wx && Wy && g_lx && g_ly, "iic_local_backward_from_logits: null pointer");
   const int sms = sm_count_cached(current_device());
   IIC_REQUIRE(sms > 0, "iic_local_backward_from_logits: no device");
   const int rc = local_bwd_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                    g_lx, g_ly, sms, 1, inv_temperature, st);
+                                    g_lx, g_ly, gx_sn, gy_sn, sms, 1, inv_temperature, st);
   if (rc < 0) {
     set_error("iic_local_backward_from_logits: shape not covered by the fused kernel (needs padding 1, K == 10, "
               "W %% 4 == 0, W <= 248, 16-byte aligned rows)");

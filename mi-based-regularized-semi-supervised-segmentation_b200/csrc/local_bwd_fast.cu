@@ -53,6 +53,7 @@ struct BwdFastParams {
   const float* grad_loss;
   float* gx;
   float* gy;
+  long long gx_sn, gy_sn;    // sample strides of the gradient tensors in elements (channel planes and rows are dense)
   // FROM_LOGITS: the maps are logits; gx / gy receive the gradient with respect to the logits
   const float* lx; long long lx_sn, lx_sc, lx_sh;
   const float* ly; long long ly_sn, ly_sc, ly_sh;
@@ -268,7 +269,7 @@ local_bwd_fast_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_con
         }
       }
       if (active) {
-        float* out = (sweep == 0 ? P.gx : P.gy) + (((size_t)n * P.K + oc0) * P.H + (h0 + rr)) * P.W + col0 + NPX * q;
+        float* out = (sweep == 0 ? P.gx + (size_t)n * P.gx_sn : P.gy + (size_t)n * P.gy_sn) + ((size_t)oc0 * P.H + (h0 + rr)) * P.W + col0 + NPX * q;
         const size_t cs = (size_t)P.H * P.W;
 #pragma unroll
         for (int c = 0; c < KB / 2; ++c) {
@@ -296,8 +297,8 @@ static int launch_bwd_fast(const CUtensorMap& mx, const CUtensorMap& my, const B
 // 0 = launched, 1 = error, -1 = not eligible (caller falls back to the other kernels)
 int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                       int from_logits, float inv_temp, cudaStream_t st) {
+                       const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, long long gx_sn,
+                       long long gy_sn, int sms, int from_logits, float inv_temp, cudaStream_t st) {
   using namespace bwdfast;
   if (pad != 1 && pad != 3) return -1;
   // output-channel block: 10 for the udaiic cluster counts (10, 20), 8 for other multiples of 8 (.., 128)
@@ -307,7 +308,7 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   const int WROW = (KB + 3) & ~3;
   if (W % 4 != 0 || W < 4) return -1;
   if (from_logits && W > 248) return -1;
-  if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
+  if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15) || (gx_sn & 3) || (gy_sn & 3)) return -1;
   const int T = 2 * pad + 1, T2 = T * T, Kp = (K + 3) & ~3;
   const int CB = from_logits ? 10 : (KB == 10 ? 5 : 4);   // the fused softmax needs all K channels in one stage
   const int nthreads = 512, stages = from_logits ? 2 : (pad == 1 ? 4 : 3);
@@ -328,7 +329,7 @@ int local_bwd_fast_try(const float* x, long long x_sn, long long x_sc, long long
   P.stage_bytes = (P.box_bytes + 127u) & ~127u;
   const size_t smem = (size_t)P.stage_bytes * stages;
   if (smem > 226 * 1024) return -1;
-  P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
+  P.grad_loss = grad_loss; P.gx = gx; P.gy = gy; P.gx_sn = gx_sn; P.gy_sn = gy_sn;
   P.lx = x; P.lx_sn = x_sn; P.lx_sc = x_sc; P.lx_sh = x_sh;
   P.ly = y; P.ly_sn = y_sn; P.ly_sc = y_sc; P.ly_sh = y_sh;
   P.inv_temp = inv_temp;

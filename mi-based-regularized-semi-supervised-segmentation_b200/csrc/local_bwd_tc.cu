@@ -56,7 +56,8 @@ struct Params {
   int n_items;                  // B * ceil(H / 2)
   const float* wimg;            // [16 slices][9 taps]{fp32 [2 chunks][128 out][4 in], bf16 [wh, wl][128 out][8 in]}
   const float* grad_loss;       // device scalar or null
-  float* out;                   // (B, 128, H, W) dense
+  float* out;                   // (B, 128, H, W), channel planes dense
+  long long out_sn;             // sample stride of `out` in elements
   int dbg;                      // bring-up switches (IIC_TC_DBG): 1 no source loads, 2 no weight loads, 4 no transform, 8 no stores
 };
 
@@ -250,7 +251,7 @@ local_bwd_tc_kernel(const __grid_constant__ CUtensorMap maps, const Params P) {
       for (int orow = 0; orow < nrow; ++orow)
         for (int mt = 0; mt < ntile; ++mt) {
           const int c = mt * 128 + q4 * 32 + lane;
-          float* dst = P.out + (size_t)n * KC * plane + (size_t)(r + orow) * P.W + c;
+          float* dst = P.out + (size_t)n * P.out_sn + (size_t)(r + orow) * P.W + c;
 #pragma unroll 1
           for (int ch = 0; ch < KC / 32; ++ch) {
             uint32_t v[32];
@@ -304,7 +305,7 @@ size_t local_bwd_tc_image_bytes(int K, int pad) {
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
 int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                      long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
-                     const float* grad_loss, float* gx, float* gy, cudaStream_t st) {
+                     const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st) {
   using namespace bwdtc;
   if (K != KC || pad != 1 || W % 4 != 0 || W > MAXW || W < 8) return -1;
   CUtensorMap mx, my;
@@ -324,9 +325,9 @@ int local_bwd_tc_try(const float* x, long long x_sn, long long x_sc, long long x
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y);
   IIC_CHECK_CUDA(cudaGetLastError());
   const int dbg = tc::bringup_env("IIC_TC_DBG", 0);
-  Params Pgx{B, H, W, n_items, img_x, grad_loss, gx, dbg};     // dL/dx from y
+  Params Pgx{B, H, W, n_items, img_x, grad_loss, gx, gx_sn, dbg};     // dL/dx from y
   local_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(my, Pgx);
-  Params Pgy{B, H, W, n_items, img_y, grad_loss, gy, dbg};     // dL/dy from x
+  Params Pgy{B, H, W, n_items, img_y, grad_loss, gy, gy_sn, dbg};     // dL/dy from x
   local_bwd_tc_kernel<<<grid, NTHREADS, SMEM_BYTES, st>>>(mx, Pgy);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;

@@ -55,6 +55,7 @@ struct Params {
   const float* wimg;
   const float* grad_loss;
   float* out;
+  long long out_sn;             // sample stride of `out` in elements
 };
 
 // Wc[cin][ty*T+tx][Kp4] -> per (slice, tx) a tile {fp32 [2 chunks][T*KP rows][4 in], bf16 [wh, wl][T*KP rows][8 in]},
@@ -292,7 +293,7 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
               if (orow + h < rv) {
-                float* dst = P.out + (size_t)n * P.K * plane + (size_t)(r0 + orow + h) * P.W + c;
+                float* dst = P.out + (size_t)n * P.out_sn + (size_t)(r0 + orow + h) * P.W + c;
 #pragma unroll
                 for (int o = 0; o < 24; ++o)
                   if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
@@ -342,7 +343,7 @@ size_t local_bwd_tcrb_image_bytes(int K, int pad) {
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
 int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                        long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* Wx, float* Wy,
-                       const float* grad_loss, float* gx, float* gy, cudaStream_t st) {
+                       const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st) {
   using namespace bwdrb;
   if (K < 16 || K > 24 || (pad != 1 && pad != 3) || W % 4 != 0 || W < 8) return -1;
   // maps wider than one TMA box are cut into column panels: 128 columns (one pixel tile, no padding) when that divides
@@ -383,8 +384,8 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wx, img_x, K, Kp4, KP, NS, T);
   weight_image_kernel<<<(wthreads + 255) / 256, 256, 0, st>>>(Wy, img_y, K, Kp4, KP, NS, T);
   IIC_CHECK_CUDA(cudaGetLastError());
-  Params Pgx{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_x, grad_loss, gx};     // dL/dx from y
-  Params Pgy{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_y, grad_loss, gy};     // dL/dy from x
+  Params Pgx{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_x, grad_loss, gx, gx_sn};     // dL/dx from y
+  Params Pgy{B, H, W, K, KP, NS, R, nblk, n_items, PW, npanel, wslice, na, nraw, img_y, grad_loss, gy, gy_sn};     // dL/dy from x
   if (T == 3) {
     if (int rc = launch<3>(my, Pgx, grid, smem, st)) return rc;
     return launch<3>(mx, Pgy, grid, smem, st);

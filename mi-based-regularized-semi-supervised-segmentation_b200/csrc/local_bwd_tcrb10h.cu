@@ -1,15 +1,22 @@
-// Backward sweeps of the local IIC term on the tensor cores for 10 clusters, 3 x 3 window (BASELINE config 2: the
-// udaiic default head of the benchmark): row-block scheme of local_bwd_tcrb.cu with two changes that make it pay at
-// K = 10, where padding the 10 input channels to two 8-channel slices would cost as many MMAs as the FFMA2 kernel has
-// FMA time:
-//  * the reduction dimension of an MMA need not be "8 channels of one tap".  In the no-swizzle K-major layout the two
-//    16-byte chunks of an operand row are independent arrays, so the main MMAs take channels 0-7 (one per column tap tx),
-//    and ONE extra "leftover" MMA per source row takes the slots (ch 8, ch 9) x (tx 0, 1, 2): the transform warps write a
-//    second row buffer whose pixel row b holds those six tap-shifted values, the weight image a matching tile.
-//    8 MMAs (4 products) per source row and 128-pixel tile instead of 12.
-//  * the B*H image rows are dealt to the CTAs as equal contiguous shares cut into chunks of at most 16 rows (no tail
-//    wave; an item is a chunk, not a fixed block), and the whole weight image (12 KB) is loaded once per CTA.
+// Backward sweeps of the local IIC term on the tensor cores for 10 clusters, 3 x 3 window (BASELINE config 2), fp16-split
+// variant of local_bwd_tcrb10.cu.  Same pipeline (TMA row loads, transform warps, four issuing warps, double-buffered
+// TMEM accumulators, coalesced drain); what changes is how fp32 accuracy is obtained from the tensor pipe:
+//   local_bwd_tcrb10.cu   a*w = tf32(a)*tf32(w) [kind::tf32, K = 8 per MMA] + bf16 corrections [kind::f16, K = 16]:
+//                         8 MMAs per source row and 128-pixel tile, 128 bytes of operand per pixel written by the transform
+//   here                  a = a1 + a2, w = w1 + w2 with a1 = fp16(a), a2 = fp16(a - a1) (22 bits together), and
+//                         a*w = a1*w1 + a2*w1 + a1*w2 (+ a2*w2 ~ 2^-22, dropped).  kind::f16 takes K = 16 slots per MMA, and a
+//                         reduction slot need not be "channel c of one part": the 30 (part, channel) products of a column
+//                         tap fill exactly two MMAs --
+//                           MMA 1: a1[0..7] | a1[8], a1[9], a2[0..5]    x   w1[0..7] | w1[8], w1[9], w1[0..5]
+//                           MMA 2: a2[6..9], a1[0..3] | a1[4..9], 0, 0  x   w1[6..9], w2[0..3] | w2[4..9], 0, 0
+//                         6 MMAs per source row and tile, 64 bytes of operand per pixel.  The kernel is bound by shared-memory
+//                         operand traffic (MMA fetch + transform), so this is where the time goes down.
+// fp16 range: the maps are probabilities (<= 1), scaled by 2^8 before the split so that the second part stays normal
+// down to 2^-22 of the first; the coefficients are scaled by a power of two that brings their largest magnitude to
+// [2^12, 2^13) (found by every CTA from the 2 x 900 coefficients while it builds its weight images); both scales are
+// exact and are undone in the drain.
 //   out[n,o,r,c] = g * sum_{cin,ty,tx} Wc[cin][ty*3+tx][o] * src[n,cin,r+ty-1,c+tx-1]     (iic_loss.py:123, backward)
+#include <cuda_fp16.h>
 #include <stdlib.h>
 
 #include "common.cuh"
@@ -17,7 +24,7 @@
 #include "tma.cuh"
 
 namespace iic {
-namespace bwdrb10 {
+namespace bwdrb10h {
 using namespace tc;
 
 constexpr int T = 3, PAD = 1;
@@ -27,17 +34,19 @@ constexpr int RMAX = 8;                  // output rows per item: 8 x 2 tiles x 
 constexpr int TBUF = 2 * RMAX * KP;      // TMEM columns of one accumulator buffer
 constexpr int APX = 272;
 constexpr int MAXW = 248;
-constexpr int A_PART = 2 * APX * 16;     // 8704
-constexpr int A_ROW = 2 * A_PART;        // 17408: fp32 part + bf16 part
-constexpr int A_SLOT = 2 * A_ROW;        // main row buffer + leftover row buffer
-constexpr int NA = 4;
+constexpr int A_CHUNK = APX * 16;        // one 16-byte chunk array: pixel b of the buffer at b * 16
+constexpr int A_SLOT = 4 * A_CHUNK;      // 17408: the four chunks (c0 c1 | c2 c3) of one source row
+constexpr int NA = 6;
 constexpr int RAW_SLOT = 10 * 256 * 4;   // 10240
 constexpr int NRAW = 6;
 constexpr int WROWS = T * KP;            // 48 rows per weight chunk
-constexpr int W_TILE = 4 * WROWS * 16;   // 3072
-constexpr int W_IMG = 4 * W_TILE;        // tx 0, 1, 2 and the leftover tile
+constexpr int W_TILE = 2 * WROWS * 16;   // 1536: one MMA's B operand (two chunks)
+constexpr int W_IMG = 6 * W_TILE;        // (tx 0, 1, 2) x (MMA 1, MMA 2)
 constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
 constexpr int SMEM_BYTES = NA * A_SLOT + 2 * W_IMG + NRAW * RAW_SLOT + 1024;   // both sweeps' weight images stay resident
+constexpr float A_SCALE = 256.f;         // 2^8
+constexpr int A_SCALE_LOG2 = 8;
+constexpr int W_TARGET_LOG2 = 12;        // largest |coefficient| scaled into [2^12, 2^13)
 
 
 
@@ -57,26 +66,40 @@ struct Params {
   long long out_sn[2];          // sample strides of the two gradient tensors in elements
 };
 
-// Wc[cin][ty*3+tx][Kp4] -> tiles tx = 0..2 (input channels 0-7) and the leftover tile (slots (ch 8, ch 9) x tx);
-// each tile {fp32 [2 chunks][48 rows][4 slots], bf16 [wh, wl][48 rows][8 slots]}, rows ordered (2-ty)*16 + o.
-// Every CTA builds both sweeps' images (2 x 12 KB from 2 x 3.6 KB of L2-resident coefficients) straight into its own
-// shared memory: no extra launch, no scratch allocation.  e = row in [0, 2 * 4 * 48).
-__device__ __forceinline__ void build_weight_row(const float* __restrict__ Wc, unsigned char* img, int e, int K, int Kp4) {
-  const int row = e % WROWS, tile = e / WROWS;
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {          // a at the lower address
+  const __half2 p = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&p);
+}
+__device__ __forceinline__ uint4 pack_h8(const float* v) {
+  return make_uint4(pack_h2(v[0], v[1]), pack_h2(v[2], v[3]), pack_h2(v[4], v[5]), pack_h2(v[6], v[7]));
+}
+// v -> (h, l): h = fp16(v), l = fp16(v - h)
+__device__ __forceinline__ void split_h(float v, float& h, float& l) {
+  h = __half2float(__float2half_rn(v));
+  l = __half2float(__float2half_rn(v - h));
+}
+
+// Wc[cin][ty*3+tx][Kp4] -> per column tap tx the two B operands of the header comment, each [2 chunks][48 rows][8 fp16],
+// rows ordered (2-ty)*16 + o, values scaled by 2^wexp.  Every CTA builds both sweeps' images (2 x 9 KB from 2 x 3.6 KB of
+// L2-resident coefficients) straight into its own shared memory.  e = row in [0, 3 * 48).
+__device__ __forceinline__ void build_weight_row(const float* __restrict__ Wc, unsigned char* img, int e, int K, int Kp4, float wscale) {
+  const int row = e % WROWS, tx = e / WROWS;
   const int ty = T - 1 - row / KP, o = row % KP;
-  float v[8];
+  float w1[10], w2[10];
 #pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    int cin, tx;
-    if (tile < 3) { cin = q; tx = tile; }
-    else { cin = 8 + (q & 1); tx = q >> 1; }                 // slots (8,tx0) (9,tx0) (8,tx1) (9,tx1) (8,tx2) (9,tx2) - -
-    v[q] = (cin < K && o < K && tx < T) ? __ldg(Wc + ((size_t)cin * T * T + ty * T + tx) * Kp4 + o) : 0.f;
+  for (int c = 0; c < 10; ++c) {
+    const float v = (c < K && o < K) ? __ldg(Wc + ((size_t)c * T * T + ty * T + tx) * Kp4 + o) * wscale : 0.f;
+    split_h(v, w1[c], w2[c]);
   }
-  float4* t4 = reinterpret_cast<float4*>(img) + (size_t)tile * (4 * WROWS);
-  t4[row] = make_float4(v[0], v[1], v[2], v[3]);
-  t4[WROWS + row] = make_float4(v[4], v[5], v[6], v[7]);
-  reinterpret_cast<uint4*>(t4)[2 * WROWS + row] = pack8<false>(v);
-  reinterpret_cast<uint4*>(t4)[3 * WROWS + row] = pack8<true>(v);
+  const float c0[8] = {w1[0], w1[1], w1[2], w1[3], w1[4], w1[5], w1[6], w1[7]};
+  const float c1[8] = {w1[8], w1[9], w1[0], w1[1], w1[2], w1[3], w1[4], w1[5]};
+  const float c2[8] = {w1[6], w1[7], w1[8], w1[9], w2[0], w2[1], w2[2], w2[3]};
+  const float c3[8] = {w2[4], w2[5], w2[6], w2[7], w2[8], w2[9], 0.f, 0.f};
+  uint4* t = reinterpret_cast<uint4*>(img + (size_t)tx * 2 * W_TILE);
+  t[row] = pack_h8(c0);
+  t[WROWS + row] = pack_h8(c1);
+  t[2 * WROWS + row] = pack_h8(c2);
+  t[3 * WROWS + row] = pack_h8(c3);
 }
 
 // the chunk of image rows that starts at global row r (rows of all images, B*H) inside the CTA share [r, R1)
@@ -92,10 +115,11 @@ __device__ __forceinline__ Chunk next_chunk(long long r, long long R1, int H, in
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
-local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
+local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], a_full[NA], a_empty[NA], w_full, accum_full[2], tmem_ready[2];
   __shared__ uint32_t tmem_base_s;
+  __shared__ float wmax_s[4];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* a_ring = smem;
   unsigned char* w_img = smem + NA * A_SLOT;
@@ -187,21 +211,19 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
             const int ty_max = q < T - 1 ? q : T - 1;
             const int ty_min = q - c.nr + 1 > 0 ? q - c.nr + 1 : 0;
             const uint32_t nn = (uint32_t)((ty_max - ty_min + 1) * KP);
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((nn >> 3) << 17) | (8u << 24);
-            const uint32_t idesc_bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((nn >> 3) << 17) | (8u << 24);
+            // kind::f16, fp16 operands (a_format = b_format = 0), fp32 accumulator, M = 128, N = nn
+            const uint32_t idesc_f16 = (1u << 4) | ((nn >> 3) << 17) | (8u << 24);
             const uint32_t d_tmem = tmem_base + (uint32_t)(buf * TBUF + (mt * RMAX + (q - ty_max)) * KP);
-            const uint64_t a_main = make_desc_kmajor_noswz(smem_u32(a_ring + a * A_SLOT), APX * 16) + (uint64_t)(mt * 128 + 8 - PAD);
-            const uint64_t a_left = a_main + (uint64_t)(A_ROW / 16);
+            // chunks c0 | c1 of buffer pixel mt*128 + 8 - PAD (+ tx); c2 | c3 are two chunk arrays further on
+            const uint64_t a_12 = make_desc_kmajor_noswz(smem_u32(a_ring + a * A_SLOT), A_CHUNK) + (uint64_t)(mt * 128 + 8 - PAD);
+            const uint64_t a_34 = a_12 + (uint64_t)(2 * A_CHUNK / 16);
             const uint64_t b_base = w_base + (uint64_t)((T - 1 - ty_max) * KP);
 #pragma unroll
             for (int tx = 0; tx < T; ++tx) {
-              const uint64_t bt = b_base + (uint64_t)tx * (4 * WROWS);
-              umma_bf16(d_tmem, a_main + (uint64_t)(A_PART / 16 + tx), bt + 2 * WROWS, idesc_bf16);
-              umma_tf32(d_tmem, a_main + (uint64_t)tx, bt, idesc);
+              const uint64_t bt = b_base + (uint64_t)tx * (2 * W_TILE / 16);
+              umma_bf16(d_tmem, a_12 + (uint64_t)tx, bt, idesc_f16);
+              umma_bf16(d_tmem, a_34 + (uint64_t)tx, bt + (uint64_t)(W_TILE / 16), idesc_f16);
             }
-            const uint64_t bl = b_base + (uint64_t)3 * (4 * WROWS);       // leftover tile: taps are inside the row
-            umma_bf16(d_tmem, a_left + (uint64_t)(A_PART / 16), bl + 2 * WROWS, idesc_bf16);
-            umma_tf32(d_tmem, a_left, bl, idesc);
           }
           if (par == 0) TRACE(1 + mt, 2);
           umma_commit(&a_empty[a]);
@@ -236,29 +258,23 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
         mbar_wait(&raw_full[s], sph, 4);
         if (tid == 0 && wid == 4) TRACE(3, 2);
         unsigned char* am = a_ring + a * A_SLOT;
-        unsigned char* al = am + A_ROW;
         const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_SLOT);
         for (int px = tid; px < SW; px += 128) {
-          float v[8];
+          float h[10], l[10];
 #pragma unroll
-          for (int ch = 0; ch < 8; ++ch) v[ch] = raw[ch * SW + px];
-          const int off = (px + 4) * 16;
-          *reinterpret_cast<float4*>(am + off) = make_float4(v[0], v[1], v[2], v[3]);
-          *reinterpret_cast<float4*>(am + off + APX * 16) = make_float4(v[4], v[5], v[6], v[7]);
-          *reinterpret_cast<uint4*>(am + A_PART + off) = pack8<true>(v);
-          *reinterpret_cast<uint4*>(am + A_PART + off + APX * 16) = pack8<false>(v);
-          float w[8];
-#pragma unroll
-          for (int tx = 0; tx < 3; ++tx) {
-            const bool in = px + tx < SW;
-            w[2 * tx] = (in && P.K > 8) ? raw[8 * SW + px + tx] : 0.f;
-            w[2 * tx + 1] = (in && P.K > 9) ? raw[9 * SW + px + tx] : 0.f;
+          for (int ch = 0; ch < 10; ++ch) {
+            const float v = ch < P.K ? raw[ch * SW + px] * A_SCALE : 0.f;
+            split_h(v, h[ch], l[ch]);
           }
-          w[6] = 0.f; w[7] = 0.f;
-          *reinterpret_cast<float4*>(al + off) = make_float4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<float4*>(al + off + APX * 16) = make_float4(w[4], w[5], w[6], w[7]);
-          *reinterpret_cast<uint4*>(al + A_PART + off) = pack8<true>(w);
-          *reinterpret_cast<uint4*>(al + A_PART + off + APX * 16) = pack8<false>(w);
+          const int off = (px + 4) * 16;
+          const float c0[8] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
+          const float c1[8] = {h[8], h[9], l[0], l[1], l[2], l[3], l[4], l[5]};
+          const float c2[8] = {l[6], l[7], l[8], l[9], h[0], h[1], h[2], h[3]};
+          const float c3[8] = {h[4], h[5], h[6], h[7], h[8], h[9], 0.f, 0.f};
+          *reinterpret_cast<uint4*>(am + off) = pack_h8(c0);
+          *reinterpret_cast<uint4*>(am + A_CHUNK + off) = pack_h8(c1);
+          *reinterpret_cast<uint4*>(am + 2 * A_CHUNK + off) = pack_h8(c2);
+          *reinterpret_cast<uint4*>(am + 3 * A_CHUNK + off) = pack_h8(c3);
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[s]);
@@ -274,7 +290,8 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
   } else if (wid >= 14) {
     // ===== epilogue: drain, store, zero =====
     const int q4 = wid & 3;
-    const float g = P.grad_loss ? __ldg(P.grad_loss) : 1.f;
+    float unscale = 1.f;
+    const float g0 = P.grad_loss ? __ldg(P.grad_loss) : 1.f;
     const size_t plane = (size_t)P.H * P.W;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     auto zero_accumulators = [&](int buf) {
@@ -287,14 +304,33 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
     };
     zero_accumulators(0);
     zero_accumulators(1);
-    // the weight images: these four warps are idle until the first chunk is finished
-    for (int e = threadIdx.x - 14 * 32; e < 2 * 4 * WROWS; e += 128) {
-      const int sweep = e / (4 * WROWS);
-      build_weight_row(P.Wc[sweep], w_img + sweep * W_IMG, e - sweep * 4 * WROWS, P.K, P.Kp4);
+    // the weight images: these four warps are idle until the first chunk is finished.  First the power-of-two scale that
+    // brings the largest coefficient magnitude into [2^12, 2^13) (every CTA finds it from the 2 x K*9*Kp4 coefficients,
+    // L2-resident), then the fp16 (w1, w2) images.
+    {
+      const int etid = threadIdx.x - 14 * 32;
+      const int ncoef = P.K * T * T * P.Kp4;
+      float mx = 0.f;
+      for (int e = etid; e < 2 * ncoef; e += 128) mx = fmaxf(mx, fabsf(__ldg(P.Wc[e >= ncoef] + (e >= ncoef ? e - ncoef : e))));
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) wmax_s[q4] = mx;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+      mx = fmaxf(fmaxf(wmax_s[0], wmax_s[1]), fmaxf(wmax_s[2], wmax_s[3]));
+      int wexp = 0;
+      if (mx > 0.f && mx < 3.0e38f) wexp = W_TARGET_LOG2 - ilogbf(mx);
+      if (wexp > 100) wexp = 100;                       // denormal-sized coefficients: keep the scale finite
+      const float wscale = scalbnf(1.f, wexp);
+      unscale = scalbnf(1.f, -(wexp + A_SCALE_LOG2));
+      for (int e = etid; e < 2 * 3 * WROWS; e += 128) {
+        const int sweep = e / (3 * WROWS);
+        build_weight_row(P.Wc[sweep], w_img + sweep * W_IMG, e - sweep * 3 * WROWS, P.K, P.Kp4, wscale);
+      }
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     __syncwarp();
     if (lane == 0) mbar_arrive(&w_full);
+    const float g = g0 * unscale;
     int i = 0;
     for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
@@ -356,13 +392,13 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, i
              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-}  // namespace bwdrb10
+}  // namespace bwdrb10h
 
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
-int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+int local_bwd_tcrb10h_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
                          const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st) {
-  using namespace bwdrb10;
+  using namespace bwdrb10h;
   if ((K != 9 && K != 10) || pad != 1 || W % 4 != 0 || W > MAXW || W < 8) return -1;
   const int device = current_device();
   const int sms = sm_count_cached(device);
@@ -371,11 +407,11 @@ int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long lo
   CUtensorMap mx, my;
   if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh)) return -1;
   if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh)) return -1;
-  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10_kernel), (int)(SMEM_BYTES)));
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10h_kernel), (int)(SMEM_BYTES)));
   const int Kp4 = (K + 3) & ~3;
   Params P{B, H, W, K, {Wx, Wy}, Kp4, grad_loss, {gx, gy}, {gx_sn, gy_sn}};
   // one launch, two sweeps per CTA: dL/dx from y (sweep 0), then dL/dy from x (sweep 1)
-  local_bwd_tcrb10_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
+  local_bwd_tcrb10h_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -31,6 +31,7 @@ struct BwdTmaParams {
   const float* grad_loss;
   float* gx;
   float* gy;
+  long long gx_sn, gy_sn;   // sample strides of the gradient tensors in elements
 };
 
 template <int T, int OCB>
@@ -164,7 +165,7 @@ local_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_cons
       const int n = it / (P.tiles_h * P.tiles_w);
       const int tt = it - n * (P.tiles_h * P.tiles_w);
       const int row0 = (tt / P.tiles_w) * BT_ROWS + 2 * wid, col0 = (tt % P.tiles_w) * BT_TW + 4 * lane;
-      float* out = sweep == 0 ? P.gx : P.gy;
+      float* out = sweep == 0 ? P.gx + (size_t)n * P.gx_sn : P.gy + (size_t)n * P.gy_sn;
       if (col0 < P.W) {
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
@@ -173,7 +174,7 @@ local_bwd_tma_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_cons
 #pragma unroll
             for (int c = 0; c < NP; ++c) {
               const int oc = 2 * c;
-              float* dst = out + (((size_t)n * P.K + oc) * P.H + row) * P.W + col0;
+              float* dst = out + ((size_t)oc * P.H + row) * P.W + col0;
               if (oc < P.K)
                 *reinterpret_cast<float4*>(dst) = make_float4(acc[c][r][0].x, acc[c][r][1].x, acc[c][r][2].x, acc[c][r][3].x);
               if (oc + 1 < P.K)
@@ -200,12 +201,12 @@ static int launch_bwd_tma(const CUtensorMap& mx, const CUtensorMap& my, const Bw
 // 0 = launched, 1 = error, -1 = not eligible (caller falls back to the generic kernel)
 int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y,
                       long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
-                      const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, int sms,
-                      cudaStream_t st) {
+                      const float* Wx, const float* Wy, const float* grad_loss, float* gx, float* gy, long long gx_sn,
+                      long long gy_sn, int sms, cudaStream_t st) {
   const int T = 2 * pad + 1;
   if (T > 3 || K > 12 || K < 1) return -1;
   if (W % 4 != 0) return -1;
-  if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15)) return -1;
+  if ((reinterpret_cast<uintptr_t>(gx) & 15) || (reinterpret_cast<uintptr_t>(gy) & 15) || (gx_sn & 3) || (gy_sn & 3)) return -1;
   BwdTmaParams P;
   P.B = B; P.K = K; P.Kp = (K + 3) & ~3; P.H = H; P.W = W; P.pad = pad;
   P.tiles_h = (H + BT_ROWS - 1) / BT_ROWS;
@@ -225,7 +226,7 @@ int local_bwd_tma_try(const float* x, long long x_sn, long long x_sc, long long 
   P.CB = CB; P.nchunk = K / CB;
   P.box_bytes = (unsigned)((size_t)CB * P.XR * BT_XP * 4);
   P.stage_bytes = (P.box_bytes + 127u) & ~127u;
-  P.Wx = Wx; P.Wy = Wy; P.grad_loss = grad_loss; P.gx = gx; P.gy = gy;
+  P.Wx = Wx; P.Wy = Wy; P.grad_loss = grad_loss; P.gx = gx; P.gy = gy; P.gx_sn = gx_sn; P.gy_sn = gy_sn;
   CUtensorMap mx, my;
   if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, BT_XP, P.XR, CB)) return -1;
   if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, BT_XP, P.XR, CB)) return -1;

@@ -179,23 +179,32 @@ def _local_epilogue(J, K, pad, lamda):
     return loss, Wx, Wy
 
 
-def _local_backward(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, step_w):
+def _local_backward_into(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, step_w, gx, gy):
+    """iic_local_backward writing into the given (B, K, H, W) tensors / channel-block views (dense rows and planes, any
+    sample stride); with several patches they must be zero-filled (the patches accumulate)."""
     lib = _lib.load()
     x, y = _w_contig(x), _w_contig(y)
     B, K, H, W = x.shape
     m, msn, msc, msh = _mask_args(mask, x)
-    npatch = lib.iic_local_num_patches(H, W, patch_h, patch_w, step_h, step_w)
-    alloc = torch.zeros if npatch > 1 else torch.empty
-    gx = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
-    gy = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
+    for g in (gx, gy):
+        assert g.shape == x.shape and g.stride(3) == 1 and g.stride(2) == W and g.stride(1) == H * W, (g.shape, g.stride())
     grad = grad.to(torch.float32).reshape(())
     with torch.cuda.device(x.device):
         rc = lib.iic_local_backward(x.data_ptr(), x.stride(0), x.stride(1), x.stride(2),
                                     y.data_ptr(), y.stride(0), y.stride(1), y.stride(2),
                                     _ptr(m), msn, msc, msh, B, K, H, W, pad, patch_h, patch_w, step_h, step_w,
                                     Wx.data_ptr(), Wy.data_ptr(), grad.data_ptr(), gx.data_ptr(), gy.data_ptr(),
-                                    _stream(x.device))
+                                    gx.stride(0), gy.stride(0), _stream(x.device))
     _lib.check(rc, "iic_local_backward")
+
+
+def _local_backward(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, step_w):
+    B, K, H, W = x.shape
+    npatch = _lib.load().iic_local_num_patches(H, W, patch_h, patch_w, step_h, step_w)
+    alloc = torch.zeros if npatch > 1 else torch.empty
+    gx = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
+    gy = alloc((B, K, H, W), dtype=torch.float32, device=x.device)
+    _local_backward_into(x, y, mask, Wx, Wy, grad, pad, patch_h, patch_w, step_h, step_w, gx, gy)
     return gx, gy
 
 
@@ -229,21 +238,27 @@ def _local_joint_logits(lx, ly, pad, inv_temperature):
     return J
 
 
-def _local_backward_logits(lx, ly, Wx, Wy, grad, pad, inv_temperature):
+def _local_backward_logits_into(lx, ly, Wx, Wy, grad, pad, inv_temperature, gx, gy):
     lib = _lib.load()
     lx, ly = _logit_maps(lx, ly)
     B, K, H, W = lx.shape
-    gx = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
-    gy = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
     grad = grad.to(torch.float32).reshape(())
     with torch.cuda.device(lx.device):
         rc = lib.iic_local_backward_from_logits(lx.data_ptr(), lx.stride(0), lx.stride(1), lx.stride(2),
                                                 ly.data_ptr(), ly.stride(0), ly.stride(1), ly.stride(2),
                                                 B, K, H, W, pad, float(inv_temperature), Wx.data_ptr(), Wy.data_ptr(),
-                                                grad.data_ptr(), gx.data_ptr(), gy.data_ptr(), _stream(lx.device))
+                                                grad.data_ptr(), gx.data_ptr(), gy.data_ptr(), gx.stride(0), gy.stride(0),
+                                                _stream(lx.device))
     if rc == _lib.UNSUPPORTED:
         raise FusedShapeUnsupported(lib.iic_b200_last_error().decode())
     _lib.check(rc, "iic_local_backward_from_logits")
+
+
+def _local_backward_logits(lx, ly, Wx, Wy, grad, pad, inv_temperature):
+    B, K, H, W = lx.shape
+    gx = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
+    gy = torch.empty((B, K, H, W), dtype=torch.float32, device=lx.device)
+    _local_backward_logits_into(lx, ly, Wx, Wy, grad, pad, inv_temperature, gx, gy)
     return gx, gy
 
 
@@ -281,11 +296,18 @@ def _global_epilogue(J, lamb, symmetric, want_losses):
 
 
 def _global_backward(x, y, J, lamb, symmetric, g_loss, g_no_lamb, gP):
-    lib = _lib.load()
-    x, y = _w_contig(x), _w_contig(y)
     N, K = x.shape
     gx = torch.empty((N, K), dtype=torch.float32, device=x.device)
     gy = torch.empty((N, K), dtype=torch.float32, device=x.device)
+    _global_backward_into(x, y, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy)
+    return gx, gy
+
+
+def _global_backward_into(x, y, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy):
+    lib = _lib.load()
+    x, y = _w_contig(x), _w_contig(y)
+    N, K = x.shape
+    assert gx.shape == x.shape and gy.shape == x.shape and gx.stride(1) == 1 and gy.stride(1) == 1
     if g_loss is not None:
         g_loss = g_loss.to(torch.float32).reshape(())
     if g_no_lamb is not None:
@@ -295,10 +317,9 @@ def _global_backward(x, y, J, lamb, symmetric, g_loss, g_no_lamb, gP):
     with torch.cuda.device(x.device):
         rc = lib.iic_global_backward(x.data_ptr(), x.stride(0), y.data_ptr(), y.stride(0), N, K, J.data_ptr(),
                                      float(lamb), int(symmetric), _ptr(g_loss), _ptr(g_no_lamb), _ptr(gP),
-                                     gx.data_ptr(), gy.data_ptr(),
+                                     gx.data_ptr(), gy.data_ptr(), gx.stride(0), gy.stride(0),
                                      _stream(x.device))
     _lib.check(rc, "iic_global_backward")
-    return gx, gy
 
 
 def _as_oci(t: torch.Tensor) -> Tuple[int, int, int]:
@@ -745,7 +766,7 @@ def _finish_terms(terms, check_simplex):
                 it.kind, it.K, it.lamda = _lib.ITEM_LOCAL, K, t.lamda
                 it.slots, it.layout, it.n_slots, it.nb, it.slot_stride = ws.data_ptr(), info.layout, info.n_slots, info.nb, info.slot_stride
                 it.pad, it.n_patches = t.pad, npatch
-                it.epilogue_workspace = st.epilogue_ws(K, t.pad, npatch, dev).data_ptr() if K > 32 else None
+                it.epilogue_workspace = st.epilogue_ws(K, t.pad, npatch, dev).data_ptr()      # used when the epilogue is not fused
                 it.loss_out, it.Wx, it.Wy = loss_buf[lo:].data_ptr(), Wx.data_ptr(), Wy.data_ptr()
                 E = npatch * T * T * K * K
                 recs.append(dict(kind="local", x=x, y=y, mask=m, Wx=Wx, Wy=Wy, loss=loss_buf[lo], K=K, T=T, npatch=npatch,
@@ -799,13 +820,61 @@ def _finish_terms(terms, check_simplex):
     return recs
 
 
+def _block_of(t: torch.Tensor):
+    """(base, n0, c0) when `t` is the block ``base.view(N, C, *spatial)[n0:n0+B, c0:c0+K]`` of a contiguous tensor it is a
+    differentiable VIEW of -- what ``chunk`` / ``unbind`` / slicing of a batched cluster-head output give
+    (contrastyou/trainer/_utils.py:137-168, semi_seg/epocher.py:269-273).  The gradient of such a view can be written
+    straight into its block of the base's gradient instead of going through autograd's view backward (a zero-filled
+    full-size tensor plus a copy per view).  None for leaves and for anything that is not such a block."""
+    if t.is_leaf or t._base is None:
+        return None
+    base = t._base
+    if not (base.requires_grad and base.is_contiguous() and base.dtype == t.dtype and base.dim() >= t.dim()):
+        return None
+    N = base.shape[0]
+    if N == 0:
+        return None
+    if t.dim() == 4:
+        B, K, H, W = t.shape
+        if tuple(base.shape[-2:]) != (H, W):
+            return None
+        plane = H * W
+        C = base.numel() // (N * plane)
+        want = (C * plane, plane, W, 1)
+    else:
+        B, K = t.shape
+        plane = 1
+        C = base.numel() // N
+        want = (C, 1)
+    st = t.stride()
+    if any(sz > 1 and a != b for sz, a, b in zip(t.shape, st, want)):
+        return None
+    off = t.storage_offset() - base.storage_offset()
+    n0, rem = divmod(off, C * plane)
+    c0, r2 = divmod(rem, plane)
+    if off < 0 or r2 or n0 + B > N or c0 + K > C:
+        return None
+    return base, n0, c0
+
+
+def _block_view(G: torch.Tensor, like: torch.Tensor, n0: int, c0: int) -> torch.Tensor:
+    N = G.shape[0]
+    if like.dim() == 4:
+        B, K, H, W = like.shape
+        return G.view(N, -1, H, W)[n0:n0 + B, c0:c0 + K]
+    B, K = like.shape
+    return G.view(N, -1)[n0:n0 + B, c0:c0 + K]
+
+
 class IICTermsFunction(torch.autograd.Function):
     """The losses of one or many IIC terms -- local (iic_loss.py:107-149,171-186) and global (iic_loss.py:43-94) -- from
-    ONE finish launch.  apply(terms, check_simplex, *tensors): `terms` carries the geometry, `tensors` the differentiable
-    inputs (x, y of every term in order).  Outputs per local term: loss; per global term: loss, loss_no_lamb, P."""
+    ONE finish launch.  apply(terms, check_simplex, slots, *sources): `terms` carries geometry and the input views,
+    `sources` the distinct differentiable tensors behind them, `slots[2*i]`, `slots[2*i+1]` = (source index, block or
+    None) for x and y of term i.  Outputs per local term: loss; per global term: loss, loss_no_lamb, P.  In backward
+    every term's gradient kernel writes directly into its block of the source's gradient."""
 
     @staticmethod
-    def forward(ctx, terms, check_simplex, *tensors):
+    def forward(ctx, terms, check_simplex, slots, *sources):
         recs = _finish_terms(terms, check_simplex)
         outs, saved = [], []
         for r in recs:
@@ -818,40 +887,88 @@ class IICTermsFunction(torch.autograd.Function):
         ctx.save_for_backward(*saved)
         ctx.meta = [(t.__class__, getattr(t, "pad", None), getattr(t, "patch", None), getattr(t, "step", None),
                      getattr(t, "logits", False), getattr(t, "inv_temperature", 1.0), getattr(t, "lamb", None),
-                     getattr(t, "symmetric", True), r.get("mask") is not None) for t, r in zip(terms, recs)]
+                     getattr(t, "symmetric", True), r.get("mask") is not None, r.get("npatch", 1))
+                    for t, r in zip(terms, recs)]
+        ctx.slots = slots
+        ctx.src_meta = [(tuple(s_.shape), s_.device) for s_ in sources]
+        # a source whose distinct blocks tile it completely needs no zero fill
+        cover = [0] * len(sources)
+        seen = set()
+        for k, (si, blk) in enumerate(slots):
+            t = terms[k // 2]
+            v = t.x if k % 2 == 0 else t.y
+            if blk is not None and (si, blk) not in seen:
+                seen.add((si, blk))
+                cover[si] += v.numel()
+        ctx.covered = [c == s_.numel() for c, s_ in zip(cover, sources)]
         ctx.set_materialize_grads(False)
         return tuple(outs)
 
     @staticmethod
     def backward(ctx, *grads):
         sv = list(ctx.saved_tensors)
-        res, gi, si = [], 0, 0
-        for cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask in ctx.meta:
+        slots = ctx.slots
+        n_src = len(ctx.src_meta)
+        # which sources get a complete set of gradients (then their buffer need not be zeroed)
+        gi, need_zero, any_grad = 0, [False] * n_src, [False] * n_src
+        for ti, m in enumerate(ctx.meta):
+            n_out = 1 if m[0] is LocalTerm else 3
+            has = any(g is not None for g in grads[gi:gi + n_out])
+            gi += n_out
+            for k in (2 * ti, 2 * ti + 1):
+                si, blk = slots[k]
+                if has:
+                    any_grad[si] = True
+                if (blk is not None and not has) or (has and m[9] > 1):
+                    need_zero[si] = True          # a block nobody writes, or patches that accumulate into their output
+        G = [None] * n_src
+        written = set()
+
+        def target(k, like):
+            """Where the gradient of input k goes: (tensor to write into, accumulate-from-temp?)."""
+            si, blk = slots[k]
+            shape, dev = ctx.src_meta[si]
+            if G[si] is None:
+                zero = need_zero[si] or (blk is not None and not ctx.covered[si])
+                G[si] = (torch.zeros if zero else torch.empty)(shape, dtype=torch.float32, device=dev)
+            dst = G[si] if blk is None else _block_view(G[si], like, blk[0], blk[1])
+            if (si, blk) in written:
+                return torch.zeros_like(like, memory_format=torch.contiguous_format), dst      # second use: add afterwards
+            written.add((si, blk))
+            return dst, None
+
+        gi, si_ = 0, 0
+        for ti, (cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask, npatch) in enumerate(ctx.meta):
             if cls is LocalTerm:
-                x, y, Wx, Wy = sv[si:si + 4]
-                si += 4
+                x, y, Wx, Wy = sv[si_:si_ + 4]
+                si_ += 4
                 mask = None
                 if has_mask:
-                    mask = sv[si]
-                    si += 1
+                    mask = sv[si_]
+                    si_ += 1
                 g = grads[gi]
                 gi += 1
                 if g is None:
-                    res += [None, None]
-                elif logits:
-                    res += list(ops.local_backward_logits(x, y, Wx, Wy, g.contiguous(), pad, inv_t))
+                    continue
+                (gx, ax), (gy, ay) = target(2 * ti, x), target(2 * ti + 1, y)
+                if logits:
+                    _local_backward_logits_into(x, y, Wx, Wy, g.contiguous(), pad, inv_t, gx, gy)
                 else:
-                    res += list(ops.local_backward(x, y, mask, Wx, Wy, g.contiguous(), pad, patch[0], patch[1], step[0], step[1]))
+                    _local_backward_into(x, y, mask, Wx, Wy, g.contiguous(), pad, patch[0], patch[1], step[0], step[1], gx, gy)
             else:
-                x, y, J = sv[si:si + 3]
-                si += 3
+                x, y, J = sv[si_:si_ + 3]
+                si_ += 3
                 g1, g2, gP = grads[gi:gi + 3]
                 gi += 3
                 if g1 is None and g2 is None and gP is None:
-                    res += [None, None]
-                else:
-                    res += list(ops.global_backward(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP))
-        return (None, None, *res)
+                    continue
+                (gx, ax), (gy, ay) = target(2 * ti, x), target(2 * ti + 1, y)
+                _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
+            if ax is not None:
+                ax += gx
+            if ay is not None:
+                ay += gy
+        return (None, None, None, *[G[i] if any_grad[i] else None for i in range(n_src)])
 
 
 def iic_terms(terms, check_simplex=False):
@@ -867,8 +984,16 @@ def iic_terms(terms, check_simplex=False):
     for c0 in range(0, len(batch), MAX_TERMS_PER_FINISH):
         idx = batch[c0:c0 + MAX_TERMS_PER_FINISH]
         sub = [terms[i] for i in idx]
-        flat = [v for t in sub for v in (t.x, t.y)]
-        res = list(IICTermsFunction.apply(sub, check_simplex, *flat))
+        sources, index, slots = [], {}, []
+        for t in sub:
+            for v in (t.x, t.y):
+                blk = _block_of(v) if torch.is_grad_enabled() and v.requires_grad else None
+                src = blk[0] if blk is not None else v
+                if id(src) not in index:
+                    index[id(src)] = len(sources)
+                    sources.append(src)
+                slots.append((index[id(src)], (blk[1], blk[2]) if blk is not None else None))
+        res = list(IICTermsFunction.apply(sub, check_simplex, slots, *sources))
         for i, t in zip(idx, sub):
             if isinstance(t, LocalTerm):
                 out[i] = res.pop(0)

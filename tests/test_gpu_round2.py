@@ -62,12 +62,15 @@ def test_dispatch_branches_without_env(iic, cuda_device, B, K, H, W, pad, patch)
     _check_local(iic, cuda_device, B, K, H, W, pad, patch, 777 + B + K + W)
 
 
-@pytest.mark.parametrize("opt", ["tcp_p1", "tcrb_p1", "tc10_force", "no_tc", "no_fast", "no_tma", "no_fused_epilogue"])
+@pytest.mark.parametrize("opt", ["tcp_p1", "tcrb_p1", "tc10_force", "tc10_tf32", "no_tc", "no_fast", "no_tma", "no_fused_epilogue"])
 def test_forced_kernel_families(iic, cuda_device, opt):
     """The same small inputs through the kernel family a switch forces must agree with the oracle (and therefore with
     the default dispatch).  K = 20 / padding 1 for the packed joint and the row-block backward, K = 10 for the rest."""
     shape = (2, 20, 40, 64, 1, 512) if opt in ("tcp_p1", "tcrb_p1") else (2, 10, 40, 64, 1, 512)
-    with option(iic, opt, 1):
+    with contextlib.ExitStack() as stack:
+        stack.enter_context(option(iic, opt, 1))
+        if opt == "tc10_tf32":                          # small map: the K = 10 tensor-core backward must be forced as well
+            stack.enter_context(option(iic, "tc10_force", 1))
         a = _check_local(iic, cuda_device, *shape, seed=4242)
     b = _check_local(iic, cuda_device, *shape, seed=4242)
     assert abs(a[0] - b[0]) <= 2e-6 * abs(b[0])
