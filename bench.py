@@ -492,7 +492,7 @@ def run_b200(args):
                 out = step_fn(inp)
     torch.cuda.current_stream().wait_stream(side)
     torch.cuda.synchronize()
-    n_own, own_names = count_own_launches(torch, lambda: step_fn(sets[0])) if rank == 0 else (None, [])
+    n_own, own_names = count_own_launches(torch, lambda: step_fn(sets[0]))      # on EVERY rank: the step holds an exchange
     if use_graph:
         try:
             for inp in sets:
@@ -590,9 +590,12 @@ def run_b200(args):
             gathered.append(torch.cat(buf, 0).requires_grad_(t_.requires_grad) if rank == 0 else None)
         mg = {"loss_bits_identical_on_all_ranks": bool(identical)}
         if rank == 0:
-            iic_b200.set_data_parallel(False)
-            full_step = build_step(wl_iic, B * world, crits, iic_b200.iic_losses, uda_fn, torch)
-            loss_full, grads_full = full_step(gathered)
+            iops._dist_enabled = False               # this rank only, and only for this call: no collective teardown
+            try:
+                full_step = build_step(wl_iic, B * world, crits, iic_b200.iic_losses, uda_fn, torch)
+                loss_full, grads_full = full_step(gathered)
+            finally:
+                iops._dist_enabled = True
             rel = abs(loss_full.item() - loss_dp.item()) / max(abs(loss_full.item()), 1e-12)
             gd = grads_dp[0].double()
             gf = grads_full[0][:B].double()

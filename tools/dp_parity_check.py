@@ -103,7 +103,7 @@ for transport in ("peer_memory", "nccl"):
     ins.append((iic_b200.IIDLoss(), torch.from_numpy(gx[lo:hi]).to(dev).requires_grad_(True),
                 torch.from_numpy(gy[lo:hi]).to(dev).requires_grad_(True)))
 
-    def step():
+    def step(ins=ins):
         out = iic_b200.iic_losses(ins)
         flat = [o[0] if isinstance(o, tuple) else o for o in out]
         grads = torch.autograd.grad(sum(flat), [t for _, p, q in ins for t in (p, q)])
@@ -122,12 +122,14 @@ for transport in ("peer_memory", "nccl"):
             side = torch.cuda.Stream(device=dev)
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
-                step()
+                # fresh leaves made on the capture stream (autograd ties a leaf's gradient to the stream it first saw)
+                ins_g = [(c, p.detach().clone().requires_grad_(True), q.detach().clone().requires_grad_(True)) for c, p, q in ins]
+                step(ins_g)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=side):
-                gflat, ggrads = step()
+                gflat, ggrads = step(ins_g)
             for _ in range(4):
                 graph.replay()
             torch.cuda.synchronize()
