@@ -306,13 +306,17 @@ def cpu_reference_run(cfg_id, world, steps, warmup, budget_s=150.0):
             times.append(time.perf_counter() - t0)
         return times
 
-    # size the per-step sample so that the whole run ends within `budget_s`: one full-batch probe step first
-    probe_B = min(B_full, 2)
-    t_probe = min(run(probe_B, 1, 1, 1))
-    est_full = t_probe * B_full / probe_B
-    B = B_full
-    if est_full * (steps + warmup) > budget_s:
-        B = max(1, min(B_full, int(B_full * budget_s / (est_full * (steps + warmup)))))
+    # size the per-step sample so that the whole run ends within `budget_s`: grow the batch from 1 by doubling while the
+    # MEASURED step time says the run still fits (CPU time is far from linear in the batch for the large-filter conv2d)
+    B, t_last = 1, None
+    while True:
+        t_last = min(run(B, 1, 0 if t_last is not None else 1, 1))
+        nxt = min(2 * B, B_full)
+        if B == B_full or 2.2 * t_last * (nxt / B) / 2.0 * (steps + warmup) > budget_s:
+            break
+        B = nxt
+    if t_last * (steps + warmup) > 3 * budget_s and B > 1:
+        B //= 2
     nsets = NSETS if NSETS * input_set_bytes(wl, B) < 8e9 else 1
     times = run(B, steps, warmup, nsets)
     ms = statistics.mean(times) * 1e3

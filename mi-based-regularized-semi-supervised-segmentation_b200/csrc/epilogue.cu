@@ -2,7 +2,7 @@
 //   * local epilogue: min-shift, per-displacement normalise, symmetrise, marginals, entropy and the
 //     analytic dL/dJ                                    (contrastyou/losses/iic_loss.py:124-146,186)
 //   * global joint / epilogue / backward on (N,K) rows  (contrastyou/losses/iic_loss.py:43-94)
-#include "common.cuh"
+#include "epilogue.cuh"
 
 namespace iic {
 
@@ -20,100 +20,18 @@ __global__ void __launch_bounds__(256) local_epilogue_kernel(
     double* __restrict__ loss64_out, float* __restrict__ Wx, float* __restrict__ Wy,
     double* __restrict__ GA_out, int* __restrict__ flags, EpiWorkspace* ws) {
   extern __shared__ __align__(16) double sm[];
-  double* scratch = sm;            // 33
-  double* marg = sm + 40;          // K : marginal (row sum == column sum of the symmetric P)
-  double* lm = marg + K;           // K : log(marg + eps)
-  double* gm = lm + K;             // K : log(marg + eps) + marg / (marg + eps)
   double* partial_loss = reinterpret_cast<double*>(ws + 1);
-
   const int T2 = T * T;
   const int patch = blockIdx.x / T2, d = blockIdx.x % T2;
-  const int dy = d / T, dx = d % T;
   const size_t KK = (size_t)K * K;
-  const double* Jp = J + (size_t)patch * T2 * KK;
-  const double* Jd = Jp + (size_t)d * KK;
-  const double eps = 1e-16;
   const int Kp = (K + 3) & ~3;
-  const int tid = threadIdx.x, nt = blockDim.x;
-
-  // 1. m = min over every displacement and both cluster axes of this patch (iic_loss.py:124)
-  double mn = __longlong_as_double(0x7ff0000000000000LL);
-  bool has_nan = false;
-  for (size_t e = tid; e < (size_t)T2 * KK; e += nt) {
-    const double v = Jp[e];
-    has_nan |= (v != v);
-    mn = fmin(mn, v);
-  }
-  const double m = block_min_nan(mn, has_nan, scratch);
-
-  // 2. A = J_d - m + 1e-16 ; s = sum A ; marginals of P = (A + A^T) / (2 s)
-  for (int k = tid; k < K; k += nt) {
-    double rs = 0.0, cs = 0.0;
-    for (int q = 0; q < K; ++q) {
-      rs += Jd[(size_t)k * K + q] - m + 1e-16;
-      cs += Jd[(size_t)q * K + k] - m + 1e-16;
-    }
-    marg[k] = rs + cs;        // scaled by 1/(2s) below
-    lm[k] = rs;               // stash the row sum for the total
-  }
-  __syncthreads();
-  double part = 0.0;
-  for (int k = tid; k < K; k += nt) part += lm[k];
-  const double s = block_sum(part, scratch);
-  for (int k = tid; k < K; k += nt) {
-    const double mk = marg[k] / (2.0 * s);
-    marg[k] = mk;
-    lm[k] = log(mk + eps);
-    gm[k] = lm[k] + mk / (mk + eps);
-  }
-  __syncthreads();
-
-  // 3. loss_d and tot = sum_ij GQ_ij Q_ij.  P is symmetric and its row and column marginals agree, so
-  //    GP (d loss / d P) is symmetric too and GQ = (GP + GP^T)/2 = GP.
-  double l_part = 0.0, t_part = 0.0;
-  for (size_t e = tid; e < KK; e += nt) {
-    const int i = (int)(e / K), j = (int)(e % K);
-    const double a = Jd[e] - m + 1e-16, at = Jd[(size_t)j * K + i] - m + 1e-16;
-    const double q = a / s;
-    const double p = (a + at) / (2.0 * s);
-    const double lp = log(p + eps);
-    l_part += -p * (lp - lamda * lm[j] - lamda * lm[i]);
-    const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
-    t_part += gq * q;
-  }
-  const double loss_d = block_sum(l_part, scratch);
-  const double tot = block_sum(t_part, scratch);
-
-  // 4. GA = dL/dJ_d = (GQ - tot) / s, scaled by 1/(T^2 n_patches); write the two sweep layouts
-  //    Wy[patch][cin=i][dy*T+dx][j]            (gy[j] += Wy * x_i shifted by (dy-pad, dx-pad))
-  //    Wx[patch][cin=j][(T-1-dy)*T+(T-1-dx)][i] (gx[i] += Wx * y_j shifted by (pad-dy, pad-dx))
+  const int tid = threadIdx.x;
   const double scale = 1.0 / ((double)T2 * (double)n_patches);
-  float* Wxp = Wx + (size_t)patch * K * T2 * Kp;
-  float* Wyp = Wy + (size_t)patch * K * T2 * Kp;
-  const int dflip = (T - 1 - dy) * T + (T - 1 - dx);
-  for (size_t e = tid; e < (size_t)K * Kp; e += nt) {
-    const int a_ = (int)(e / Kp), b_ = (int)(e % Kp);   // a_ = cin, b_ = cout (padded)
-    float wy = 0.f, wx = 0.f;
-    if (b_ < K) {
-      // Wy: cin = i = a_, cout = j = b_ ; Wx: cin = j = a_, cout = i = b_.  GA is symmetric in (i,j)
-      // only through GQ; (GQ - tot)/s is symmetric as well, so one evaluation serves both.
-      const int i = a_, j = b_;
-      const double a = Jd[(size_t)i * K + j] - m + 1e-16, at = Jd[(size_t)j * K + i] - m + 1e-16;
-      const double p = (a + at) / (2.0 * s);
-      const double lp = log(p + eps);
-      const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
-      const double ga = (gq - tot) / s * scale;
-      wy = (float)ga;
-      wx = (float)ga;
-      if (GA_out) {
-        GA_out[((size_t)patch * T2 + d) * KK + (size_t)i * K + j] = ga;
-      }
-    }
-    Wyp[((size_t)a_ * T2 + d) * Kp + b_] = wy;
-    Wxp[((size_t)a_ * T2 + dflip) * Kp + b_] = wx;
-  }
+  const double loss_d = local_epilogue_block(J + (size_t)patch * T2 * KK, K, T, d, lamda, scale,
+                                             Wx + (size_t)patch * K * T2 * Kp, Wy + (size_t)patch * K * T2 * Kp,
+                                             GA_out ? GA_out + ((size_t)patch * T2 + d) * KK : nullptr, sm);
 
-  // 5. last CTA sums the per-displacement losses in index order (deterministic)
+  // last CTA sums the per-displacement losses in index order (deterministic)
   __shared__ bool is_last;
   if (tid == 0) {
     partial_loss[blockIdx.x] = loss_d;
@@ -211,48 +129,7 @@ __global__ void __launch_bounds__(1024) global_epilogue_kernel(const double* __r
                                                                float* __restrict__ P_out,
                                                                int* __restrict__ flags) {
   extern __shared__ __align__(16) double sm[];
-  double* scratch = sm;      // 33
-  double* pi = sm + 40;      // K  row marginals    p_i = sum_j P[i][j]
-  double* pj = pi + K;       // K  column marginals p_j = sum_i P[i][j]
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const size_t KK = (size_t)K * K;
-  const double eps = 1e-10;
-  auto Jsym = [&](int i, int j) {
-    return symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
-  };
-  double part = 0.0;
-  for (size_t e = tid; e < KK; e += nt) part += Jsym((int)(e / K), (int)(e % K));
-  const double S = block_sum(part, scratch);
-  for (int k = tid; k < K; k += nt) {
-    double r = 0.0, c = 0.0;
-    for (int q = 0; q < K; ++q) {
-      r += Jsym(k, q);
-      c += Jsym(q, k);
-    }
-    pi[k] = r / S;
-    pj[k] = c / S;
-  }
-  __syncthreads();
-  double l1 = 0.0, l2 = 0.0;
-  for (size_t e = tid; e < KK; e += nt) {
-    const int i = (int)(e / K), j = (int)(e % K);
-    const double p = Jsym(i, j) / S;
-    if (P_out) P_out[e] = (float)p;
-    if (losses_out) {
-      const double lp = log(p + eps), lj = log(pj[j] + eps), li = log(pi[i] + eps);
-      l1 += -p * (lp - lamb * lj - lamb * li);
-      l2 += -p * (lp - lj - li);
-    }
-  }
-  if (losses_out) {
-    const double L1 = block_sum(l1, scratch);
-    const double L2 = block_sum(l2, scratch);
-    if (tid == 0) {
-      losses_out[0] = (float)L1;
-      losses_out[1] = (float)L2;
-      if (L1 != L1 || L2 != L2) atomicOr(flags, IIC_FLAG_NAN_LOSS);
-    }
-  }
+  global_epilogue_block(J, K, lamb, symmetric, losses_out, P_out, flags, sm);
 }
 
 // Every CTA rebuilds GJ = d(objective)/dJ in shared memory (K*K doubles -> floats), then produces a

@@ -13,6 +13,7 @@
 // co-residency); the only wait is the last CTA's bounded wait for the peers' flags.  One warp handles one displacement
 // of one term, which is why the fused epilogue is limited to K <= 32; terms with more clusters take phase 1 (+ the
 // exchange) here and the multi-CTA epilogue kernels of epilogue.cu afterwards.
+#include "epilogue.cuh"
 #include "xchg.cuh"
 
 namespace iic {
@@ -23,6 +24,12 @@ constexpr int FIN_WARPS = FIN_THREADS / 32;
 constexpr int FIN_MAX_K = 32;              // fused epilogue: one warp per displacement
 constexpr int FIN_MAX_UNITS = 1024;        // (term, patch, displacement) triples with a fused epilogue
 constexpr int FIN_MAX_PATCHES = 256;       // (term, patch) pairs with a fused epilogue
+constexpr int FIN_SMALL_UNITS = 32;        // the last CTA runs the epilogues itself only for batches this small (one round of
+                                           // its warps) whose joints fit its shared-memory stage; larger batches take the
+                                           // multi-CTA batched epilogue kernel as a second launch
+constexpr int FIN_BIG_MAX_UNITS = 16384;   // displacement units of one batched epilogue launch (workspace: one double each)
+constexpr size_t FIN_WS_TICKETS = 64;      // workspace: [0] phase-1 ticket, [1] rank-sum ticket; per-term tickets from here
+constexpr size_t FIN_WS_LOSSES = 256;      // workspace: unit losses from here
 
 struct FinItem {
   const float* slots;            // local terms: per-CTA partial joints
@@ -51,6 +58,7 @@ struct FinBatch {
   int* flags;
   unsigned int* ticket;          // self-resetting arrival counter (workspace)
   int rank, world;
+  int xchg_mode;                 // 1: the last CTA exchanges and sums (small batches); 2: it only publishes (xchg_sum_kernel follows)
   long long capacity;
   unsigned long long timeout_ns;
   XchgPeers peers;
@@ -111,13 +119,35 @@ __device__ void reduce_unit(const FinBatch& B, const FinItem& it, long long unit
 
 // J = x^T y of one global term, fp64, rows walked in order by every thread (deterministic); both simplex assertions
 // (iic_loss.py:50-51,82-83) ride along
-__device__ void global_rows_unit(const FinBatch& B, const FinItem& it, int par) {
+__device__ void global_rows_unit(const FinBatch& B, const FinItem& it, double* scratch /* FIN_WARPS*33 doubles */, int par) {
   const int K = it.K, KK = K * K;
-  for (int e = threadIdx.x; e < KK; e += FIN_THREADS) {
-    const int i = e / K, j = e - i * K;
-    double a = 0.0;
-    for (long long n = 0; n < it.N; ++n) a += (double)__ldg(it.x + n * it.x_sn + i) * (double)__ldg(it.y + n * it.y_sn + j);
-    store_joint(B, it, e, a, par);
+  // G row groups x K*K entries: group g walks rows g, g+G, ... (short dependent chains), then entry e adds the G
+  // partial sums in group order -- a fixed order, so the result is deterministic
+  int G = FIN_THREADS / KK;
+  if (G > FIN_WARPS * 33 / KK) G = FIN_WARPS * 33 / KK;
+  if (G < 1) G = 1;
+  __syncthreads();
+  if (G == 1) {
+    for (int e = threadIdx.x; e < KK; e += FIN_THREADS) {
+      const int i = e / K, j = e - i * K;
+      double a = 0.0;
+      for (long long n = 0; n < it.N; ++n) a += (double)__ldg(it.x + n * it.x_sn + i) * (double)__ldg(it.y + n * it.y_sn + j);
+      store_joint(B, it, e, a, par);
+    }
+  } else {
+    const int g = threadIdx.x / KK, e = threadIdx.x - g * KK;
+    if (g < G) {
+      const int i = e / K, j = e - i * K;
+      double a = 0.0;
+      for (long long n = g; n < it.N; n += G) a += (double)__ldg(it.x + n * it.x_sn + i) * (double)__ldg(it.y + n * it.y_sn + j);
+      scratch[g * KK + e] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < KK) {
+      double t = 0.0;
+      for (int q = 0; q < G; ++q) t += scratch[q * KK + threadIdx.x];
+      store_joint(B, it, threadIdx.x, t, par);
+    }
   }
   if (B.flags && it.check_simplex) {
     bool bad = false;
@@ -137,13 +167,15 @@ __device__ __forceinline__ long long item_units(const FinItem& it) {
   return (long long)it.n_patches * ((Eper + 31) / 32);
 }
 
-// J was written by other CTAs of this launch (and, after an exchange, summed by this one): read it past L1
-__device__ __forceinline__ double ldj(const double* p) { return __ldcg(p); }
+// J was written by other CTAs of this launch (and, after an exchange, summed by this one): read it past L1 -- unless
+// the last CTA has staged all joints in shared memory (small batches: config 2's 1000 doubles), where `p` points there
+__device__ __forceinline__ double ldj(const double* p, bool staged) { return staged ? *p : __ldcg(p); }
 
 // ---- phase 2: epilogues, one warp per (term, patch, displacement) -----------------------------------------------------------
 // Same arithmetic as local_epilogue_kernel (epilogue.cu); sc = 3*K doubles of per-warp scratch.
-__device__ double warp_local_displacement(const double* __restrict__ Jp, int d, int K, int T, double m, double lamda,
-                                          double scale, float* __restrict__ Wxp, float* __restrict__ Wyp, double* sc) {
+__device__ double warp_local_displacement(const double* __restrict__ Jp, bool staged, int d, int K, int T, double m,
+                                          double lamda, double scale, float* __restrict__ Wxp, float* __restrict__ Wyp,
+                                          double* sc) {
   const int lane = threadIdx.x & 31;
   const int KK = K * K, T2 = T * T, Kp = (K + 3) & ~3;
   const double* Jd = Jp + (size_t)d * KK;
@@ -155,60 +187,63 @@ __device__ double warp_local_displacement(const double* __restrict__ Jp, int d, 
   for (int k = lane; k < K; k += 32) {
     double rs = 0.0, cs = 0.0;
     for (int q = 0; q < K; ++q) {
-      rs += ldj(Jd + k * K + q) - m + 1e-16;
-      cs += ldj(Jd + q * K + k) - m + 1e-16;
+      rs += ldj(Jd + k * K + q, staged) - m + 1e-16;
+      cs += ldj(Jd + q * K + k, staged) - m + 1e-16;
     }
     marg[k] = rs + cs;
     part += rs;
   }
   const double s = warp_sum(part);
+  const double inv_2s = 1.0 / (2.0 * s), inv_s = 2.0 * inv_2s;
   for (int k = lane; k < K; k += 32) {
-    const double mk = marg[k] / (2.0 * s);
+    const double mk = marg[k] * inv_2s;
     marg[k] = mk;
     lm[k] = log(mk + eps);
     gm[k] = lm[k] + mk / (mk + eps);
   }
   __syncwarp();
+  // pass 1 over the padded (cin, cout) grid the coefficient tensors use: loss, tot = sum GQ * Q, and GQ itself parked
+  // (as float, it is read back by the same lane) in its final Wy slot -- the second log per entry is gone
+  const int dy = d / T, dx = d - dy * T;
+  const int dflip = (T - 1 - dy) * T + (T - 1 - dx);
   double l_part = 0.0, t_part = 0.0;
-  for (int e = lane; e < KK; e += 32) {
-    const int i = e / K, j = e - i * K;
-    const double a = ldj(Jd + e) - m + 1e-16, at = ldj(Jd + j * K + i) - m + 1e-16;
-    const double q = a / s;
-    const double p = (a + at) / (2.0 * s);
-    const double lp = log(p + eps);
-    l_part += -p * (lp - lamda * lm[j] - lamda * lm[i]);
-    const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
-    t_part += gq * q;
+  for (int e = lane; e < K * Kp; e += 32) {
+    const int i = e / Kp, j = e - i * Kp;                // i = cin, j = cout (padded)
+    float gqf = 0.f;
+    if (j < K) {
+      const double a = ldj(Jd + i * K + j, staged) - m + 1e-16, at = ldj(Jd + j * K + i, staged) - m + 1e-16;
+      const double p = (a + at) * inv_2s;
+      const double lp = log(p + eps);
+      l_part += -p * (lp - lamda * lm[j] - lamda * lm[i]);
+      const double gq = -lp - p / (p + eps) + lamda * (gm[j] + gm[i]);
+      t_part += gq * (a * inv_s);
+      gqf = (float)gq;
+    }
+    Wyp[((size_t)i * T2 + d) * Kp + j] = gqf;
   }
   const double loss_d = warp_sum(l_part);
   const double tot = warp_sum(t_part);
-  const int dy = d / T, dx = d - dy * T;
-  const int dflip = (T - 1 - dy) * T + (T - 1 - dx);
+  const double cs = inv_s * scale;
+  // pass 2: GA = dL/dJ_d = (GQ - tot) / s, scaled by 1/(T^2 n_patches), in the two sweep layouts
+  //    Wy[cin=i][dy*T+dx][j]   and   Wx[cin=j][(T-1-dy)*T+(T-1-dx)][i]  (GA is symmetric in (i, j))
   for (int e = lane; e < K * Kp; e += 32) {
-    const int a_ = e / Kp, b_ = e - a_ * Kp;             // a_ = cin, b_ = cout (padded)
-    float w = 0.f;
-    if (b_ < K) {
-      const double a = ldj(Jd + a_ * K + b_) - m + 1e-16, at = ldj(Jd + b_ * K + a_) - m + 1e-16;
-      const double p = (a + at) / (2.0 * s);
-      const double lp = log(p + eps);
-      const double gq = -lp - p / (p + eps) + lamda * (gm[b_] + gm[a_]);
-      w = (float)((gq - tot) / s * scale);
-    }
-    Wyp[((size_t)a_ * T2 + d) * Kp + b_] = w;
-    Wxp[((size_t)a_ * T2 + dflip) * Kp + b_] = w;
+    const int i = e / Kp, j = e - i * Kp;
+    float* wy = Wyp + ((size_t)i * T2 + d) * Kp + j;
+    const float w = j < K ? (float)(((double)*wy - tot) * cs) : 0.f;
+    *wy = w;
+    Wxp[((size_t)i * T2 + dflip) * Kp + j] = w;
   }
   __syncwarp();
   return loss_d;
 }
 
 // global term: P = sym(J)/S, the two entropy expressions (global_epilogue_kernel's arithmetic); sc = 2*K doubles
-__device__ void warp_global_term(const FinItem& it, int* flags, double* sc) {
+__device__ void warp_global_term(const FinItem& it, const double* J, bool staged, int* flags, double* sc) {
   const int lane = threadIdx.x & 31;
   const int K = it.K, KK = K * K;
-  const double* J = it.J;
   const double eps = 1e-10, lamb = it.lamda;
   const bool sym = it.symmetric != 0;
-  auto Jsym = [&](int i, int j) { return sym ? (ldj(J + i * K + j) + ldj(J + j * K + i)) / 2.0 : ldj(J + i * K + j); };
+  auto Jsym = [&](int i, int j) { return sym ? (ldj(J + i * K + j, staged) + ldj(J + j * K + i, staged)) / 2.0 : ldj(J + i * K + j, staged); };
   double part = 0.0;
   for (int e = lane; e < KK; e += 32) part += Jsym(e / K, e % K);
   const double S = warp_sum(part);
@@ -273,7 +308,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
       long long first = blockIdx.x - (base % gridDim.x);
       if (first < 0) first += gridDim.x;
       for (long long u = first; u < nu; u += gridDim.x) {
-        if (it.kind == IIC_ITEM_GLOBAL_ROWS) global_rows_unit(B, it, par);
+        if (it.kind == IIC_ITEM_GLOBAL_ROWS) global_rows_unit(B, it, &sm[0][0], par);
         else reduce_unit(B, it, u, sm, par);
       }
       base += nu;
@@ -292,6 +327,12 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     if (tid < B.world) {
       XchgHeader* ph = reinterpret_cast<XchgHeader*>(B.peers.base[tid]);
       st_release_sys(&ph->flags[par][B.rank], seq);
+    }
+    if (B.xchg_mode == 2) {                            // large batch: xchg_sum_kernel waits and sums with all SMs
+      if (tid == 0) *B.ticket = 0;
+      return;
+    }
+    if (tid < B.world) {
       // a slow peer is waited for; the bound only keeps a dead peer from hanging the GPU and is reported as a flag
       if (!xchg_wait_flag(hdr, par, tid, seq, B.timeout_ns) && B.flags) atomicOr(B.flags, IIC_FLAG_XCHG_TIMEOUT);
     }
@@ -309,6 +350,15 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
   if (!B.do_epilogue) return;
   __syncthreads();
 
+  // small batches (config 2: 900 + 100 doubles): all joints into shared memory -- the phase-1 scratch is free now
+  const bool staged = B.E_total <= (long long)(FIN_WARPS * 33);
+  double* Js = &sm[0][0];
+  if (staged) {
+    for (long long e = tid; e < B.E_total; e += FIN_THREADS) Js[e] = __ldcg(B.J_all + e);
+    __syncthreads();
+  }
+  const double* Jbase = staged ? Js : B.J_all;
+
   // per (term, patch): m = min over every displacement and both cluster axes (iic_loss.py:124), NaN-propagating
   int npatch_total = 0;
   for (int i = 0; i < B.n; ++i) {
@@ -316,11 +366,11 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     if (it.kind != IIC_ITEM_LOCAL) continue;
     const long long Eper = it.E / it.n_patches;
     for (int p = 0; p < it.n_patches; ++p, ++npatch_total) {
-      const double* Jp = it.J + (size_t)p * Eper;
+      const double* Jp = Jbase + (it.J - B.J_all) + (size_t)p * Eper;
       double mn = __longlong_as_double(0x7ff0000000000000LL);
       bool has_nan = false;
       for (long long e = tid; e < Eper; e += FIN_THREADS) {
-        const double v = ldj(Jp + e);
+        const double v = ldj(Jp + e, staged);
         has_nan |= (v != v);
         mn = fmin(mn, v);
       }
@@ -336,7 +386,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     for (int i = 0; i < B.n; ++i) {
       const FinItem& it = B.it[i];
       if (it.kind == IIC_ITEM_GLOBAL_ROWS) {
-        if ((ubase % FIN_WARPS) == wid) warp_global_term(it, B.flags, wscratch[wid]);
+        if ((ubase % FIN_WARPS) == wid) warp_global_term(it, Jbase + (it.J - B.J_all), staged, B.flags, wscratch[wid]);
         ubase += 1;
         continue;
       }
@@ -348,7 +398,8 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
       if (first < 0) first += FIN_WARPS;
       for (int u = first; u < nu; u += FIN_WARPS) {
         const int p = u / T2, d = u - p * T2;
-        const double ld = warp_local_displacement(it.J + (size_t)p * Eper, d, it.K, it.T, patch_min[pbase + p], it.lamda, scale,
+        const double ld = warp_local_displacement(Jbase + (it.J - B.J_all) + (size_t)p * Eper, staged, d, it.K, it.T,
+                                                  patch_min[pbase + p], it.lamda, scale,
                                                   it.Wx + (size_t)p * it.K * T2 * Kp, it.Wy + (size_t)p * it.K * T2 * Kp,
                                                   wscratch[wid]);
         if (lane == 0) unit_loss[ubase + u] = ld;
@@ -374,11 +425,86 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
   }
 }
 
+// ---- large batches -----------------------------------------------------------------------------------------------------
+// Second half of the exchange with all SMs: wait for every rank's flag, add the ranks' slots in rank order, last CTA
+// advances the sequence counter.
+__global__ void __launch_bounds__(FIN_THREADS) xchg_sum_kernel(double* __restrict__ J_all, long long E_total, XchgPeers peers,
+                                                               int rank, int world, long long capacity,
+                                                               unsigned long long timeout_ns, int* __restrict__ flags,
+                                                               unsigned int* __restrict__ ticket) {
+  XchgHeader* hdr = reinterpret_cast<XchgHeader*>(peers.base[rank]);
+  __shared__ unsigned long long seq_s;
+  __shared__ int last_s;
+  if (threadIdx.x == 0) seq_s = *reinterpret_cast<volatile unsigned long long*>(&hdr->seq) + 1;
+  __syncthreads();
+  const unsigned long long seq = seq_s;
+  const int par = (int)(seq & 1ull);
+  if (threadIdx.x < world && !xchg_wait_flag(hdr, par, threadIdx.x, seq, timeout_ns) && flags) atomicOr(flags, IIC_FLAG_XCHG_TIMEOUT);
+  __syncthreads();
+  const double* src = xchg_slot(peers.base[rank], par, world, 0, capacity);
+  for (long long e = (long long)blockIdx.x * FIN_THREADS + threadIdx.x; e < E_total; e += (long long)gridDim.x * FIN_THREADS) {
+    double s = 0.0;
+    for (int r = 0; r < world; ++r) s += __ldcg(src + (size_t)r * capacity + e);
+    J_all[e] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last_s = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (last_s && threadIdx.x == 0) {
+    *ticket = 0;
+    *reinterpret_cast<volatile unsigned long long*>(&hdr->seq) = seq;      // every CTA has read it by now
+  }
+}
+
+// All epilogues of a batch, one CTA per (term, patch, displacement) / per global term -- the arithmetic of
+// local_epilogue_kernel / global_epilogue_kernel (epilogue.cuh).  Per term, the last of its CTAs adds the displacement
+// losses in index order.
+__global__ void __launch_bounds__(256) batched_epilogue_kernel(const __grid_constant__ FinBatch B, unsigned int* __restrict__ tickets,
+                                                               double* __restrict__ unit_loss) {
+  extern __shared__ __align__(16) double esm[];
+  __shared__ int last_s;
+  int item = 0, ubase = 0;
+  for (; item < B.n; ++item) {
+    const int nu = B.it[item].kind == IIC_ITEM_GLOBAL_ROWS ? 1 : B.it[item].n_patches * B.it[item].T * B.it[item].T;
+    if ((int)blockIdx.x < ubase + nu) break;
+    ubase += nu;
+  }
+  if (item >= B.n) return;
+  const FinItem& it = B.it[item];
+  if (it.kind == IIC_ITEM_GLOBAL_ROWS) {
+    global_epilogue_block(it.J, it.K, it.lamda, it.symmetric, it.loss_out, it.P_out, B.flags, esm);
+    return;
+  }
+  const int T2 = it.T * it.T, Kp = (it.K + 3) & ~3;
+  const int u = (int)blockIdx.x - ubase, p = u / T2, d = u - p * T2, nu = it.n_patches * T2;
+  const long long Eper = it.E / it.n_patches;
+  const double scale = 1.0 / ((double)T2 * (double)it.n_patches);
+  const double loss_d = local_epilogue_block(it.J + (size_t)p * Eper, it.K, it.T, d, it.lamda, scale,
+                                             it.Wx + (size_t)p * it.K * T2 * Kp, it.Wy + (size_t)p * it.K * T2 * Kp, nullptr, esm);
+  if (threadIdx.x == 0) {
+    unit_loss[blockIdx.x] = loss_d;
+    __threadfence();
+    last_s = (atomicAdd(&tickets[item], 1u) == (unsigned)nu - 1) ? 1 : 0;
+  }
+  __syncthreads();
+  if (last_s && threadIdx.x == 0) {
+    __threadfence();
+    const volatile double* pl = unit_loss + ubase;
+    double total = 0.0;
+    for (int q = 0; q < nu; ++q) total += pl[q];
+    total *= scale;
+    it.loss_out[0] = (float)total;
+    if (total != total && B.flags) atomicOr(B.flags, IIC_FLAG_NAN_LOSS);
+    tickets[item] = 0;
+  }
+}
+
 }  // namespace iic
 
 using namespace iic;
 
-extern "C" size_t iic_finish_workspace_bytes(void) { return 64; }
+extern "C" size_t iic_finish_workspace_bytes(void) { return FIN_WS_LOSSES + (size_t)FIN_BIG_MAX_UNITS * sizeof(double); }
 
 extern "C" int iic_finish(const iic_finish_item* items_host, int n_items, double* J_all, long long E_total, int* flags,
                           void* workspace, void* const* xchg_bufs_host, int rank, int world, long long xchg_capacity,
@@ -444,31 +570,50 @@ extern "C" int iic_finish(const iic_finish_item* items_host, int n_items, double
       d.P_out = s.P_out;
       epi_units += 1;
     }
-    if (s.K > FIN_MAX_K) fused = false;
     units += (d.kind == IIC_ITEM_GLOBAL_ROWS) ? 1 : (long long)d.n_patches * ((d.E / d.n_patches + 31) / 32);
     off += d.E;
   }
   IIC_REQUIRE(off == E_total, "iic_finish: the terms hold %lld joint entries, E_total says %lld", off, E_total);
-  if (epi_units > FIN_MAX_UNITS || epi_patches > FIN_MAX_PATCHES) fused = false;
-  B.do_epilogue = fused ? 1 : 0;
+  // small batches (config 2: one local + one global term): the last CTA exchanges and runs the epilogues itself;
+  // anything larger: phase 1 here, then the rank sum and the epilogues as multi-CTA launches
+  const bool small = fused && epi_units <= FIN_SMALL_UNITS && epi_patches <= FIN_MAX_PATCHES && E_total <= (long long)FIN_WARPS * 33;
+  B.do_epilogue = small ? 1 : 0;
+  B.xchg_mode = small ? 1 : 2;
   int sms = sm_count_cached(current_device());
   if (sms <= 0) sms = 148;
   long long grid = units < sms ? units : sms;
   if (grid < 1) grid = 1;
+  unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
   finish_kernel<<<(unsigned)grid, FIN_THREADS, 0, st>>>(B);
   IIC_CHECK_CUDA(cudaGetLastError());
-  if (want_epilogue && !fused) {
-    // wide cluster heads (K > 32) or very many patches: the multi-CTA epilogue kernels, one launch per term
-    for (int i = 0; i < n_items; ++i) {
-      const iic_finish_item& s = items_host[i];
-      const FinItem& d = B.it[i];
-      if (s.kind == IIC_ITEM_LOCAL) {
-        IIC_REQUIRE(s.epilogue_workspace, "iic_finish: term %d needs epilogue_workspace (K > 32 or a large batch)", i);
-        IIC_CHECK_RC(iic_local_epilogue(d.J, s.K, s.pad, s.n_patches, s.lamda, s.loss_out, nullptr, s.Wx, s.Wy, nullptr, flags,
-                                        s.epilogue_workspace, stream));
-      } else {
-        IIC_CHECK_RC(iic_global_epilogue(d.J, s.K, s.lamda, s.symmetric, s.loss_out, s.P_out, flags, stream));
-      }
+  if (small) return 0;
+  if (world > 1) {
+    long long g2 = (E_total + FIN_THREADS - 1) / FIN_THREADS;
+    if (g2 > sms) g2 = sms;
+    xchg_sum_kernel<<<(unsigned)g2, FIN_THREADS, 0, st>>>(J_all, E_total, B.peers, rank, world, xchg_capacity, B.timeout_ns, flags,
+                                                          tickets + 1);
+    IIC_CHECK_CUDA(cudaGetLastError());
+  }
+  if (!want_epilogue) return 0;
+  if (fused && epi_units <= FIN_BIG_MAX_UNITS) {
+    int kmax = 1;
+    for (int i = 0; i < n_items; ++i) kmax = items_host[i].K > kmax ? items_host[i].K : kmax;
+    const size_t smem = (40 + 3 * (size_t)kmax) * sizeof(double);
+    batched_epilogue_kernel<<<(unsigned)epi_units, 256, smem, st>>>(B, tickets + FIN_WS_TICKETS / sizeof(unsigned int),
+                                                                    reinterpret_cast<double*>((unsigned char*)workspace + FIN_WS_LOSSES));
+    IIC_CHECK_CUDA(cudaGetLastError());
+    return 0;
+  }
+  // no_fused_epilogue / enormous batches: the single-term epilogue kernels, one launch per term
+  for (int i = 0; i < n_items; ++i) {
+    const iic_finish_item& s = items_host[i];
+    const FinItem& d = B.it[i];
+    if (s.kind == IIC_ITEM_LOCAL) {
+      IIC_REQUIRE(s.epilogue_workspace, "iic_finish: term %d needs epilogue_workspace", i);
+      IIC_CHECK_RC(iic_local_epilogue(d.J, s.K, s.pad, s.n_patches, s.lamda, s.loss_out, nullptr, s.Wx, s.Wy, nullptr, flags,
+                                      s.epilogue_workspace, stream));
+    } else {
+      IIC_CHECK_RC(iic_global_epilogue(d.J, s.K, s.lamda, s.symmetric, s.loss_out, s.P_out, flags, stream));
     }
   }
   return 0;

@@ -121,12 +121,13 @@ def test_five_heads_one_finish(iic, cuda_device, K, pad, H, W):
         ol, ogx, ogy = O.iid_segmentation_small_path_loss(xs[s], ys[s], pad, 1024, with_grads=True)
         assert _loss_close(losses[s].item(), ol), (s, losses[s].item(), ol)
         assert relmax(g[:B, s], ogx / S) <= GRAD_RTOL and relmax(g[B:, s], ogy / S) <= GRAD_RTOL
-    # and the one-by-one public calls give the same bits (same kernels, same reduction order)
+    # and the one-by-one public calls agree (same joint kernels; a single small term runs its epilogue inside the
+    # finish launch, a batch in the multi-CTA epilogue kernel: same fp64 arithmetic, different summation order)
     t2 = t.detach().clone().requires_grad_(True)
     v2 = t2.view(2 * B, S, K, H, W)
     for s in range(S):
         a, b = torch.chunk(v2[:, s], 2, 0)
-        assert crit(a, b).item() == losses[s].item()
+        assert abs(crit(a, b).item() - losses[s].item()) <= 1e-6 * abs(losses[s].item())
 
 
 def test_config3_iteration_one_finish(iic, cuda_device):
