@@ -120,8 +120,8 @@ def peaks():
 
 
 # dram bytes per launch of the dominant kernel from one `ncu --set full` capture; None until measured for the current kernel
-TRAFFIC_BWD = (217.3e6, "ncu --set full, profiles/r01_ncu_local_bwd_tcrb10.txt: dram__bytes_read 133.4 MB + dram__bytes_write 83.8 MB per "
-               "launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)")
+TRAFFIC_BWD = (218.0e6, "ncu --set full, profiles/r02_ncu_config2_kernels.txt (local_bwd_tcrb10h_kernel): dram__bytes_read 133.5 MB + "
+               "dram__bytes_write 84.5 MB per launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -639,7 +639,7 @@ def run_b200(args):
     tc10 = (K in (9, 10) and pad == 1 and not iic_b200._lib.load().iic_b200_get_option(b"no_tc")
             and not iic_b200._lib.load().iic_b200_get_option(b"no_tc10"))
     if K in (9, 10) and pad == 1:
-        kname = ("local_bwd_tcrb10_kernel (tcgen05, both gradient sweeps in one launch)" if tc10
+        kname = ("local_bwd_tcrb10h_kernel (tcgen05 kind::f16 on fp16-split operands, both gradient sweeps in one launch)" if tc10
                  else "local_bwd_fast_kernel<10,1,16,4,5,false>")
     elif 16 <= K <= 24:
         kname = "local_bwd_tcrb_kernel (tcgen05 row-block sweeps, one launch per gradient + weight images)"
