@@ -11,8 +11,9 @@ from .losses.iic_loss import (IIDLoss, IIDSegmentationLoss, IIDSegmentationSmall
 from .losses.kl_losses import KL_div, MSELoss, dice_from_counts, sup_kl_from_logits, uda_from_logits  # noqa: F401
 from .ops import set_data_parallel, data_parallel_transport, ddp_loss_scale  # noqa: F401
 from .semi_seg._utils import IICLossWrapper, combine_iic_losses, iic_regularization  # noqa: F401
+from .semi_seg.meters import DeferredScalarMeters  # noqa: F401
 
 __all__ = ["IIDLoss", "IIDSegmentationLoss", "IIDSegmentationSmallPathLoss", "compute_joint", "patch_generator",
-           "iic_losses", "iic_regularization", "combine_iic_losses",
+           "iic_losses", "iic_regularization", "combine_iic_losses", "DeferredScalarMeters",
            "KL_div", "MSELoss", "uda_from_logits", "sup_kl_from_logits", "dice_from_counts", "TensorRandomFlip", "draw_flip_flags", "flip_stack", "IICLossWrapper", "set_check_mode", "get_check_mode",
            "check_mode", "raise_if_flagged", "set_data_parallel", "data_parallel_transport", "ddp_loss_scale"]

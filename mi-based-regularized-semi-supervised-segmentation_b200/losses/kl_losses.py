@@ -24,7 +24,12 @@ _KIND = {"mse": 0, "kl": 1}
 
 
 class KL_div(nn.Module):
-    r"""KL(target || prob) = -\sum target * log((prob+eps)/(target+eps)); reduction "mean" or "sum"."""
+    r"""KL(target || prob) = -\sum target * log((prob+eps)/(target+eps)); reduction "mean" or "sum".
+
+    ``reduction="none"`` (the per-pixel map of dc2:loss/kl_losses.py:121-126) is accepted by the constructor like the
+    reference's, but ``forward`` raises ``NotImplementedError`` for it: no caller on the udaiic path uses it
+    (``semi_seg/trainer.py:137,194`` and ``semi_seg/main.py`` build ``KL_div()`` with the default), and the fused kernels
+    never materialise the per-pixel map."""
 
     def __init__(self, reduction="mean", eps=1e-16, weight: Union[List[float], Tensor] = None, verbose=True):
         super().__init__()

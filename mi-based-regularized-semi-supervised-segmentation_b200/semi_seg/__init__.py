@@ -1,1 +1,2 @@
 from ._utils import IICLossWrapper, IIDLoss  # noqa: F401
+from .meters import DeferredScalarMeters  # noqa: F401

@@ -222,3 +222,22 @@ def test_product_never_imports_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "oracle" not in src.replace("the oracle", ""), f"{f} mentions the oracle"
+
+
+def test_deferred_scalar_meters_match_average_value_meter(built):
+    """DeferredScalarMeters: same means as dc2's AverageValueMeter fed with .item() values, NaN for a
+    name that was never recorded, buffer roll-over, reset."""
+    torch.manual_seed(0)
+    m = built.DeferredScalarMeters(["sup_loss", "reg_loss", "uda", "never"], capacity=4)
+    vals = torch.randn(11, 3)
+    for r in vals:
+        m.record(sup_loss=r[0], reg_loss=r[1], uda=float(r[2]))       # tensors and plain numbers
+    s = m.summary()
+    for i, n in enumerate(["sup_loss", "reg_loss", "uda"]):
+        assert abs(s[n]["mean"] - vals[:, i].double().mean().item()) < 1e-6
+    assert s["never"]["mean"] != s["never"]["mean"]                     # NaN
+    m.reset()
+    m.record(sup_loss=torch.tensor(2.0))
+    assert m.summary()["sup_loss"]["mean"] == 2.0
+    with pytest.raises(AssertionError):
+        m.record(bogus=1.0)
