@@ -212,7 +212,8 @@ int local_bwd_tcrb_try(const float* x, long long x_sn, long long x_sc, long long
                        const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
 int local_bwd_tcrb10h_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                           long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
-                          const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
+                          const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, int from_logits,
+                          float inv_temp, cudaStream_t st);
 int local_bwd_tcrb10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
                          const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st);
@@ -253,7 +254,7 @@ extern "C" int iic_local_backward(const float* x, long long x_sn, long long x_sc
         const int rc_10 = options().tc10_tf32 ? local_bwd_tcrb10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy,
                                                                       grad_loss, gx, gy, gx_sn, gy_sn, st)
                                               : local_bwd_tcrb10h_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
-                                               gx, gy, gx_sn, gy_sn, st);
+                                               gx, gy, gx_sn, gy_sn, 0, 1.f, st);
         if (rc_10 >= 0) return rc_10;
       }
       // the reference's default cluster count (16 <= K <= 24), padding 1 or 3: row-block tensor-core sweeps
@@ -331,6 +332,13 @@ extern "C" int iic_local_backward_from_logits(const float* lx, long long x_sn, l
   IIC_REQUIRE(lx && ly && Wx && Wy && g_lx && g_ly, "iic_local_backward_from_logits: null pointer");
   const int sms = sm_count_cached(current_device());
   IIC_REQUIRE(sms > 0, "iic_local_backward_from_logits: no device");
+  // the fp16-split tensor-core backward has a from-logits form (softmax in its transform warps, adjoint in its drain);
+  // same shape rule as for probabilities (enough rows to fill the SMs, or tc10_force)
+  if (!options().no_tc && !options().no_tc10 && !options().no_tma) {
+    const int rc_tc = local_bwd_tcrb10h_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss, g_lx,
+                                            g_ly, gx_sn, gy_sn, 1, inv_temperature, st);
+    if (rc_tc >= 0) return rc_tc;
+  }
   const int rc = local_bwd_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad, Wx, Wy, grad_loss,
                                     g_lx, g_ly, gx_sn, gy_sn, sms, 1, inv_temperature, st);
   if (rc < 0) {

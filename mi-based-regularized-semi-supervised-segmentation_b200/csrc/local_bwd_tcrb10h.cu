@@ -42,8 +42,11 @@ constexpr int NRAW = 6;
 constexpr int WROWS = T * KP;            // 48 rows per weight chunk
 constexpr int W_TILE = 2 * WROWS * 16;   // 1536: one MMA's B operand (two chunks)
 constexpr int W_IMG = 6 * W_TILE;        // (tx 0, 1, 2) x (MMA 1, MMA 2)
-constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM + weights, 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
+constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM (+ logit rows), 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
+constexpr int NTHREADS_FL = 704;          // from-logits form: a second epilogue set (warps 18-21) takes pixel tile 1
 constexpr int SMEM_BYTES = NA * A_SLOT + 2 * W_IMG + NRAW * RAW_SLOT + 1024;   // both sweeps' weight images stay resident
+constexpr int NL = 4;                    // from-logits form: ring of output-tensor logit rows for the drain (two row pairs)
+constexpr int SMEM_BYTES_FL = SMEM_BYTES + NL * RAW_SLOT;
 constexpr float A_SCALE = 256.f;         // 2^8
 constexpr int A_SCALE_LOG2 = 8;
 constexpr int W_TARGET_LOG2 = 12;        // largest |coefficient| scaled into [2^12, 2^13)
@@ -64,6 +67,13 @@ struct Params {
   const float* grad_loss;
   float* out[2];
   long long out_sn[2];          // sample strides of the two gradient tensors in elements
+  // from-logits form (the cluster head's SoftmaxWithT fused, contrastyou/trainer/_utils.py:15-23): the maps behind the TMA
+  // descriptors hold LOGITS; the transform warps soft-max every staged pixel, the drain applies the softmax adjoint with
+  // the probabilities of the OUTPUT tensor's pixel, recomputed from its logits (lout[sweep]: sweep 0 -> x, sweep 1 -> y)
+  int from_logits;
+  float inv_temp;
+  const float* lout[2];
+  long long l_sn[2], l_sc[2], l_sh[2];
 };
 
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) {          // a at the lower address
@@ -114,16 +124,20 @@ __device__ __forceinline__ Chunk next_chunk(long long r, long long R1, int H, in
   return c;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
+template <bool FROM_LOGITS>
+__global__ void __launch_bounds__(FROM_LOGITS ? NTHREADS_FL : NTHREADS, 1)
 local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_constant__ CUtensorMap map1, const Params P) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
   __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], a_full[NA], a_empty[NA], w_full, accum_full[2], tmem_ready[2];
+  __shared__ __align__(8) uint64_t l_full[NL], l_empty[NL];      // FROM_LOGITS: logit rows of the OUTPUT tensor for the drain
   __shared__ uint32_t tmem_base_s;
   __shared__ float wmax_s[4];
+  __shared__ float unscale_s;
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* a_ring = smem;
   unsigned char* w_img = smem + NA * A_SLOT;
   unsigned char* raw_ring = w_img + 2 * W_IMG;
+  unsigned char* l_ring = raw_ring + NRAW * RAW_SLOT;            // FROM_LOGITS only (SMEM_BYTES_FL)
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows_total = (long long)P.B * P.H;
   const long long R0 = (long long)blockIdx.x * rows_total / gridDim.x;
@@ -139,7 +153,9 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
     mbar_init(&w_full, 4);
-    for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 4); mbar_init(&tmem_ready[s], 4); }
+    const int ndset_i = (FROM_LOGITS && ntile == 2) ? 2 : 1;          // epilogue warp sets (one per pixel tile when from logits)
+    for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 4); mbar_init(&tmem_ready[s], 4 * ndset_i); }
+    for (int s = 0; s < NL; ++s) { mbar_init(&l_full[s], 1); mbar_init(&l_empty[s], 4 * ndset_i); }
     mbar_fence_init();
   }
   if (wid == 3) {
@@ -168,6 +184,26 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
           mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
           tma_load_4d(raw_ring + s * RAW_SLOT, sweep == 0 ? &map0 : &map1, &raw_full[s], -4, c.h0 - PAD + q, 0, c.n);
           if (++s == NRAW) { s = 0; sph ^= 1u; }
+        }
+        r += c.nr;
+      }
+    }
+  } else if (wid == 3) {
+    // ===== FROM_LOGITS: the warp that allocated TMEM is idle afterwards; it streams the logit rows of the OUTPUT tensor
+    // (sweep 0 writes dL/dx: rows of x = map1; sweep 1: rows of y = map0) ahead of the drain, which needs that pixel's
+    // probabilities for the softmax adjoint.  A global load inside the drain loop would put ~1 us of latency on its
+    // critical path per row pair (measured: 375 us instead of ~100 us for the kernel). =====
+    if (FROM_LOGITS && lane == 0) {
+      int t = 0, s = 0;
+      unsigned sph = 0;
+      for (int sweep = 0; sweep < 2; ++sweep)
+      for (long long r = R0; r < R1;) {
+        const Chunk c = next_chunk(r, R1, P.H, rc);
+        for (int orow = 0; orow < c.nr; ++orow, ++t) {
+          if (t >= NL) mbar_wait(&l_empty[s], sph ^ 1u, 9);
+          mbar_arrive_expect_tx(&l_full[s], raw_bytes);
+          tma_load_4d(l_ring + s * RAW_SLOT, sweep == 0 ? &map1 : &map0, &l_full[s], -4, c.h0 + orow, 0, c.n);
+          if (++s == NL) { s = 0; sph ^= 1u; }
         }
         r += c.nr;
       }
@@ -259,13 +295,36 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
         if (tid == 0 && wid == 4) TRACE(3, 2);
         unsigned char* am = a_ring + a * A_SLOT;
         const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_SLOT);
+        const int srow = c.h0 - PAD + q;                   // image row of this source row (outside the map: zero padding)
+        const bool row_in = srow >= 0 && srow < P.H;
         for (int px = tid; px < SW; px += 128) {
-          float h[10], l[10];
+          float h[10], l[10], v[10];
 #pragma unroll
-          for (int ch = 0; ch < 10; ++ch) {
-            const float v = ch < P.K ? raw[ch * SW + px] * A_SCALE : 0.f;
-            split_h(v, h[ch], l[ch]);
+          for (int ch = 0; ch < 10; ++ch) v[ch] = ch < P.K ? raw[ch * SW + px] : 0.f;
+          if (FROM_LOGITS) {
+            // softmax(logit * inv_temp) over the K channels of this pixel; pixels outside the map (TMA zero fill) must
+            // stay zero PROBABILITIES (the conv padding of iic_loss.py:123), not softmax(0) = 1/K
+            const int col = px - 4;
+            if (row_in && col >= 0 && col < P.W) {
+              float mx = v[0];
+#pragma unroll
+              for (int ch = 1; ch < 10; ++ch) if (ch < P.K) mx = fmaxf(mx, v[ch]);
+              float sum = 0.f;
+#pragma unroll
+              for (int ch = 0; ch < 10; ++ch) {
+                v[ch] = ch < P.K ? __expf((v[ch] - mx) * P.inv_temp) : 0.f;
+                sum += v[ch];
+              }
+              const float inv = 1.f / sum;
+#pragma unroll
+              for (int ch = 0; ch < 10; ++ch) v[ch] *= inv;
+            } else {
+#pragma unroll
+              for (int ch = 0; ch < 10; ++ch) v[ch] = 0.f;
+            }
           }
+#pragma unroll
+          for (int ch = 0; ch < 10; ++ch) split_h(v[ch] * A_SCALE, h[ch], l[ch]);
           const int off = (px + 4) * 16;
           const float c0[8] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
           const float c1[8] = {h[8], h[9], l[0], l[1], l[2], l[3], l[4], l[5]};
@@ -290,24 +349,32 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
   } else if (wid >= 14) {
     // ===== epilogue: drain, store, zero =====
     const int q4 = wid & 3;
+    // from logits the drain does twice the work per pixel (softmax of the output pixel + adjoint), so a second set of
+    // four warps (18-21) takes pixel tile 1; each set drains and zeroes only its tile's accumulator columns
+    const int dset = wid >= 18 ? 1 : 0;
+    const int ndset = (FROM_LOGITS && ntile == 2) ? 2 : 1;
+    const int mt0 = ndset == 2 ? dset : 0, mt1 = ndset == 2 ? dset + 1 : ntile;
+    const int zc0 = ndset == 2 ? dset * RMAX * KP : 0, zc1 = ndset == 2 ? (dset + 1) * RMAX * KP : TBUF;
     float unscale = 1.f;
     const float g0 = P.grad_loss ? __ldg(P.grad_loss) : 1.f;
     const size_t plane = (size_t)P.H * P.W;
     const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
     auto zero_accumulators = [&](int buf) {
-      for (int c = 0; c < TBUF; c += 8)
+      for (int c = zc0; c < zc1; c += 8)
         asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %1, %1, %1, %1, %1, %1, %1};" ::"r"(lane_base + buf * TBUF + c), "r"(0u) : "memory");
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_ready[buf]);
     };
+    if (dset < ndset) {
     zero_accumulators(0);
     zero_accumulators(1);
+    }
     // the weight images: these four warps are idle until the first chunk is finished.  First the power-of-two scale that
     // brings the largest coefficient magnitude into [2^12, 2^13) (every CTA finds it from the 2 x K*9*Kp4 coefficients,
     // L2-resident), then the fp16 (w1, w2) images.
-    {
+    if (dset == 0) {
       const int etid = threadIdx.x - 14 * 32;
       const int ncoef = P.K * T * T * P.Kp4;
       float mx = 0.f;
@@ -326,22 +393,33 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
         const int sweep = e / (3 * WROWS);
         build_weight_row(P.Wc[sweep], w_img + sweep * W_IMG, e - sweep * 3 * WROWS, P.K, P.Kp4, wscale);
       }
+      if (etid == 0) unscale_s = unscale;
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&w_full);
+    } else {
+      mbar_wait(&w_full, 0u, 7);                       // the first set has published the scale
+      unscale = *reinterpret_cast<volatile float*>(&unscale_s);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&w_full);
     const float g = g0 * unscale;
-    int i = 0;
-    for (int sweep = 0; sweep < 2; ++sweep)
+    int i = 0, ls = 0;
+    unsigned lph = 0;
+    for (int sweep = 0; sweep < 2 && dset < ndset; ++sweep)
     for (long long r = R0; r < R1; ++i) {
       const Chunk c = next_chunk(r, R1, P.H, rc);
       const int buf = i & 1;
       mbar_wait(&accum_full[buf], (unsigned)(i >> 1) & 1u, 8);
       asm volatile("tcgen05.fence::after_thread_sync;");
-      for (int mt = 0; mt < ntile; ++mt) {
-        const int col = mt * 128 + q4 * 32 + lane;
-        const bool live = col < P.W;
-        for (int orow = 0; orow < c.nr; orow += 2) {
+      for (int orow = 0; orow < c.nr; orow += 2) {
+        const int nrow = orow + 1 < c.nr ? 2 : 1;
+        if (FROM_LOGITS) {
+          // the logit rows of this row pair have landed (ring slots ls, ls + 1)
+          mbar_wait(&l_full[ls], lph, 10);
+          if (nrow == 2) mbar_wait(&l_full[(ls + 1) % NL], (ls + 1 == NL) ? (lph ^ 1u) : lph, 10);
+        }
+        for (int mt = mt0; mt < mt1; ++mt) {
+          const int col = mt * 128 + q4 * 32 + lane;
+          const bool live = col < P.W;
           uint32_t v[2][16];
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -359,13 +437,50 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
           if (live) {
 #pragma unroll
             for (int h = 0; h < 2; ++h) {
-              if (orow + h < c.nr) {
+              if (h < nrow) {
                 float* dst = P.out[sweep] + (size_t)c.n * P.out_sn[sweep] + (size_t)(c.h0 + orow + h) * P.W + col;
+                if (!FROM_LOGITS) {
 #pragma unroll
-                for (int o = 0; o < 10; ++o)
-                  if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                  for (int o = 0; o < 10; ++o)
+                    if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                } else {
+                  // softmax adjoint: d logit_o = inv_temp * p_o * (g_o - sum_k g_k p_k), p = softmax of the output
+                  // tensor's own logits at this pixel (staged row: column c at index c + 4, conflict-free across lanes)
+                  const float* lp = reinterpret_cast<const float*>(l_ring + ((ls + h) % NL) * RAW_SLOT) + col + 4;
+                  float pr[10];
+                  float mx = -3.0e38f;
+#pragma unroll
+                  for (int o = 0; o < 10; ++o) {
+                    pr[o] = o < P.K ? lp[o * SW] : -3.0e38f;
+                    mx = fmaxf(mx, pr[o]);
+                  }
+                  float sum = 0.f;
+#pragma unroll
+                  for (int o = 0; o < 10; ++o) {
+                    pr[o] = o < P.K ? __expf((pr[o] - mx) * P.inv_temp) : 0.f;
+                    sum += pr[o];
+                  }
+                  const float inv = 1.f / sum;
+                  float dot = 0.f;
+#pragma unroll
+                  for (int o = 0; o < 10; ++o) {
+                    pr[o] *= inv;
+                    dot = fmaf(g * __uint_as_float(v[h][o]), pr[o], dot);
+                  }
+#pragma unroll
+                  for (int o = 0; o < 10; ++o)
+                    if (o < P.K) dst[(size_t)o * plane] = P.inv_temp * pr[o] * (g * __uint_as_float(v[h][o]) - dot);
+                }
               }
             }
+          }
+        }
+        if (FROM_LOGITS) {
+          // both tiles of the row pair are done: hand the ring slots back (one arrival per drain warp)
+          __syncwarp();
+          for (int h = 0; h < nrow; ++h) {
+            if (lane == 0) mbar_arrive(&l_empty[ls]);
+            if (++ls == NL) { ls = 0; lph ^= 1u; }
           }
         }
       }
@@ -397,7 +512,8 @@ static bool make_map(CUtensorMap* map, const float* base, int B, int K, int H, i
 // Returns 0 when launched, < 0 when the shape is not covered (the caller falls back to the FFMA2 kernels), > 0 on error.
 int local_bwd_tcrb10h_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, const float* Wx, const float* Wy,
-                         const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, cudaStream_t st) {
+                         const float* grad_loss, float* gx, float* gy, long long gx_sn, long long gy_sn, int from_logits,
+                         float inv_temp, cudaStream_t st) {
   using namespace bwdrb10h;
   if ((K != 9 && K != 10) || pad != 1 || W % 4 != 0 || W > MAXW || W < 8) return -1;
   const int device = current_device();
@@ -407,11 +523,14 @@ int local_bwd_tcrb10h_try(const float* x, long long x_sn, long long x_sc, long l
   CUtensorMap mx, my;
   if (!make_map(&mx, x, B, K, H, W, x_sn, x_sc, x_sh)) return -1;
   if (!make_map(&my, y, B, K, H, W, y_sn, y_sc, y_sh)) return -1;
-  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10h_kernel), (int)(SMEM_BYTES)));
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10h_kernel<false>), (int)(SMEM_BYTES)));
+  IIC_CHECK_RC(ensure_dyn_smem((const void*)(local_bwd_tcrb10h_kernel<true>), (int)(SMEM_BYTES_FL)));
   const int Kp4 = (K + 3) & ~3;
-  Params P{B, H, W, K, {Wx, Wy}, Kp4, grad_loss, {gx, gy}, {gx_sn, gy_sn}};
+  Params P{B, H, W, K, {Wx, Wy}, Kp4, grad_loss, {gx, gy}, {gx_sn, gy_sn}, from_logits, inv_temp, {x, y}, {x_sn, y_sn}, {x_sc, y_sc},
+           {x_sh, y_sh}};
   // one launch, two sweeps per CTA: dL/dx from y (sweep 0), then dL/dy from x (sweep 1)
-  local_bwd_tcrb10h_kernel<<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
+  if (from_logits) local_bwd_tcrb10h_kernel<true><<<sms, NTHREADS_FL, SMEM_BYTES_FL, st>>>(my, mx, P);
+  else local_bwd_tcrb10h_kernel<false><<<sms, NTHREADS, SMEM_BYTES, st>>>(my, mx, P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -93,6 +93,29 @@ def test_from_logits_wide_map_falls_back(iic, cuda_device):
     assert relmax(b.grad.cpu().numpy(), O.softmax_backward(p2, g2)) <= GRAD_RTOL
 
 
+@pytest.mark.parametrize("B,H,W,T,force", [(6, 224, 224, 1.0, False), (3, 37, 44, 0.7, True), (2, 40, 248, 1.0, True)])
+def test_from_logits_tensor_core_backward(iic, cuda_device, B, H, W, T, force):
+    """The from-logits form of the fp16-split tensor-core backward (softmax in its transform warps, softmax adjoint in
+    its drain): chosen by itself at config-2 size, forced on small / ragged maps; loss and LOGIT gradients against the
+    fp64 oracle chained through its own softmax (contrastyou/trainer/_utils.py:15-23 feeding iic_loss.py:107-149)."""
+    rng = np.random.default_rng(600 + H + W)
+    l1, l2 = _logit_views(rng, B, 10, H, W)
+    with contextlib.ExitStack() as stack:
+        if force:
+            stack.enter_context(option(iic, "tc10_force", 1))
+        a = torch.from_numpy(l1).to(cuda_device).requires_grad_(True)
+        b = torch.from_numpy(l2).to(cuda_device).requires_grad_(True)
+        loss = iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=512).from_logits(a, b, T=T)
+        (0.5 * loss).backward()
+    p1, p2 = O.softmax(l1, 1, T), O.softmax(l2, 1, T)
+    ol, g1, g2 = O.iid_segmentation_small_path_loss(p1, p2, 1, 512, with_grads=True)
+    ex = relmax(a.grad.cpu().numpy(), 0.5 * O.softmax_backward(p1, g1, 1, T))
+    ey = relmax(b.grad.cpu().numpy(), 0.5 * O.softmax_backward(p2, g2, 1, T))
+    print(f"loss err {abs(loss.item() - ol) / abs(ol):.2e}, grad err {max(ex, ey):.2e}")
+    assert _loss_close(loss.item(), ol), (loss.item(), ol)
+    assert ex <= GRAD_RTOL and ey <= GRAD_RTOL, (ex, ey)
+
+
 # ---------------------------------------------------------------------------------------------------
 # many terms, ONE finish launch: the (layer x sub-head) loop of semi_seg/epocher.py:249-277
 # ---------------------------------------------------------------------------------------------------
