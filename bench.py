@@ -392,6 +392,28 @@ def count_own_launches(torch, fn):
         return None, [f"profiler unavailable: {type(e).__name__}"]
 
 
+def static_launch_count(wl, world):
+    """Fallback for gpu_launches when the profiler is unavailable: kernels of libiic_b200.so per step, from the dispatch
+    rules (joint 1; finish 1, +1 batched epilogue for large batches, +1 rank sum when they are exchanged; backward 1 per
+    local term, or 2 sweeps + 2 weight images on the K = 20 / K = 128 tensor-core kernels; global backward 1; UDA 2)."""
+    n, units, entries = 0, 0, 0
+    for kind, S, K, H, W, pad, patch, w in wl["groups"]:
+        T2 = (2 * pad + 1) ** 2
+        if kind == "local":
+            n += S * (1 + (1 if K <= 10 else 4))
+            units += S * T2
+            entries += S * T2 * K * K
+        else:
+            n += S
+            units += S
+            entries += S * K * K
+    big = units > 32 or entries > 1056
+    n += 1 + (1 if big else 0) + (1 if (big and world > 1) else 0)
+    if wl["uda"]:
+        n += 2
+    return n
+
+
 def udaiic_iteration_extra(dev, iters=8):
     """Whole udaiic training iterations/s on the REFERENCE's own UDAIICEpocher (semi_seg/epocher.py:137-188,308-323,
     loaded unmodified from oracle/_ref by oracle/ref_epocher.py), yaml defaults (K = 20, 5 sub-heads, layers Conv5 /
@@ -851,8 +873,10 @@ def run_b200(args):
                                        "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4 + d2h_grads,
                                        "ms_per_step": round(e2e_ms_g, 4)},
                     "host_buffers": "pinned, allocated after binding the process to the GPU's NUMA node", "numa": numa},
-            "gpu_launches": (n_own * args.steps) if n_own else None,
-            "gpu_launches_per_step": n_own, "gpu_kernels": own_names,
+            "gpu_launches": (n_own or static_launch_count(wl, world)) * args.steps,
+            "gpu_launches_per_step": n_own or static_launch_count(wl, world),
+            "gpu_launches_source": "counted with torch.profiler on one eager step" if n_own else "dispatch rules (profiler unavailable)",
+            "gpu_kernels": own_names,
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu_line,

@@ -55,9 +55,13 @@ constexpr int W_TARGET_LOG2 = 12;        // largest |coefficient| scaled into [2
 
 #ifdef IIC_TC_TRACE
 __device__ long long g_trace[4][64][6];
+__device__ long long g_ctrace[32][8];      // per chunk i: issuer (tile 0, parity 0) [0] before / [1] after the tmem_ready wait;
+                                           // drain warp 14 [2] before / [3] after the accum_full wait, [4] drained, [5] zeroed
 #define TRACE(role, slot) do { if (blockIdx.x == 0 && tt >= 16 && tt < 80) g_trace[role][tt - 16][slot] = clock64(); } while (0)
+#define CTRACE(slot) do { if (blockIdx.x == 0 && i < 32) g_ctrace[i][slot] = clock64(); } while (0)
 #else
 #define TRACE(role, slot) do { } while (0)
+#define CTRACE(slot) do { } while (0)
 #endif
 
 struct Params {
@@ -226,7 +230,9 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
       const uint64_t w_base = w_base0 + (uint64_t)(sweep * (W_IMG / 16));
       const Chunk c = next_chunk(r, R1, P.H, rc);
       const int buf = i & 1;
+      if (lane == 0 && wid == 1) CTRACE(0);
       mbar_wait(&tmem_ready[buf], (unsigned)(i >> 1) & 1u, 6);   // this buffer's accumulators are zeroed
+      if (lane == 0 && wid == 1) CTRACE(1);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const int nq = c.nr + T - 1;
       for (int q = 0; q < nq; ++q, ++tt) {
@@ -297,43 +303,65 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
         const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_SLOT);
         const int srow = c.h0 - PAD + q;                   // image row of this source row (outside the map: zero padding)
         const bool row_in = srow >= 0 && srow < P.H;
-        for (int px = tid; px < SW; px += 128) {
-          float h[10], l[10], v[10];
+        // Two pixels per thread (tid and tid + 128), all loads first: the traced pixel loop was latency-bound (one warp of
+        // the group per SM sub-partition, ~130 dependent instructions per pixel, stores and loads both in shared memory so
+        // the compiler would not overlap iterations) and set the stage period.  Pairs of channels are split with
+        // packed conversions -- hp = fp16x2(v), lp = fp16x2(v - float(hp)) -- and the four chunks are assembled from
+        // those registers directly (every chunk boundary of the slot layout falls on an even channel).
+        float v[2][10];
 #pragma unroll
-          for (int ch = 0; ch < 10; ++ch) v[ch] = ch < P.K ? raw[ch * SW + px] : 0.f;
+        for (int u = 0; u < 2; ++u) {
+          const int px = tid + u * 128;
+#pragma unroll
+          for (int ch = 0; ch < 10; ++ch) v[u][ch] = (ch < P.K && px < SW) ? raw[ch * SW + px] : 0.f;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const int px = tid + u * 128;
           if (FROM_LOGITS) {
             // softmax(logit * inv_temp) over the K channels of this pixel; pixels outside the map (TMA zero fill) must
             // stay zero PROBABILITIES (the conv padding of iic_loss.py:123), not softmax(0) = 1/K
             const int col = px - 4;
             if (row_in && col >= 0 && col < P.W) {
-              float mx = v[0];
+              float mx = v[u][0];
 #pragma unroll
-              for (int ch = 1; ch < 10; ++ch) if (ch < P.K) mx = fmaxf(mx, v[ch]);
+              for (int ch = 1; ch < 10; ++ch) if (ch < P.K) mx = fmaxf(mx, v[u][ch]);
               float sum = 0.f;
 #pragma unroll
               for (int ch = 0; ch < 10; ++ch) {
-                v[ch] = ch < P.K ? __expf((v[ch] - mx) * P.inv_temp) : 0.f;
-                sum += v[ch];
+                v[u][ch] = ch < P.K ? __expf((v[u][ch] - mx) * P.inv_temp) : 0.f;
+                sum += v[u][ch];
               }
               const float inv = 1.f / sum;
 #pragma unroll
-              for (int ch = 0; ch < 10; ++ch) v[ch] *= inv;
+              for (int ch = 0; ch < 10; ++ch) v[u][ch] *= inv;
             } else {
 #pragma unroll
-              for (int ch = 0; ch < 10; ++ch) v[ch] = 0.f;
+              for (int ch = 0; ch < 10; ++ch) v[u][ch] = 0.f;
             }
           }
+        }
 #pragma unroll
-          for (int ch = 0; ch < 10; ++ch) split_h(v[ch] * A_SCALE, h[ch], l[ch]);
-          const int off = (px + 4) * 16;
-          const float c0[8] = {h[0], h[1], h[2], h[3], h[4], h[5], h[6], h[7]};
-          const float c1[8] = {h[8], h[9], l[0], l[1], l[2], l[3], l[4], l[5]};
-          const float c2[8] = {l[6], l[7], l[8], l[9], h[0], h[1], h[2], h[3]};
-          const float c3[8] = {h[4], h[5], h[6], h[7], h[8], h[9], 0.f, 0.f};
-          *reinterpret_cast<uint4*>(am + off) = pack_h8(c0);
-          *reinterpret_cast<uint4*>(am + A_CHUNK + off) = pack_h8(c1);
-          *reinterpret_cast<uint4*>(am + 2 * A_CHUNK + off) = pack_h8(c2);
-          *reinterpret_cast<uint4*>(am + 3 * A_CHUNK + off) = pack_h8(c3);
+        for (int u = 0; u < 2; ++u) {
+          const int px = tid + u * 128;
+          uint32_t hp[5], lp[5];
+#pragma unroll
+          for (int c2 = 0; c2 < 5; ++c2) {
+            const float s0 = v[u][2 * c2] * A_SCALE, s1 = v[u][2 * c2 + 1] * A_SCALE;
+            const __half2 hh = __floats2half2_rn(s0, s1);
+            const float2 hf = __half22float2(hh);
+            const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+            hp[c2] = *reinterpret_cast<const uint32_t*>(&hh);
+            lp[c2] = *reinterpret_cast<const uint32_t*>(&ll);
+          }
+          if (px < SW) {
+            const int off = (px + 4) * 16;
+            // c0 = h0..7 | c1 = h8 h9 l0..5 | c2 = l6..9 h0..3 | c3 = h4..9 0 0   (see the header comment)
+            *reinterpret_cast<uint4*>(am + off) = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+            *reinterpret_cast<uint4*>(am + A_CHUNK + off) = make_uint4(hp[4], lp[0], lp[1], lp[2]);
+            *reinterpret_cast<uint4*>(am + 2 * A_CHUNK + off) = make_uint4(lp[3], lp[4], hp[0], hp[1]);
+            *reinterpret_cast<uint4*>(am + 3 * A_CHUNK + off) = make_uint4(hp[2], hp[3], hp[4], 0u);
+          }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[s]);
@@ -408,7 +436,9 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     for (long long r = R0; r < R1; ++i) {
       const Chunk c = next_chunk(r, R1, P.H, rc);
       const int buf = i & 1;
+      if (lane == 0 && wid == 14) CTRACE(2);
       mbar_wait(&accum_full[buf], (unsigned)(i >> 1) & 1u, 8);
+      if (lane == 0 && wid == 14) CTRACE(3);
       asm volatile("tcgen05.fence::after_thread_sync;");
       for (int orow = 0; orow < c.nr; orow += 2) {
         const int nrow = orow + 1 < c.nr ? 2 : 1;
@@ -485,7 +515,9 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
         }
       }
       r += c.nr;
+      if (lane == 0 && wid == 14) CTRACE(4);
       zero_accumulators(buf);
+      if (lane == 0 && wid == 14) CTRACE(5);
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");

@@ -520,11 +520,9 @@ def test_modules_are_parameter_free(iic):
 
 
 # ---------------------------------------------------------------------------------------------------
-# KEEP LAST IN THIS FILE.  Batched cluster heads (iic_b200.trainer): their outputs are channel-block views of one
-# tensor, i.e. inputs whose SAMPLE stride is not K*H*W.  The C ABI takes the strides, but no earlier GPU test passes
-# such views; this one was written after the round's last GPU run, hence non-strict xfail and last position.
+# Batched cluster heads (iic_b200.trainer): their outputs are channel-block views of one tensor, i.e. inputs whose
+# SAMPLE stride is not K*H*W (passing on the GPU since round 1's driver run; the xfail marker of its first version is gone)
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.xfail(strict=False, reason="first GPU run of strided (channel-block) inputs pending")
 def test_batched_heads_feed_strided_views(iic, cuda_device):
     from iic_b200.trainer import ClusterHead, LocalClusterHead
     torch.manual_seed(4)
