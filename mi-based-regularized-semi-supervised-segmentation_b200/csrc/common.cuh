@@ -50,6 +50,7 @@ struct Options {
   int tcp_p1 = 0;             // IIC_B200_TCP_P1: packed tensor-core joint also at padding 1 (16 <= K <= 24)
   int tcrb_p1 = 0;            // IIC_B200_TCRB_P1: row-block tensor-core backward at padding 1 whatever the map size
   int tc10_force = 0;         // IIC_B200_TC10_FORCE: K = 10 tensor-core backward whatever the map size
+  int no_tcj10 = 0;           // IIC_B200_NO_TCJ10: FFMA2 joint instead of the tensor-core joint for K <= 10, padding 1
   int tc10_tf32 = 0;          // IIC_B200_TC10_TF32: the tf32 + bf16-correction K = 10 backward instead of the fp16-split one
   int no_fused_epilogue = 0;  // IIC_B200_NO_FUSED_EPILOGUE: slot reduce and epilogue as two launches
   int xchg_timeout_ms = 0;    // IIC_B200_XCHG_TIMEOUT_MS: bound of the peer wait in the joint exchange

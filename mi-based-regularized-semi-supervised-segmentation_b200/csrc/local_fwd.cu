@@ -390,6 +390,9 @@ int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long
                        long long y_sn, long long y_sc, long long y_sh, int B, int K, int H, int W, int pad,
                        float* partial, int max_ctas, int* ncta, cudaStream_t st);
 size_t local_joint_tcp_slot_floats(int K, int pad);
+int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
+                          long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial, int max_ctas,
+                          int* ncta, int* flags, int* checked, cudaStream_t st);
 int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                         long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial,
                         size_t partial_floats, double* J_out, SlotInfo* info, cudaStream_t st);
@@ -452,7 +455,18 @@ static int local_joint_impl(const float* x, long long x_sn, long long x_sc, long
         return 0;
       }
     }
-    int rc = options().no_fast ? -1
+    // 10 clusters, 3 x 3 window, large maps (BASELINE config 2): fp16-split tensor-core joint (local_fwd_tcj10.cu)
+    int rc = -1;
+    if (!options().no_tc && !options().no_tcj10) {
+      const int sms = sm_count_cached(device);
+      if (sms > 0 && sms <= pl.slots_per_patch) {
+        rc = local_joint_tcj10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace, sms, &ncta,
+                                   flags, &checked, st);
+        if (rc == 0 && checked) flags = nullptr;
+      }
+    }
+    if (rc < 0)
+      rc = options().no_fast ? -1
                  : local_joint_fast_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad,
                                         (float*)workspace, pl.slots_per_patch, &ncta, flags, &checked, 0, 1.f, st);
     if (rc == 0 && checked) flags = nullptr;       // done inside the joint kernel

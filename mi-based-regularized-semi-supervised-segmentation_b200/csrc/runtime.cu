@@ -51,6 +51,7 @@ static const OptionEntry kOptions[] = {
     {"tcp_p1", "IIC_B200_TCP_P1", &Options::tcp_p1},
     {"tcrb_p1", "IIC_B200_TCRB_P1", &Options::tcrb_p1},
     {"tc10_force", "IIC_B200_TC10_FORCE", &Options::tc10_force},
+    {"no_tcj10", "IIC_B200_NO_TCJ10", &Options::no_tcj10},
     {"tc10_tf32", "IIC_B200_TC10_TF32", &Options::tc10_tf32},
     {"no_fused_epilogue", "IIC_B200_NO_FUSED_EPILOGUE", &Options::no_fused_epilogue},
     {"xchg_timeout_ms", "IIC_B200_XCHG_TIMEOUT_MS", &Options::xchg_timeout_ms},

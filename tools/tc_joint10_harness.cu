@@ -1,0 +1,65 @@
+// Stand-alone timing harness for the fp16-split tensor-core joint (csrc/local_fwd_tcj10.cu): the kernel alone, and with
+// one pipeline stage switched off at a time (which stage bounds the row rate).
+//   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -DIIC_TCJ_DEBUG -lcuda -o tools/_bin/tc_joint10 tools/tc_joint10_harness.cu
+//   tools/_bin/tc_joint10 [B H W K]
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+
+#include "../mi-based-regularized-semi-supervised-segmentation_b200/csrc/common.cuh"
+namespace iic {
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) { va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof(g_err), fmt, ap); va_end(ap); }
+const char* get_error() { return g_err; }
+int current_device() { return 0; }
+int sm_count_cached(int) { return 148; }
+static Options g_opt;
+const Options& options() { return g_opt; }
+int ensure_dyn_smem(const void* f, int bytes) { return cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes) == cudaSuccess ? 0 : 1; }
+}
+#include "../mi-based-regularized-semi-supervised-segmentation_b200/csrc/local_fwd_tcj10.cu"
+
+int main(int argc, char** argv) {
+  int B = 32, H = 224, W = 224, K = 10;
+  if (argc >= 5) { B = atoi(argv[1]); H = atoi(argv[2]); W = atoi(argv[3]); K = atoi(argv[4]); }
+  const size_t n = (size_t)B * K * H * W;
+  std::vector<float> h(n);
+  srand(3);
+  for (size_t i = 0; i < n; ++i) h[i] = (float)rand() / RAND_MAX / K * 2.f;
+  float *dx_, *dy_, *part;
+  cudaMalloc(&dx_, n * 4); cudaMalloc(&dy_, n * 4); cudaMalloc(&part, (size_t)148 * 9 * K * K * 4);
+  cudaMemcpy(dx_, h.data(), n * 4, cudaMemcpyHostToDevice);
+  cudaMemcpy(dy_, h.data(), n * 4, cudaMemcpyHostToDevice);
+  using namespace iic;
+  using namespace iic::fwdtcj10;
+  CUtensorMap mx, my;
+  const long long sc = (long long)H * W, sn = sc * K;
+  if (!make_map_4d(&mx, dx_, B, K, H, W, sn, sc, W, W + 8, 1, K) || !make_map_4d(&my, dy_, B, K, H, W, sn, sc, W, W + 8, 1, K)) { printf("map failed\n"); return 1; }
+  ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES);
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  const int modes[] = {0, 1, 2, 3, 4, 5, 6, 7};
+  for (int m : modes) {
+    Params P; P.B = B; P.H = H; P.W = W; P.K = K; P.partial = part; P.flags = nullptr; P.dbg = m;
+    local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(mx, my, P);
+    cudaError_t err = cudaDeviceSynchronize();
+    if (err != cudaSuccess) { printf("mode %d: %s\n", m, cudaGetErrorString(err)); return 1; }
+    const int reps = 5;
+    cudaEventRecord(e0);
+    for (int r = 0; r < reps; ++r) local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(mx, my, P);
+    cudaEventRecord(e1);
+    cudaDeviceSynchronize();
+    float ms; cudaEventElapsedTime(&ms, e0, e1);
+    printf("mode %d (%s%s%s): %.1f us\n", m, m & 1 ? "no-mma " : "", m & 2 ? "no-transform " : "", m & 4 ? "no-tma" : "", ms / reps * 1e3);
+    if (m == 0 || m == 7 || m == 3) {
+      static long long tr[5][256];
+      cudaMemcpyFromSymbol(tr, g_tcj_trace, sizeof(tr));
+      const long long t0 = tr[0][0];
+      printf("  job: producer-issue | transform: loop-top, raw-ready, job-end | issuer: row-ready   (clk from first TMA issue)\n");
+      for (int i = 20; i < 44; ++i)
+        printf("  %3d: %7lld | %7lld %7lld %7lld | %7lld\n", i, tr[0][i] - t0, tr[2][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[1][i] - t0);
+    }
+  }
+  return 0;
+}
