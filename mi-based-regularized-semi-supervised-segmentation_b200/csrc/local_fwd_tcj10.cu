@@ -1,20 +1,22 @@
-// Joint of the local IIC term on the tensor cores for 10 clusters, 3 x 3 window (BASELINE config 2):
+// Joint of the local IIC term on the tensor cores for up to 10 clusters, 3 x 3 window (BASELINE config 2):
 //   J[dy][dx][i][j] = sum_{n,u,v} x[n,i,u+dy-1,v+dx-1] * y[n,j,u,v]                       (iic_loss.py:120-123)
 // The FFMA2 kernel (local_fwd_fast3.inc) needs 900 FMAs per pixel and sits at 57 % of the FP32 pipe; the round-1
 // tensor-core attempt lost because every x element was rewritten six times (three column shifts x fp32 + bf16 copies).
 // Here every element is written ONCE:
 //   * operands are fp16 hi/lo pairs (a = a1 + a2, 22 bits; all four part products are computed, fp32 accumulation),
-//     staged PIXEL-major: one 64-byte group of 32 slots per pixel, [a1(0..9) a2(0..9) 0 x 12], 64-byte swizzled;
-//   * the MMA consumes them MN-major (reduction = pixels, 16 per instruction): the M atoms of A are four consecutive x
-//     rows (dy - 1 .. dy + 2, the fourth unused), the N atoms of B are the SAME y row at three pixel shifts -- an atom
-//     stride of one pixel (64 bytes), i.e. overlapping atoms: tools/mn_major_micro.cu shows the hardware takes them and
-//     applies the swizzle to the absolute address.  One MMA (M = 128, N = 96, K = 16 pixels) therefore adds 16 pixels of
-//     one y row into all nine displacements: D[(dy, x slot), (shift, y slot)].
-// Pipeline per CTA (one per SM, its share of the B*H image rows): TMA row loads (x and y interleaved) -> eight transform
-// warps (thread = pixel: split, pack, four swizzled 16-byte stores; the simplex assertion of iic_loss.py:113 rides along)
-// -> one issuing lane -> five TMEM accumulator sets taken round robin by y row (shortens every accumulation run: the
-// tensor core accumulates in fp32 with truncation, local_fwd_tc.cu) -> at the end four warps drain the sets, add the parts
-// and write this CTA's slot in the standard [d][i][j] layout that iic_finish reduces.
+//     staged PIXEL-major: one 128-byte group per pixel holding TWO image rows, 32 slots each
+//     [a1(0..9) a2(0..9) 0 x 12 | the same for the next row], 128-byte swizzled;
+//   * the MMA consumes them MN-major (reduction = pixels, 16 per instruction).  The M atoms of A are two consecutive x row
+//     pairs (four rows); the N atoms of B are the SAME y row pair at three pixel shifts -- an atom stride of one pixel, i.e.
+//     overlapping atoms: tools/mn_major_micro.cu shows the hardware takes them and applies the swizzle to the absolute
+//     address.  One MMA (M = 128, N = 192, K = 16 pixels) adds 16 pixels of two y rows into all nine displacements:
+//     D[(x row a, x slot), (shift, y row r, y slot)], dy = a - r.
+// Per CTA (one per SM, its share of the B*H image rows): eight warps stage the x row pairs and eight the y row pairs
+// straight from global memory (thread = two pixels of a row, 8-byte loads, the next pair's loads in flight while this one is split,
+// packed and stored with swizzled 16-byte stores; the simplex assertion of iic_loss.py:113 rides along) -> one issuing
+// lane -> two TMEM accumulator sets taken in turn by y row pair -> four warps read each set out as soon as its pair is done
+// (fp32 register sums: short tensor-core accumulation runs keep the truncation bias of the TMEM adds below 2e-6) and at
+// the end add the (part x part) products and the two y rows and write this CTA's slot in the [d][i][j] layout of iic_finish.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -27,288 +29,346 @@ namespace fwdtcj10 {
 using namespace tc;
 
 constexpr int PAD = 1;
-constexpr int NPXB = 256;                // pixels per row buffer
-constexpr int ROWB = NPXB * 64;          // 16 KB: [pixel][32 fp16 slots]
-constexpr int NX = 5, NXM = 2;           // x row ring + mirror slots (slots 0, 1 are written twice so that four consecutive
-                                         // slots starting anywhere in the ring are contiguous)
-constexpr int NY = 3;                    // y row ring; NX = NY + 2 lets one wait cover both rings (see the transform loop)
-constexpr int NRAW = 4;
-constexpr int RAW_SLOT = 10 * 256 * 4;   // 10240: fp32 [K][W + 8]
-constexpr int NSET = 5;                  // TMEM accumulator sets of 96 columns
-constexpr int NCOL = 96;
-constexpr int MAXW = 236;                // (W + 2) pixels of an x row in at most 15 k-steps of 16
-constexpr int NTHREADS = 14 * 32;        // warps: 0 TMA, 1 issuer, 2-9 transform, 10-13 drain (13 also allocates TMEM)
-constexpr int X_BYTES = (NX + NXM) * ROWB;
-constexpr int SMEM_BYTES = X_BYTES + NY * ROWB + NRAW * RAW_SLOT + 1024;
-constexpr float SCALE = 256.f;           // both maps are scaled by 2^8 before the split; 2^-16 in the drain
+constexpr int NPXB = 248;                // pixels per row-pair buffer (15 k-steps of 16 + the two shifts, rounded to 8)
+constexpr int PAIRB = NPXB * 128;        // 31744 bytes, a multiple of the 1024-byte swizzle period
+constexpr int NXP = 4;                   // x pair ring; slot 0 is mirrored in slot NXP so that two consecutive slots
+                                         // starting anywhere in the ring are contiguous
+constexpr int NYP = 2;                   // y pair ring
+constexpr int NSET = 2, NCOL = 192;      // TMEM accumulator sets (NSET == NYP: y_done of a pair is also "set full")
+constexpr float SCALE = 1024.f;          // both maps are scaled by 2^10 before the split; 2^-20 in the drain
+constexpr int MAXW = 236;                // (W + 2) pixels of an x row in at most 15 k-steps
+constexpr int NTHREADS = 20 * 32;        // warps: 0-7 x pairs, 8-15 y pairs, 16-19 drain; 16 also allocates TMEM and issues the MMAs
+constexpr int X_BYTES = (NXP + 1) * PAIRB;
+constexpr int SMEM_BYTES = X_BYTES + NYP * PAIRB + 1024;
 
 struct Params {
+  const float* x; long long x_sn, x_sc, x_sh;
+  const float* y; long long y_sn, y_sc, y_sh;
   int B, H, W, K;
   float* partial;      // [gridDim.x][9][K][K]
   int* flags;          // nullable: simplex assertion on x
 #ifdef IIC_TCJ_DEBUG
-  int dbg;             // harness only: 1 = no MMAs, 2 = no transform work, 4 = no TMA loads
+  int dbg;             // harness only: 1 = no MMAs, 2 = no transform work, 8 = no global loads, 16 = issuer does not wait
 #endif
 };
 #ifdef IIC_TCJ_DEBUG
 #define TCJ_DBG(bit) (P.dbg & (bit))
-__device__ long long g_tcj_trace[5][256];
-#define TCJ_T(role, idx) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 256) g_tcj_trace[role][idx] = clock64(); } while (0)
+__device__ long long g_tcj_trace[4][64];
+#define TCJ_T(role, idx) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_tcj_trace[role][idx] = clock64(); } while (0)
 #else
-#define TCJ_DBG(bit) 0
 #define TCJ_T(role, idx) do { } while (0)
+#define TCJ_DBG(bit) 0
 #endif
 
-// MN-major, SWIZZLE_64B: LBO = byte stride between the 32-slot atoms along M / N, SBO = stride between groups of 8 pixels
-__device__ __forceinline__ uint64_t make_desc_mn_sw64(uint32_t saddr, uint32_t lbo_bytes) {
+// MN-major, SWIZZLE_128B: LBO = byte stride between the 64-slot atoms along M / N, SBO = stride between groups of 8 pixels
+__device__ __forceinline__ uint64_t make_desc_mn_sw128(uint32_t saddr, uint32_t lbo_bytes) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
-  d |= (uint64_t)(512 >> 4) << 32;
+  d |= (uint64_t)(1024 >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)4 << 61;
+  d |= (uint64_t)2 << 61;
   return d;
 }
 
-// the chunk of image rows that starts at global row r (rows of all images, B*H) inside the CTA share [r, R1)
-struct Chunk { int n, h0, nr; };
-__device__ __forceinline__ Chunk next_chunk(long long r, long long R1, int H) {
+// Walk over the chunks (rows of one image) of the CTA share [R0, R1) of the B*H image rows.  Local x row lr is image row
+// h0 - 1 + lr, local y row ly is image row h0 + ly; y pair Q (rows 2Q, 2Q+1) meets x pairs Q and Q + 1 (rows 2Q .. 2Q+3).
+struct Chunk {
+  int n, h0, nr, npy;          // image, first row, rows, y pairs (x pairs = npy + 1)
+};
+__device__ __forceinline__ Chunk chunk_at(long long r, long long R1, int H) {
   Chunk c;
   c.n = (int)(r / H);
   c.h0 = (int)(r - (long long)c.n * H);
   c.nr = H - c.h0;
   if (c.nr > R1 - r) c.nr = (int)(R1 - r);
+  c.npy = (c.nr + 1) >> 1;
   return c;
 }
 
-__global__ void __launch_bounds__(NTHREADS, 1)
-local_joint_tcj10_kernel(const __grid_constant__ CUtensorMap mapx, const __grid_constant__ CUtensorMap mapy, const Params P) {
+// One thread stages two consecutive pixels of one row of the pair, all channels (ten 8-byte loads).  Thread t of the 256 of
+// a group: row t / npp, pixel pair t % npp (npp = W / 2 <= 128).  The staging is bound by instruction issue and latency,
+// not by bytes: sixteen staging warps with little work each, and loads without predicates -- a row or column outside
+// the map is read from the nearest one inside and multiplied by zero (`mul`, which otherwise carries the 2^10 scale).
+struct Tile { float2 f[10]; float mul; };
+
+template <bool IS_Y, bool FULLK>
+__device__ __forceinline__ void load_tile(Tile& t, const Params& P, const Chunk& c, int pair, int pp, int rr) {
+  const float* base = IS_Y ? P.y : P.x;
+  const long long sn = IS_Y ? P.y_sn : P.x_sn, sc = IS_Y ? P.y_sc : P.x_sc, sh = IS_Y ? P.y_sh : P.x_sh;
+  const int npp = P.W >> 1;
+  const int lrow = 2 * pair + rr;
+  const int row = IS_Y ? c.h0 + lrow : c.h0 - PAD + lrow;
+  // y rows past the chunk belong to another CTA (or image): they must count as zero.  x rows past the rows any valid
+  // y row meets only multiply those zeros, so any finite value will do (row inside the image) or zero (outside).
+  const bool ok = pp < npp && row >= 0 && row < P.H && (!IS_Y || lrow < c.nr) && !TCJ_DBG(8);
+  t.mul = ok ? SCALE : 0.f;
+  const int rowc = min(max(row, 0), P.H - 1), ppc = min(pp, npp - 1);
+  const float* ptr = base + (long long)c.n * sn + (long long)rowc * sh + 2 * ppc;
+#pragma unroll
+  for (int ch = 0; ch < 10; ++ch)
+    t.f[ch] = __ldg(reinterpret_cast<const float2*>(ptr + (FULLK ? ch : min(ch, P.K - 1)) * sc));
+}
+
+// Split, pack and store one thread's two pixels into the pair buffer(s): pixel b = column + boff, the row's three 16-byte
+// chunks at ((4 * row + k) ^ (b & 7)).  Eight consecutive lanes (one phase of a 128-bit store) hold pixels 2 apart, which
+// the swizzle sends to four distinct bank groups only; so the upper four lanes of a phase take their two pixels in the
+// other order and the eight stores of a phase fall on eight different groups.
+// Split of the value scaled by 2^10: hi = cut to 11 significant bits (a mask; exact in fp16), lo = fp16(value - hi): 21-22
+// bits in all.  The scale keeps the lo parts out of the fp16 subnormals, which the tensor core reads as zero (measured:
+// unscaled maps lose 1.5e-4 of the joint); what still falls below 2^-14 is at most 6e-8 of the unscaled value range.
+template <bool FULLK>
+__device__ __forceinline__ void store_tile(const Tile& t, unsigned char* dst, unsigned char* dst2, int boff, int pp, int rr,
+                                           bool flip, int K) {
+  float2 hi[10], lo[10];
+#pragma unroll
+  for (int ch = 0; ch < 10; ++ch) {
+    const float m = (FULLK || ch < K) ? t.mul : 0.f;
+    const float2 sv = __fmul2_rn(t.f[ch], make_float2(m, m));
+    hi[ch] = make_float2(__uint_as_float(__float_as_uint(sv.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(sv.y) & 0xFFFFE000u));
+    lo[ch] = __ffma2_rn(hi[ch], make_float2(-1.f, -1.f), sv);
+  }
+  const int cb = 4 * rr;
+#pragma unroll
+  for (int s2 = 0; s2 < 2; ++s2) {
+    uint32_t hp[5], lp[5];
+#pragma unroll
+    for (int c2 = 0; c2 < 5; ++c2) {
+      const __half2 h0 = __floats2half2_rn(hi[2 * c2].x, hi[2 * c2 + 1].x), h1 = __floats2half2_rn(hi[2 * c2].y, hi[2 * c2 + 1].y);
+      const __half2 l0 = __floats2half2_rn(lo[2 * c2].x, lo[2 * c2 + 1].x), l1 = __floats2half2_rn(lo[2 * c2].y, lo[2 * c2 + 1].y);
+      const uint32_t uh0 = *reinterpret_cast<const uint32_t*>(&h0), uh1 = *reinterpret_cast<const uint32_t*>(&h1);
+      const uint32_t ul0 = *reinterpret_cast<const uint32_t*>(&l0), ul1 = *reinterpret_cast<const uint32_t*>(&l1);
+      hp[c2] = ((s2 == 0) != flip) ? uh0 : uh1;
+      lp[c2] = ((s2 == 0) != flip) ? ul0 : ul1;
+    }
+    const int b = 2 * pp + (s2 ^ (flip ? 1 : 0)) + boff;
+    const int sw = b & 7;
+    // slots [h0..h9 | l0..l9 | 0 x 12] = chunks (h0-7) (h8 h9 l0-5) (l6-9 0 0 0 0) (0)
+    const uint4 c0 = make_uint4(hp[0], hp[1], hp[2], hp[3]);
+    const uint4 c1 = make_uint4(hp[4], lp[0], lp[1], lp[2]);
+    const uint4 c2v = make_uint4(lp[3], lp[4], 0u, 0u);
+    unsigned char* px = dst + b * 128;
+    *reinterpret_cast<uint4*>(px + (((cb + 0) ^ sw) << 4)) = c0;
+    *reinterpret_cast<uint4*>(px + (((cb + 1) ^ sw) << 4)) = c1;
+    *reinterpret_cast<uint4*>(px + (((cb + 2) ^ sw) << 4)) = c2v;
+    if (dst2) {
+      unsigned char* px2 = dst2 + b * 128;
+      *reinterpret_cast<uint4*>(px2 + (((cb + 0) ^ sw) << 4)) = c0;
+      *reinterpret_cast<uint4*>(px2 + (((cb + 1) ^ sw) << 4)) = c1;
+      *reinterpret_cast<uint4*>(px2 + (((cb + 2) ^ sw) << 4)) = c2v;
+    }
+  }
+}
+
+// The staging loop of one group of eight warps (x: warps 0-7, y: warps 8-15).  Pair number `count` of the group (running
+// over the chunks) goes to ring slot count % NRING once the slot's last occupant has been read: x slots are released by
+// the issuer's x_free commits, y slots by y_done.  The next pair's loads are issued before this pair is converted; the two
+// register tiles swap roles every step.
+template <bool IS_Y, bool FULLK>
+__device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long long R1, unsigned char* ring,
+                                            unsigned char* mirror, uint64_t* full, uint64_t* released) {
+  constexpr int NRING = IS_Y ? NYP : NXP;
+  const int tid = threadIdx.x & 255, lane = threadIdx.x & 31;
+  const int npp = P.W >> 1, rr = tid >= npp ? 1 : 0, pp = tid - rr * npp;
+  const bool flip = (lane >> 2) & 1;
+  long long r = R0;
+  if (r >= R1) return;
+  Chunk c = chunk_at(r, R1, P.H);
+  int pl = 0, count = 0;
+  bool bad = false;
+  Tile ta, tb;
+  load_tile<IS_Y, FULLK>(ta, P, c, 0, pp, rr);
+  // one step: issue the loads of the job after this one into `nxt`, then convert and publish `cur`; false after the last job
+  auto step = [&](Tile& cur, Tile& nxt) -> bool {
+    long long rn = r;
+    Chunk cn = c;
+    int pn = pl + 1;
+    if (pn >= (IS_Y ? c.npy : c.npy + 1)) { rn = r + c.nr; pn = 0; if (rn < R1) cn = chunk_at(rn, R1, P.H); }
+    const bool more = rn < R1;
+    if (more) load_tile<IS_Y, FULLK>(nxt, P, cn, pn, pp, rr);
+    if (count >= NRING) mbar_wait(&released[count % NRING], (unsigned)(count / NRING - 1) & 1u, IS_Y ? 3 : 2);
+    const int slot = count % NRING;
+    if (!TCJ_DBG(2)) {
+      if (!IS_Y && P.flags && cur.mul != 0.f) {
+        // simplex(x_out) of iic_loss.py:113 on the rows of the map
+        float2 sum = cur.f[0];
+#pragma unroll
+        for (int ch = 1; ch < 10; ++ch) sum = __fadd2_rn(sum, (FULLK || ch < P.K) ? cur.f[ch] : make_float2(0.f, 0.f));
+        if (!(fabsf(sum.x - 1.f) <= 2e-4f) || !(fabsf(sum.y - 1.f) <= 2e-4f)) bad = true;
+      }
+      if (pp < npp)
+        store_tile<FULLK>(cur, ring + slot * PAIRB, (!IS_Y && slot == 0) ? mirror : nullptr, IS_Y ? 2 : 1, pp, rr, flip, P.K);
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[slot]);
+    ++count;
+    r = rn; c = cn; pl = pn;
+    return more;
+  };
+  while (true) {
+    if (!step(ta, tb)) break;
+    if (!step(tb, ta)) break;
+  }
+  if (!IS_Y && P.flags && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Params P) {
   extern __shared__ __align__(1024) unsigned char smem_dyn[];
-  __shared__ __align__(8) uint64_t raw_full[NRAW], raw_empty[NRAW], y_full[NY], y_done[NY], all_done;
+  __shared__ __align__(8) uint64_t x_full[NXP], x_free[NXP], y_full[NYP], y_done[NYP], set_free[NSET];
   __shared__ uint32_t tmem_base_s;
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* x_ring = smem;
   unsigned char* y_ring = smem + X_BYTES;
-  unsigned char* raw_ring = y_ring + NY * ROWB;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const long long rows_total = (long long)P.B * P.H;
   const long long R0 = (long long)blockIdx.x * rows_total / gridDim.x;
   const long long R1 = (long long)(blockIdx.x + 1) * rows_total / gridDim.x;
-  const int SW = P.W + 8;
-  const int raw_bytes = P.K * SW * 4;
   const int ksteps = (P.W + 2 + 15) / 16;
+  if (wid == 0) TCJ_T(0, 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 8); }
-    for (int s = 0; s < NY; ++s) { mbar_init(&y_full[s], 8); mbar_init(&y_done[s], 1); }
-    mbar_init(&all_done, 1);
+    for (int s = 0; s < NXP; ++s) { mbar_init(&x_full[s], 8); mbar_init(&x_free[s], 1); }
+    for (int s = 0; s < NYP; ++s) { mbar_init(&y_full[s], 8); mbar_init(&y_done[s], 1); }
+    for (int s = 0; s < NSET; ++s) mbar_init(&set_free[s], 3);
     mbar_fence_init();
   }
-  if (wid == 13) {
+  if (wid == 16) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
-  // the row buffers start as zeros: the columns outside the map (and slots 20..31) are never written again
-  for (int e = threadIdx.x; e < (X_BYTES + NY * ROWB) / 16; e += NTHREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
+  // the pair buffers start as zeros: the columns outside the map and the unused slots are never written again
+  for (int e = threadIdx.x; e < (X_BYTES + NYP * PAIRB) / 16; e += NTHREADS) reinterpret_cast<uint4*>(smem)[e] = make_uint4(0, 0, 0, 0);
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;");
   const uint32_t tmem_base = tmem_base_s;
+  if (wid == 0) TCJ_T(0, 1);
 
-  if (wid == 0) {
-    // ===== TMA producer: raw rows in job order  X(h0-1) X(h0) X(h0+1) Y(h0) X(h0+2) Y(h0+1) ... X(h0+nr) Y(h0+nr-1) =====
-    if (lane == 0) {
-      tma_prefetch_desc(&mapx);
-      tma_prefetch_desc(&mapy);
-      int t = 0, s = 0;
-      unsigned sph = 0;
-      for (long long r = R0; r < R1;) {
-        const Chunk c = next_chunk(r, R1, P.H);
-        const int njobs = 2 * c.nr + 2;
-        for (int j = 0; j < njobs; ++j, ++t) {
-          // job j: j < 3 -> X local row j; else alternating Y(ly), X(lr): j = 3 + 2*ly -> Y(ly); j = 4 + 2*ly -> X(ly + 3)
-          const bool is_y = j >= 3 && ((j - 3) & 1) == 0;
-          const int lrow = j < 3 ? j : (is_y ? (j - 3) / 2 : (j - 4) / 2 + 3);
-          if (t >= NRAW) mbar_wait(&raw_empty[s], sph ^ 1u, 1);
-          TCJ_T(0, t);
-          if (TCJ_DBG(4)) { mbar_arrive(&raw_full[s]); if (++s == NRAW) { s = 0; sph ^= 1u; } continue; }
-          mbar_arrive_expect_tx(&raw_full[s], raw_bytes);
-          if (is_y) tma_load_4d(raw_ring + s * RAW_SLOT, &mapy, &raw_full[s], -4, c.h0 + lrow, 0, c.n);
-          else tma_load_4d(raw_ring + s * RAW_SLOT, &mapx, &raw_full[s], -4, c.h0 - PAD + lrow, 0, c.n);
-          if (++s == NRAW) { s = 0; sph ^= 1u; }
-        }
-        r += c.nr;
-      }
+  if (wid < 16) {
+    if (P.K == 10) {
+      if (wid < 8) stage_pairs<false, true>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
+      else stage_pairs<true, true>(P, R0, R1, y_ring, nullptr, y_full, y_done);
+    } else {
+      if (wid < 8) stage_pairs<false, false>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
+      else stage_pairs<true, false>(P, R0, R1, y_ring, nullptr, y_full, y_done);
     }
-  } else if (wid == 1) {
-    // ===== MMA issuer: per y row `ksteps` MMAs (M = 128: four x rows; N = 96: the y row at three shifts; K = 16 pixels) =====
-    // kind::f16, fp16 operands, fp32 accumulator, A and B MN-major (bits 15, 16), N = 96, M = 128
+  } else {
+    // ===== warps 16-19: MMA issue (warp 16) and drain (all four, TMEM lane quarter = wid & 3) =====
+    // Issue, per y row pair: `ksteps` MMAs (M = 128: two x pairs; N = 192: the y pair at three shifts; K = 16 pixels),
+    // kind::f16, fp16 operands, fp32 accumulator, A and B MN-major (bits 15, 16).
+    // Drain: every pair's accumulator set is read out as soon as its MMAs are done and added up in registers in fp32 with
+    // rounding -- the tensor core adds with truncation, and runs longer than one pair (15 MMAs) would leave a bias of 1e-5
+    // in the joint (measured with two sets accumulated over the CTA's whole share: 1.7e-5).  Warp 16 issues pair q + 1
+    // before it drains pair q, so the tensor pipe always has the next pair queued; the set of pair q is needed again by
+    // pair q + 2, which that warp issues after the drain and the other three report through set_free.
     const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NCOL >> 3) << 17) | (8u << 24);
-    int yg = 0, xbase = 0;                 // running counts of y rows and of x rows at the chunk start
-    for (long long r = R0; r < R1;) {
-      const Chunk c = next_chunk(r, R1, P.H);
-      for (int ly = 0; ly < c.nr; ++ly, ++yg) {
-        const int ys = yg % NY;
-        mbar_wait(&y_full[ys], (unsigned)(yg / NY) & 1u, 5);       // y row ly and x rows ly .. ly + 2 are in place
-        asm volatile("tcgen05.fence::after_thread_sync;");
-        TCJ_T(1, yg);
-        if (lane == 0) {
-          const int xs = (xbase + ly) % NX;                         // slot of x local row ly (= image row u - 1)
-          const uint64_t a0 = make_desc_mn_sw64(smem_u32(x_ring + xs * ROWB), ROWB);
-          const uint64_t b0 = make_desc_mn_sw64(smem_u32(y_ring + ys * ROWB), 64);
-          const uint32_t d_tmem = tmem_base + (uint32_t)((yg % NSET) * NCOL);
-          for (int k = 0; k < (TCJ_DBG(1) ? 0 : ksteps); ++k)
-            umma_bf16(d_tmem, a0 + (uint64_t)(k * 64), b0 + (uint64_t)(k * 64), idesc, (yg >= NSET || k > 0) ? 1u : 0u);   // 16 pixels = 1024 bytes = 64 address units
-          umma_commit(&y_done[ys]);
-        }
-        __syncwarp();
+    const int a = wid & 3;                      // TMEM lane quarter = x row of the A tile
+    const uint32_t lane_base = tmem_base + ((uint32_t)(a * 32) << 16);
+    // tot[shift][y row][j]: the hi and lo y slots added
+    float tot[3][2][10];
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int yr = 0; yr < 2; ++yr)
+#pragma unroll
+        for (int j = 0; j < 10; ++j) tot[s][yr][j] = 0.f;
+
+    auto issue = [&](int yq, int ql, int xpbase, bool last_of_chunk) {
+      const int ys = yq % NYP;
+      const int xp1 = xpbase + ql + 1;                    // the later of the two x pairs (staged in order)
+      mbar_wait(&y_full[ys], (unsigned)(yq / NYP) & 1u, 5);
+      mbar_wait(&x_full[xp1 % NXP], (unsigned)(xp1 / NXP) & 1u, 6);
+      // the accumulator set of this pair has been read out by the other three drain warps (pair yq - NSET)
+      if (yq >= NSET) mbar_wait(&set_free[yq % NSET], (unsigned)((yq - NSET) / NSET) & 1u, 7);
+      asm volatile("tcgen05.fence::after_thread_sync;");
+      TCJ_T(1, yq);
+      if (lane == 0) {
+        const int xs = (xpbase + ql) % NXP;
+        const uint64_t a0 = make_desc_mn_sw128(smem_u32(x_ring + xs * PAIRB), PAIRB);
+        const uint64_t b0 = make_desc_mn_sw128(smem_u32(y_ring + ys * PAIRB), 128);
+        const uint32_t d_tmem = tmem_base + (uint32_t)((yq % NSET) * NCOL);
+        for (int k = 0; k < (TCJ_DBG(1) ? 0 : ksteps); ++k)     // 16 pixels = 2048 bytes = 128 address units
+          umma_bf16(d_tmem, a0 + (uint64_t)(k * 128), b0 + (uint64_t)(k * 128), idesc, k > 0 ? 1u : 0u);
+        umma_commit(&y_done[ys]);
+        // x pair ql is not read again; neither is the chunk's last x pair after its last y pair
+        umma_commit(&x_free[xs]);
+        if (last_of_chunk) umma_commit(&x_free[(xpbase + ql + 1) % NXP]);
       }
-      xbase += c.nr + 2;
-      r += c.nr;
-    }
-    if (lane == 0) umma_commit(&all_done);
-    __syncwarp();
-  } else if (wid >= 2 && wid < 10) {
-    // ===== transform: all eight warps take every job together, thread = pixel column =====
-    const int tid = threadIdx.x - 64;           // 0..255
-    int t = 0, s = 0, yg = 0, xg = 0;           // job counter, raw slot, running y / x row counts
-    unsigned sph = 0;
-    bool bad = false;
-    for (long long r = R0; r < R1;) {
-      const Chunk c = next_chunk(r, R1, P.H);
-      // a new chunk reuses x slots whose rows the previous chunk's last y rows may still be reading: wait for all of them
-      if (yg > 0)
-        for (int q = yg > NY ? yg - NY : 0; q < yg; ++q) mbar_wait(&y_done[q % NY], (unsigned)(q / NY) & 1u, 6);
-      const int njobs = 2 * c.nr + 2;
-      const int ybase = yg;
-      for (int j = 0; j < njobs; ++j, ++t) {
-        const bool is_y = j >= 3 && ((j - 3) & 1) == 0;
-        const int lrow = j < 3 ? j : (is_y ? (j - 3) / 2 : (j - 4) / 2 + 3);
-        unsigned char* dst;
-        unsigned char* dst2 = nullptr;
-        int boff;
-        if (is_y) {
-          // slot reuse: y row (yg - NY) is done -- waited for by the X job just before (below), or at the chunk start
-          dst = y_ring + (yg % NY) * ROWB;
-          boff = 2;                            // buffer pixel = column + 2
-        } else {
-          // x local row lrow takes the slot of the x row NX before it, last read by y local row lrow - NX = (lrow - 2) - NY:
-          // the same y row whose slot the NEXT job, Y(lrow - 2), reuses (NX = NY + 2): one wait serves both
-          if (lrow >= NX) {
-            const int q = ybase + lrow - NX;
-            mbar_wait(&y_done[q % NY], (unsigned)(q / NY) & 1u, 8);
-          }
-          const int xs = xg % NX;
-          dst = x_ring + xs * ROWB;
-          if (xs < NXM) dst2 = x_ring + (xs + NX) * ROWB;
-          boff = 1;                            // buffer pixel = column + 1
-        }
-        if (wid == 2) TCJ_T(2, t);
-        mbar_wait(&raw_full[s], sph, 4);
-        if (wid == 2) TCJ_T(3, t);
-        const float* raw = reinterpret_cast<const float*>(raw_ring + s * RAW_SLOT);
-        const int col = tid;
-        if (col < P.W && !TCJ_DBG(2)) {
-          float v[10];
+      __syncwarp();
+    };
+    auto drain = [&](int yq) {
+      const int st = yq % NSET;
+      mbar_wait(&y_done[yq % NYP], (unsigned)(yq / NYP) & 1u, 9);
+      asm volatile("tcgen05.fence::after_thread_sync;");
 #pragma unroll
-          for (int ch = 0; ch < 10; ++ch) v[ch] = ch < P.K ? raw[ch * SW + col + 4] : 0.f;
-          if (!is_y && P.flags) {
-            // simplex(x_out) of iic_loss.py:113 on the rows of the map (the halo rows outside it are zero fill)
-            const int img_row = c.h0 - PAD + lrow;
-            if (img_row >= 0 && img_row < P.H) {
-              float sum = 0.f;
+      for (int s = 0; s < 3; ++s) {
+        // the 20 used slots of both y rows at this shift: 16 + 4 columns each, one wait for the four loads
+        uint32_t v[2][20];
 #pragma unroll
-              for (int ch = 0; ch < 10; ++ch) sum += v[ch];
-              if (!(fabsf(sum - 1.f) <= 2e-4f)) bad = true;
-            }
-          }
-          uint32_t hp[5], lp[5];
-#pragma unroll
-          for (int c2 = 0; c2 < 5; ++c2) {
-            const float s0 = v[2 * c2] * SCALE, s1 = v[2 * c2 + 1] * SCALE;
-            const __half2 hh = __floats2half2_rn(s0, s1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
-            hp[c2] = *reinterpret_cast<const uint32_t*>(&hh);
-            lp[c2] = *reinterpret_cast<const uint32_t*>(&ll);
-          }
-          // slots [h0..h9 | l0..l9 | 0 x 12] = chunks (h0-7) (h8 h9 l0-5) (l6-9 0 0 0 0) (0); chunk index XOR (pixel >> 1) & 3
-          const int b = col + boff;
-          const int sw = (b >> 1) & 3;
-          const uint4 c0 = make_uint4(hp[0], hp[1], hp[2], hp[3]);
-          const uint4 c1 = make_uint4(hp[4], lp[0], lp[1], lp[2]);
-          const uint4 c2v = make_uint4(lp[3], lp[4], 0u, 0u);
-          unsigned char* px = dst + b * 64;
-          *reinterpret_cast<uint4*>(px + ((0 ^ sw) << 4)) = c0;
-          *reinterpret_cast<uint4*>(px + ((1 ^ sw) << 4)) = c1;
-          *reinterpret_cast<uint4*>(px + ((2 ^ sw) << 4)) = c2v;
-          if (dst2) {
-            unsigned char* px2 = dst2 + b * 64;
-            *reinterpret_cast<uint4*>(px2 + ((0 ^ sw) << 4)) = c0;
-            *reinterpret_cast<uint4*>(px2 + ((1 ^ sw) << 4)) = c1;
-            *reinterpret_cast<uint4*>(px2 + ((2 ^ sw) << 4)) = c2v;
-          }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&raw_empty[s]);
-        if (is_y) {
-          // every x row this y row pairs with was written by earlier jobs of the same eight warps: publish the row
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&y_full[yg % NY]);
-          ++yg;
-        } else {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          ++xg;
-        }
-        if (wid == 2) TCJ_T(4, t);
-        if (++s == NRAW) { s = 0; sph ^= 1u; }
-      }
-      r += c.nr;
-    }
-    if (P.flags && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
-  } else if (wid >= 10) {
-    // ===== drain: after the last MMA add the sets and the (part x part) products, write this CTA's slot =====
-    const int q4 = wid & 3;                      // TMEM lane quarter = x row atom: dy = q4 (the fourth row is not used)
-    mbar_wait(&all_done, 0, 9);
-    asm volatile("tcgen05.fence::after_thread_sync;");
-    if (q4 < 3) {
-      const long long nrows = R1 - R0;
-      const int nsets = nrows < NSET ? (int)nrows : NSET;
-      const uint32_t lane_base = tmem_base + ((uint32_t)(q4 * 32) << 16);
-      float acc[NCOL];
-#pragma unroll
-      for (int c = 0; c < NCOL; ++c) acc[c] = 0.f;
-      for (int st = 0; st < nsets; ++st) {
-#pragma unroll
-        for (int c = 0; c < NCOL; c += 16) {
-          uint32_t v[16];
+        for (int yr = 0; yr < 2; ++yr) {
+          const uint32_t col = lane_base + (uint32_t)(st * NCOL + s * 64 + yr * 32);
           asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                         "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                       : "r"(lane_base + (uint32_t)(st * NCOL + c)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int q = 0; q < 16; ++q) acc[c + q] += __uint_as_float(v[q]);
+                       : "=r"(v[yr][0]), "=r"(v[yr][1]), "=r"(v[yr][2]), "=r"(v[yr][3]), "=r"(v[yr][4]), "=r"(v[yr][5]),
+                         "=r"(v[yr][6]), "=r"(v[yr][7]), "=r"(v[yr][8]), "=r"(v[yr][9]), "=r"(v[yr][10]), "=r"(v[yr][11]),
+                         "=r"(v[yr][12]), "=r"(v[yr][13]), "=r"(v[yr][14]), "=r"(v[yr][15])
+                       : "r"(col));
+          asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                       : "=r"(v[yr][16]), "=r"(v[yr][17]), "=r"(v[yr][18]), "=r"(v[yr][19])
+                       : "r"(col + 16));
         }
-      }
-      // lane = x slot (i: hi part, 10 + i: lo part); column = 32 * shift + y slot (j: hi, 10 + j: lo); dx = 2 - shift
-      float* slot = P.partial + (size_t)blockIdx.x * (9 * P.K * P.K);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int sft = 0; sft < 3; ++sft)
+        for (int yr = 0; yr < 2; ++yr)
+#pragma unroll
+          for (int j = 0; j < 10; ++j) tot[s][yr][j] += __uint_as_float(v[yr][j]) + __uint_as_float(v[yr][10 + j]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;");
+      __syncwarp();
+      if (wid != 16 && lane == 0) mbar_arrive(&set_free[st]);
+    };
+
+    int yq = 0, xpbase = 0;
+    for (long long r = R0; r < R1;) {
+      const Chunk c = chunk_at(r, R1, P.H);
+      for (int ql = 0; ql < c.npy; ++ql, ++yq) {
+        if (wid == 16) issue(yq, ql, xpbase, ql == c.npy - 1);
+        if (yq >= 1) drain(yq - 1);
+      }
+      xpbase += c.npy + 1;
+      r += c.nr;
+    }
+    if (yq >= 1) drain(yq - 1);
+    if (wid == 16) TCJ_T(0, 2);
+    // lane = x slot (i: hi part, 10 + i: lo part).  dy = a - (y row), dx = 2 - shift.  The two y rows land in two staging
+    // arrays in shared memory (the pair buffers are free now), added when the slot is written.
+    float* stage = reinterpret_cast<float*>(smem);              // [2][9][10][10]
+#pragma unroll
+    for (int s = 0; s < 3; ++s)
+#pragma unroll
+      for (int yr = 0; yr < 2; ++yr) {
+        const int dy = a - yr;
 #pragma unroll
         for (int j = 0; j < 10; ++j) {
-          const float v = acc[sft * 32 + j] + acc[sft * 32 + 10 + j];
-          const float tot = v + __shfl_down_sync(0xffffffffu, v, 10);
-          if (lane < P.K && j < P.K)
-            slot[((size_t)(q4 * 3 + (2 - sft)) * P.K + lane) * P.K + j] = tot * (1.f / (SCALE * SCALE));
+          const float full = tot[s][yr][j] + __shfl_down_sync(0xffffffffu, tot[s][yr][j], 10);
+          if (lane < 10 && dy >= 0 && dy < 3) stage[((yr * 9 + dy * 3 + (2 - s)) * 10 + lane) * 10 + j] = full;
         }
+      }
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+    float* slot = P.partial + (size_t)blockIdx.x * (9 * P.K * P.K);
+    const int tid = threadIdx.x - 16 * 32;
+    for (int e = tid; e < 9 * P.K * P.K; e += 128) {
+      const int d = e / (P.K * P.K), ij = e - d * P.K * P.K;
+      const int i = ij / P.K, j = ij - i * P.K;
+      const int o = (d * 10 + i) * 10 + j;
+      slot[e] = (stage[o] + stage[900 + o]) * (1.f / (SCALE * SCALE));
     }
+    if (wid == 16) TCJ_T(0, 3);
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (wid == 13) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  if (wid == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 }  // namespace fwdtcj10
@@ -320,20 +380,26 @@ int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long l
                           int* ncta, int* flags, int* checked, cudaStream_t st) {
   using namespace fwdtcj10;
   *checked = 0;
-  if (pad != PAD || K < 2 || K > 10 || W % 4 != 0 || W < 8 || W > MAXW) return -1;
+  if (pad != PAD || K < 2 || K > 10 || W < 8 || W > MAXW) return -1;
   const long long rows = (long long)B * H;
-  if (rows < 4LL * max_ctas) return -1;            // small maps: the pipeline fill dominates, the FFMA2 kernel is faster
-  CUtensorMap mx, my;
-  if (!make_map_4d(&mx, x, B, K, H, W, x_sn, x_sc, x_sh, W + 8, 1, K)) return -1;
-  if (!make_map_4d(&my, y, B, K, H, W, y_sn, y_sc, y_sh, W + 8, 1, K)) return -1;
+  if (rows < 8LL * max_ctas) return -1;            // small maps: the pipeline fill dominates, the FFMA2 kernel is faster
   Params P;
+  P.x = x; P.x_sn = x_sn; P.x_sc = x_sc; P.x_sh = x_sh;
+  P.y = y; P.y_sn = y_sn; P.y_sc = y_sc; P.y_sh = y_sh;
   P.B = B; P.H = H; P.W = W; P.K = K;
   P.partial = partial;
   P.flags = flags;
+  auto rows16 = [&](const float* b, long long sn, long long sc, long long sh) {
+    return (reinterpret_cast<uintptr_t>(b) & 15) == 0 && sn % 4 == 0 && sc % 4 == 0 && sh % 4 == 0;
+  };
+  if (W % 4 != 0 || !rows16(x, x_sn, x_sc, x_sh) || !rows16(y, y_sn, y_sc, y_sh)) return -1;     // 16-byte loads
+#ifdef IIC_TCJ_DEBUG
+  P.dbg = 0;
+#endif
   *checked = flags != nullptr;
   *ncta = max_ctas;
   IIC_CHECK_RC(ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES));
-  local_joint_tcj10_kernel<<<max_ctas, NTHREADS, SMEM_BYTES, st>>>(mx, my, P);
+  local_joint_tcj10_kernel<<<max_ctas, NTHREADS, SMEM_BYTES, st>>>(P);
   IIC_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

@@ -86,6 +86,8 @@ __device__ unsigned int g_tma_dbg[8];
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned code = 0) {
   uint32_t spins = 0;
+  unsigned long long t_start = 0;
+  (void)t_start;
   while (!mbar_try_wait(bar, parity)) {
 #ifdef IIC_TMA_DEBUG
     if (++spins > (1u << 16)) {
@@ -96,7 +98,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
     }
 #else
     (void)code;
-    if (++spins > (1u << 26)) __trap();
+    // try_wait suspends the thread for a hardware-chosen time, so a spin count alone bounds nothing: 4 s by the clock
+    if ((++spins & 1023u) == 0) {
+      unsigned long long now;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+      if (t_start == 0) t_start = now;
+      else if (now - t_start > 4000000000ull) __trap();
+    }
 #endif
   }
 }

@@ -34,32 +34,32 @@ int main(int argc, char** argv) {
   cudaMemcpy(dy_, h.data(), n * 4, cudaMemcpyHostToDevice);
   using namespace iic;
   using namespace iic::fwdtcj10;
-  CUtensorMap mx, my;
   const long long sc = (long long)H * W, sn = sc * K;
-  if (!make_map_4d(&mx, dx_, B, K, H, W, sn, sc, W, W + 8, 1, K) || !make_map_4d(&my, dy_, B, K, H, W, sn, sc, W, W + 8, 1, K)) { printf("map failed\n"); return 1; }
   ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  const int modes[] = {0, 1, 2, 3, 4, 5, 6, 7};
-  for (int m : modes) {
-    Params P; P.B = B; P.H = H; P.W = W; P.K = K; P.partial = part; P.flags = nullptr; P.dbg = m;
-    local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(mx, my, P);
+  for (int m : {0, 1, 2}) {
+    Params P;
+    P.x = dx_; P.x_sn = sn; P.x_sc = sc; P.x_sh = W;
+    P.y = dy_; P.y_sn = sn; P.y_sc = sc; P.y_sh = W;
+    P.B = B; P.H = H; P.W = W; P.K = K; P.partial = part; P.flags = nullptr; P.dbg = m;
+    local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(P);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("mode %d: %s\n", m, cudaGetErrorString(err)); return 1; }
     const int reps = 5;
     cudaEventRecord(e0);
-    for (int r = 0; r < reps; ++r) local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(mx, my, P);
+    for (int r = 0; r < reps; ++r) local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(P);
     cudaEventRecord(e1);
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
-    printf("mode %d (%s%s%s): %.1f us\n", m, m & 1 ? "no-mma " : "", m & 2 ? "no-transform " : "", m & 4 ? "no-tma" : "", ms / reps * 1e3);
-    if (m == 0 || m == 7 || m == 3) {
-      static long long tr[5][256];
+    {
+      static long long tr[4][64];
       cudaMemcpyFromSymbol(tr, g_tcj_trace, sizeof(tr));
       const long long t0 = tr[0][0];
-      printf("  job: producer-issue | transform: loop-top, raw-ready, job-end | issuer: row-ready   (clk from first TMA issue)\n");
-      for (int i = 20; i < 44; ++i)
-        printf("  %3d: %7lld | %7lld %7lld %7lld | %7lld\n", i, tr[0][i] - t0, tr[2][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[1][i] - t0);
+      printf("  CTA 0: init done %lld, all MMAs done %lld, slot written %lld clk\n", tr[0][1] - t0, tr[0][2] - t0, tr[0][3] - t0);
+      printf("  pair: x-job-top y-job-top issuer-ready\n");
+      for (int i = 0; i < 16; ++i) printf("  %2d: x-top %7lld | y: top %7lld loads-issued %7lld done-wait %7lld published %7lld | issuer %7lld\n", i, tr[2][i] - t0, tr[3][4 * i] - t0, tr[3][4 * i + 1] - t0, tr[3][4 * i + 2] - t0, tr[3][4 * i + 3] - t0, tr[1][i] - t0);
     }
+    printf("mode %d (%s%s%s%s): %.1f us\n", m, m & 1 ? "no-mma " : "", m & 2 ? "no-transform " : "", m & 4 ? "no-l2-prefetch " : "", m & 8 ? "no-loads" : "", ms / reps * 1e3);
   }
   return 0;
 }
