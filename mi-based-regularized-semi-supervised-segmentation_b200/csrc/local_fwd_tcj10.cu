@@ -36,8 +36,10 @@ constexpr int NXP = 4;                   // x pair ring; slot 0 is mirrored in s
 constexpr int NYP = 2;                   // y pair ring
 constexpr int NSET = 2, NCOL = 192;      // TMEM accumulator sets (NSET == NYP: y_done of a pair is also "set full")
 constexpr float SCALE = 1024.f;          // both maps are scaled by 2^10 before the split; 2^-20 in the drain
-constexpr int MAXW = 236;                // (W + 2) pixels of an x row in at most 15 k-steps
-constexpr int NTHREADS = 20 * 32;        // warps: 0-7 x pairs, 8-15 y pairs, 16-19 drain; 16 also allocates TMEM and issues the MMAs
+constexpr int MAXW = 224;                // two rows of W / 2 pixel pairs per staging group of 224 threads; (W + 2) <= 15 k-steps of 16
+constexpr int NTHREADS = 20 * 32;        // warps: 0-6 x pairs, 7-13 y pairs, 14 and 15 MMA issue (14 allocates TMEM), 16-19 drain.
+                                         // 20 warps leave 96 registers per thread; 21 would leave 80.
+constexpr int GROUP = 7 * 32;            // threads of a staging group: two rows x W / 2 pixel pairs
 constexpr int X_BYTES = (NXP + 1) * PAIRB;
 constexpr int SMEM_BYTES = X_BYTES + NYP * PAIRB + 1024;
 
@@ -53,7 +55,7 @@ struct Params {
 };
 #ifdef IIC_TCJ_DEBUG
 #define TCJ_DBG(bit) (P.dbg & (bit))
-__device__ long long g_tcj_trace[4][64];
+__device__ long long g_tcj_trace[8][64];
 #define TCJ_T(role, idx) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_tcj_trace[role][idx] = clock64(); } while (0)
 #else
 #define TCJ_T(role, idx) do { } while (0)
@@ -160,7 +162,7 @@ __device__ __forceinline__ void store_tile(const Tile& t, unsigned char* dst, un
   }
 }
 
-// The staging loop of one group of eight warps (x: warps 0-7, y: warps 8-15).  Pair number `count` of the group (running
+// The staging loop of one group of seven warps (x: warps 0-6, y: warps 7-13).  Pair number `count` of the group (running
 // over the chunks) goes to ring slot count % NRING once the slot's last occupant has been read: x slots are released by
 // the issuer's x_free commits, y slots by y_done.  The next pair's loads are issued before this pair is converted; the two
 // register tiles swap roles every step.
@@ -168,7 +170,7 @@ template <bool IS_Y, bool FULLK>
 __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long long R1, unsigned char* ring,
                                             unsigned char* mirror, uint64_t* full, uint64_t* released) {
   constexpr int NRING = IS_Y ? NYP : NXP;
-  const int tid = threadIdx.x & 255, lane = threadIdx.x & 31;
+  const int tid = IS_Y ? threadIdx.x - GROUP : threadIdx.x, lane = threadIdx.x & 31;
   const int npp = P.W >> 1, rr = tid >= npp ? 1 : 0, pp = tid - rr * npp;
   const bool flip = (lane >> 2) & 1;
   long long r = R0;
@@ -228,12 +230,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
   if (wid == 0) TCJ_T(0, 0);
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < NXP; ++s) { mbar_init(&x_full[s], 8); mbar_init(&x_free[s], 1); }
-    for (int s = 0; s < NYP; ++s) { mbar_init(&y_full[s], 8); mbar_init(&y_done[s], 1); }
-    for (int s = 0; s < NSET; ++s) mbar_init(&set_free[s], 3);
+    for (int s = 0; s < NXP; ++s) { mbar_init(&x_full[s], 7); mbar_init(&x_free[s], 2); }
+    for (int s = 0; s < NYP; ++s) { mbar_init(&y_full[s], 7); mbar_init(&y_done[s], 1); }
+    for (int s = 0; s < NSET; ++s) mbar_init(&set_free[s], 4);
     mbar_fence_init();
   }
-  if (wid == 16) {
+  if (wid == 14) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
   }
@@ -246,23 +248,24 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
   const uint32_t tmem_base = tmem_base_s;
   if (wid == 0) TCJ_T(0, 1);
 
-  if (wid < 16) {
+  if (wid < 14) {
     if (P.K == 10) {
-      if (wid < 8) stage_pairs<false, true>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
+      if (wid < 7) stage_pairs<false, true>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
       else stage_pairs<true, true>(P, R0, R1, y_ring, nullptr, y_full, y_done);
     } else {
-      if (wid < 8) stage_pairs<false, false>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
+      if (wid < 7) stage_pairs<false, false>(P, R0, R1, x_ring, x_ring + NXP * PAIRB, x_full, x_free);
       else stage_pairs<true, false>(P, R0, R1, y_ring, nullptr, y_full, y_done);
     }
   } else {
-    // ===== warps 16-19: MMA issue (warp 16) and drain (all four, TMEM lane quarter = wid & 3) =====
+    // ===== warps 14, 15: MMA issue (even / odd pairs); warps 16-19: drain (TMEM lane quarter = wid & 3) =====
     // Issue, per y row pair: `ksteps` MMAs (M = 128: two x pairs; N = 192: the y pair at three shifts; K = 16 pixels),
     // kind::f16, fp16 operands, fp32 accumulator, A and B MN-major (bits 15, 16).
     // Drain: every pair's accumulator set is read out as soon as its MMAs are done and added up in registers in fp32 with
     // rounding -- the tensor core adds with truncation, and runs longer than one pair (15 MMAs) would leave a bias of 1e-5
-    // in the joint (measured with two sets accumulated over the CTA's whole share: 1.7e-5).  Warp 16 issues pair q + 1
-    // before it drains pair q, so the tensor pipe always has the next pair queued; the set of pair q is needed again by
-    // pair q + 2, which that warp issues after the drain and the other three report through set_free.
+    // in the joint (measured with two sets accumulated over the CTA's whole share: 1.7e-5).  tcgen05.mma of these MN-major
+    // tiles issues at the rate it executes (~130 clk each, traced: the issuing lane is held), so one warp that waits for a
+    // pair's operands and then issues leaves the tensor pipe idle during the waits (~900 clk a pair): two warps take the
+    // pairs in turn (one accumulator set each), the second waiting while the first issues.
     const uint32_t idesc = (1u << 4) | (1u << 15) | (1u << 16) | ((uint32_t)(NCOL >> 3) << 17) | (8u << 24);
     const int a = wid & 3;                      // TMEM lane quarter = x row of the A tile
     const uint32_t lane_base = tmem_base + ((uint32_t)(a * 32) << 16);
@@ -278,10 +281,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
     auto issue = [&](int yq, int ql, int xpbase, bool last_of_chunk) {
       const int ys = yq % NYP;
       const int xp1 = xpbase + ql + 1;                    // the later of the two x pairs (staged in order)
+      TCJ_T(2, yq);
       mbar_wait(&y_full[ys], (unsigned)(yq / NYP) & 1u, 5);
       mbar_wait(&x_full[xp1 % NXP], (unsigned)(xp1 / NXP) & 1u, 6);
-      // the accumulator set of this pair has been read out by the other three drain warps (pair yq - NSET)
-      if (yq >= NSET) mbar_wait(&set_free[yq % NSET], (unsigned)((yq - NSET) / NSET) & 1u, 7);
+      // the accumulator set of this pair has been read out by the four drain warps (pair yq - NSET)
+      if (yq >= NSET && !TCJ_DBG(128)) mbar_wait(&set_free[yq % NSET], (unsigned)((yq - NSET) / NSET) & 1u, 7);
       asm volatile("tcgen05.fence::after_thread_sync;");
       TCJ_T(1, yq);
       if (lane == 0) {
@@ -292,16 +296,23 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
         for (int k = 0; k < (TCJ_DBG(1) ? 0 : ksteps); ++k)     // 16 pixels = 2048 bytes = 128 address units
           umma_bf16(d_tmem, a0 + (uint64_t)(k * 128), b0 + (uint64_t)(k * 128), idesc, k > 0 ? 1u : 0u);
         umma_commit(&y_done[ys]);
-        // x pair ql is not read again; neither is the chunk's last x pair after its last y pair
+        // an x pair is read by two y pairs, issued by the two warps: each commits it once, which releases the slot when
+        // both have (x_free counts 2); a chunk's first and last x pairs have one reader, which commits twice
         umma_commit(&x_free[xs]);
+        if (ql == 0) umma_commit(&x_free[xs]);
+        umma_commit(&x_free[(xpbase + ql + 1) % NXP]);
         if (last_of_chunk) umma_commit(&x_free[(xpbase + ql + 1) % NXP]);
       }
       __syncwarp();
+      TCJ_T(3, yq);
     };
     auto drain = [&](int yq) {
       const int st = yq % NSET;
+      if (wid == 16) TCJ_T(4, yq); else if (wid == 17) TCJ_T(6, yq);
       mbar_wait(&y_done[yq % NYP], (unsigned)(yq / NYP) & 1u, 9);
       asm volatile("tcgen05.fence::after_thread_sync;");
+      if (wid == 16) TCJ_T(5, yq); else if (wid == 17) TCJ_T(7, yq);
+      if (!TCJ_DBG(64))
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
         // the 20 used slots of both y rows at this shift: 16 + 4 columns each, one wait for the four loads
@@ -326,20 +337,20 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
       }
       asm volatile("tcgen05.fence::before_thread_sync;");
       __syncwarp();
-      if (wid != 16 && lane == 0) mbar_arrive(&set_free[st]);
+      if (lane == 0) mbar_arrive(&set_free[st]);
     };
 
     int yq = 0, xpbase = 0;
     for (long long r = R0; r < R1;) {
       const Chunk c = chunk_at(r, R1, P.H);
       for (int ql = 0; ql < c.npy; ++ql, ++yq) {
-        if (wid == 16) issue(yq, ql, xpbase, ql == c.npy - 1);
-        if (yq >= 1) drain(yq - 1);
+        if (wid < 16) { if ((yq & 1) == (wid & 1)) issue(yq, ql, xpbase, ql == c.npy - 1); }
+        else drain(yq);
       }
       xpbase += c.npy + 1;
       r += c.nr;
     }
-    if (yq >= 1) drain(yq - 1);
+    if (wid >= 16) {
     if (wid == 16) TCJ_T(0, 2);
     // lane = x slot (i: hi part, 10 + i: lo part).  dy = a - (y row), dx = 2 - shift.  The two y rows land in two staging
     // arrays in shared memory (the pair buffers are free now), added when the slot is written.
@@ -365,10 +376,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
       slot[e] = (stage[o] + stage[900 + o]) * (1.f / (SCALE * SCALE));
     }
     if (wid == 16) TCJ_T(0, 3);
+    }
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-  if (wid == 16) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  if (wid == 14) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 }  // namespace fwdtcj10

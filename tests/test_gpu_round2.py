@@ -234,3 +234,76 @@ def test_combine_iic_losses_on_device(iic, cuda_device):
     g2 = torch.autograd.grad(ref, raw)
     for a, b in zip(g1, g2):
         assert torch.allclose(a, b, rtol=1e-6, atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------------
+# tensor-core joint for K <= 10, 3 x 3 window (csrc/local_fwd_tcj10.cu): fp16 hi/lo operands, accumulator sets drained every
+# row pair.  Against the fp64 convolution of iic_loss.py:120-123 and against the FFMA2 joint it replaces on large maps.
+# ---------------------------------------------------------------------------------------------------
+def _joint64(x, y, pad):
+    J = torch.nn.functional.conv2d(x.double().permute(1, 0, 2, 3), y.double().permute(1, 0, 2, 3), padding=pad)
+    return J.permute(2, 3, 0, 1).contiguous()
+
+
+@pytest.mark.parametrize("B,K,H,W,sharp,strided", [
+    (32, 10, 224, 224, 1.0, False),   # BASELINE config 2
+    (32, 10, 224, 224, 8.0, False),   # peaked maps: most products are tiny, a few are near 1
+    (9, 10, 135, 236, 2.0, False),    # odd chunk lengths (row pairs cut by the image end), the widest map the kernel takes
+    (20, 7, 64, 40, 1.0, False),      # fewer than 10 clusters, narrow map
+    (11, 9, 112, 96, 1.0, True),      # channel block of a wider head output (sample and channel strides not dense)
+])
+def test_tensor_core_joint_k10(iic, cuda_device, B, K, H, W, sharp, strided):
+    gen = torch.Generator(device=cuda_device).manual_seed(77 + B + K)
+    if strided:
+        full = (sharp * torch.randn(B, 3 * K, H, W, device=cuda_device, generator=gen))
+        x = full[:, K:2 * K].softmax(1)
+        big = torch.zeros(B, 3 * K, H, W, device=cuda_device)
+        big[:, K:2 * K] = x
+        x = big[:, K:2 * K]
+        assert not x.is_contiguous()
+    else:
+        x = (sharp * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    y = (sharp * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    ref = _joint64(x, y, 1)
+    J = iic.ops._local_joint(x, y, None, 1, H, W, H, W, check_simplex=True)[0]
+    with option(iic, "no_tcj10", 1):
+        Jf = iic.ops._local_joint(x, y, None, 1, H, W, H, W, check_simplex=True)[0]
+    iic.raise_if_flagged(cuda_device)
+    mass = ref.sum().item() / 9.0
+    err_tc = (J - ref).abs().max().item() / mass
+    err_ff = (Jf - ref).abs().max().item() / mass
+    rel_tc = ((J - ref).abs() / ref.clamp_min(1e-300)).max().item()
+    print(f"tensor-core joint: max err / mass {err_tc:.2e} (FFMA2 {err_ff:.2e}), max rel {rel_tc:.2e}")
+    assert not torch.equal(J, Jf), "the option must select a different kernel"
+    assert err_tc <= 5e-8 and rel_tc <= 4e-6
+    # the assertion of iic_loss.py:113 rides along in the staging warps
+    bad = x.clone()
+    bad[B // 2, 0, H // 2, W // 3] += 0.01
+    with iic.check_mode("deferred"):
+        iic.ops._local_joint(bad, y, None, 1, H, W, H, W, check_simplex=True)
+        with pytest.raises(AssertionError):
+            iic.raise_if_flagged(cuda_device)
+
+
+def test_tensor_core_joint_loss_and_gradients(iic, cuda_device):
+    """The whole local term at config-2 size with the tensor-core joint against the same term with the FFMA2 joint (which the
+    oracle tests pin at small batch): loss to 2e-6, gradients to 1e-4 of their maximum."""
+    B, K, H, W = 32, 10, 224, 224
+    gen = torch.Generator(device=cuda_device).manual_seed(5)
+    base = torch.randn(B, K, H // 8, W // 8, device=cuda_device, generator=gen) * 3
+    base = torch.nn.functional.interpolate(base, size=(H, W), mode="bilinear", align_corners=False)
+    x = (base + 0.5 * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    y = (base + 0.5 * torch.randn(B, K, H, W, device=cuda_device, generator=gen)).softmax(1)
+    crit = iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=512)
+    out = {}
+    for name, off in (("tc", 0), ("ffma2", 1)):
+        with option(iic, "no_tcj10", off):
+            xr, yr = x.clone().requires_grad_(True), y.clone().requires_grad_(True)
+            loss = crit(xr, yr)
+            loss.backward()
+            out[name] = (loss.item(), xr.grad, yr.grad)
+    lt, lf = out["tc"][0], out["ffma2"][0]
+    gerr = max(((out["tc"][i] - out["ffma2"][i]).abs().max() / out["ffma2"][i].abs().max()).item() for i in (1, 2))
+    print(f"loss tc {lt:.9f} ffma2 {lf:.9f} rel {abs(lt - lf) / abs(lf):.2e}; gradient max-norm rel {gerr:.2e}")
+    assert abs(lt - lf) <= 2e-6 * abs(lf)
+    assert gerr <= GRAD_RTOL

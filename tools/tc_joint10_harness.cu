@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   const long long sc = (long long)H * W, sn = sc * K;
   ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int m : {0, 1, 2}) {
+  for (int m : {10, 1, 0}) {
     Params P;
     P.x = dx_; P.x_sn = sn; P.x_sc = sc; P.x_sh = W;
     P.y = dy_; P.y_sn = sn; P.y_sc = sc; P.y_sh = W;
@@ -52,12 +52,13 @@ int main(int argc, char** argv) {
     cudaDeviceSynchronize();
     float ms; cudaEventElapsedTime(&ms, e0, e1);
     {
-      static long long tr[4][64];
+      static long long tr[8][64];
       cudaMemcpyFromSymbol(tr, g_tcj_trace, sizeof(tr));
       const long long t0 = tr[0][0];
       printf("  CTA 0: init done %lld, all MMAs done %lld, slot written %lld clk\n", tr[0][1] - t0, tr[0][2] - t0, tr[0][3] - t0);
-      printf("  pair: x-job-top y-job-top issuer-ready\n");
-      for (int i = 0; i < 16; ++i) printf("  %2d: x-top %7lld | y: top %7lld loads-issued %7lld done-wait %7lld published %7lld | issuer %7lld\n", i, tr[2][i] - t0, tr[3][4 * i] - t0, tr[3][4 * i + 1] - t0, tr[3][4 * i + 2] - t0, tr[3][4 * i + 3] - t0, tr[1][i] - t0);
+      printf("  pair: w16 issue-start waits-done issued | w16 drain-start done-seen | w17 drain-start done-seen\n");
+      for (int i = 0; i < 14; ++i) printf("  %2d: %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, tr[2][i] - t0, tr[1][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[5][i] - t0, tr[6][i] - t0, tr[7][i] - t0);
+      if (0) for (int i = 0; i < 16; ++i) printf("  %2d: x-top %7lld | y: top %7lld loads-issued %7lld done-wait %7lld published %7lld | issuer %7lld\n", i, tr[2][i] - t0, tr[3][4 * i] - t0, tr[3][4 * i + 1] - t0, tr[3][4 * i + 2] - t0, tr[3][4 * i + 3] - t0, tr[1][i] - t0);
     }
     printf("mode %d (%s%s%s%s): %.1f us\n", m, m & 1 ? "no-mma " : "", m & 2 ? "no-transform " : "", m & 4 ? "no-l2-prefetch " : "", m & 8 ? "no-loads" : "", ms / reps * 1e3);
   }
