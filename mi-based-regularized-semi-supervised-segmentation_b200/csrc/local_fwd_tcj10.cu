@@ -56,6 +56,7 @@ struct Params {
 #ifdef IIC_TCJ_DEBUG
 #define TCJ_DBG(bit) (P.dbg & (bit))
 __device__ long long g_tcj_trace[8][64];
+__device__ unsigned long long g_tcj_cta[160][2];
 #define TCJ_T(role, idx) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_tcj_trace[role][idx] = clock64(); } while (0)
 #else
 #define TCJ_T(role, idx) do { } while (0)
@@ -180,6 +181,14 @@ __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long 
   bool bad = false;
   Tile ta, tb;
   load_tile<IS_Y, FULLK>(ta, P, c, 0, pp, rr);
+  int pending = -1;       // slot written but not yet published
+  auto publish = [&]() {
+    if (pending < 0) return;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&full[pending]);
+    pending = -1;
+  };
   // one step: issue the loads of the job after this one into `nxt`, then convert and publish `cur`; false after the last job
   auto step = [&](Tile& cur, Tile& nxt) -> bool {
     long long rn = r;
@@ -188,6 +197,7 @@ __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long 
     if (pn >= (IS_Y ? c.npy : c.npy + 1)) { rn = r + c.nr; pn = 0; if (rn < R1) cn = chunk_at(rn, R1, P.H); }
     const bool more = rn < R1;
     if (more) load_tile<IS_Y, FULLK>(nxt, P, cn, pn, pp, rr);
+    publish();            // the previous pair: its stores have had the load issue above to drain before the fence waits for them
     if (count >= NRING) mbar_wait(&released[count % NRING], (unsigned)(count / NRING - 1) & 1u, IS_Y ? 3 : 2);
     const int slot = count % NRING;
     if (!TCJ_DBG(2)) {
@@ -201,9 +211,7 @@ __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long 
       if (pp < npp)
         store_tile<FULLK>(cur, ring + slot * PAIRB, (!IS_Y && slot == 0) ? mirror : nullptr, IS_Y ? 2 : 1, pp, rr, flip, P.K);
     }
-    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&full[slot]);
+    pending = slot;
     ++count;
     r = rn; c = cn; pl = pn;
     return more;
@@ -212,6 +220,7 @@ __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long 
     if (!step(ta, tb)) break;
     if (!step(tb, ta)) break;
   }
+  publish();
   if (!IS_Y && P.flags && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(P.flags, IIC_FLAG_NOT_SIMPLEX);
 }
 
@@ -228,6 +237,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
   const long long R1 = (long long)(blockIdx.x + 1) * rows_total / gridDim.x;
   const int ksteps = (P.W + 2 + 15) / 16;
   if (wid == 0) TCJ_T(0, 0);
+#ifdef IIC_TCJ_DEBUG
+  if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][0] = t; }
+#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NXP; ++s) { mbar_init(&x_full[s], 7); mbar_init(&x_free[s], 2); }
@@ -380,6 +392,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
+#ifdef IIC_TCJ_DEBUG
+  if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][1] = t; }
+#endif
   if (wid == 14) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 

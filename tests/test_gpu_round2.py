@@ -248,7 +248,7 @@ def _joint64(x, y, pad):
 @pytest.mark.parametrize("B,K,H,W,sharp,strided", [
     (32, 10, 224, 224, 1.0, False),   # BASELINE config 2
     (32, 10, 224, 224, 8.0, False),   # peaked maps: most products are tiny, a few are near 1
-    (9, 10, 135, 236, 2.0, False),    # odd chunk lengths (row pairs cut by the image end), the widest map the kernel takes
+    (9, 10, 135, 224, 2.0, False),    # odd chunk lengths (row pairs cut by the image end), the widest map the kernel takes
     (20, 7, 64, 40, 1.0, False),      # fewer than 10 clusters, narrow map
     (11, 9, 112, 96, 1.0, True),      # channel block of a wider head output (sample and channel strides not dense)
 ])

@@ -37,7 +37,7 @@ int main(int argc, char** argv) {
   const long long sc = (long long)H * W, sn = sc * K;
   ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES);
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
-  for (int m : {10, 1, 0}) {
+  for (int m : {0}) {
     Params P;
     P.x = dx_; P.x_sn = sn; P.x_sc = sc; P.x_sh = W;
     P.y = dy_; P.y_sn = sn; P.y_sc = sc; P.y_sh = W;
@@ -57,8 +57,17 @@ int main(int argc, char** argv) {
       const long long t0 = tr[0][0];
       printf("  CTA 0: init done %lld, all MMAs done %lld, slot written %lld clk\n", tr[0][1] - t0, tr[0][2] - t0, tr[0][3] - t0);
       printf("  pair: w16 issue-start waits-done issued | w16 drain-start done-seen | w17 drain-start done-seen\n");
-      for (int i = 0; i < 14; ++i) printf("  %2d: %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, tr[2][i] - t0, tr[1][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[5][i] - t0, tr[6][i] - t0, tr[7][i] - t0);
+      if (0) for (int i = 0; i < 14; ++i) printf("  %2d: %7lld %7lld %7lld | %7lld %7lld | %7lld %7lld\n", i, tr[2][i] - t0, tr[1][i] - t0, tr[3][i] - t0, tr[4][i] - t0, tr[5][i] - t0, tr[6][i] - t0, tr[7][i] - t0);
       if (0) for (int i = 0; i < 16; ++i) printf("  %2d: x-top %7lld | y: top %7lld loads-issued %7lld done-wait %7lld published %7lld | issuer %7lld\n", i, tr[2][i] - t0, tr[3][4 * i] - t0, tr[3][4 * i + 1] - t0, tr[3][4 * i + 2] - t0, tr[3][4 * i + 3] - t0, tr[1][i] - t0);
+    }
+    {
+      static unsigned long long ct[160][2];
+      cudaMemcpyFromSymbol(ct, g_tcj_cta, sizeof(ct));
+      unsigned long long t0 = ~0ull, t1 = 0;
+      for (int i = 0; i < 148; ++i) { if (ct[i][0] < t0) t0 = ct[i][0]; if (ct[i][1] > t1) t1 = ct[i][1]; }
+      printf("  last launch: first CTA start to last CTA end %.1f us; per CTA (start offset, duration) us:\n   ", (t1 - t0) * 1e-3);
+      for (int i = 0; i < 148; ++i) { printf(" %d:(%.1f,%.1f)", i, (ct[i][0] - t0) * 1e-3, (ct[i][1] - ct[i][0]) * 1e-3); if (i % 8 == 7) printf("\n   "); }
+      printf("\n");
     }
     printf("mode %d (%s%s%s%s): %.1f us\n", m, m & 1 ? "no-mma " : "", m & 2 ? "no-transform " : "", m & 4 ? "no-l2-prefetch " : "", m & 8 ? "no-loads" : "", ms / reps * 1e3);
   }
