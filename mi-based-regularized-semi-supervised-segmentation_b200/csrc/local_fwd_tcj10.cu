@@ -57,7 +57,6 @@ struct Params {
 #define TCJ_DBG(bit) (P.dbg & (bit))
 __device__ long long g_tcj_trace[8][64];
 __device__ unsigned long long g_tcj_cta[160][2];      // per CTA: %globaltimer at start and end
-__device__ unsigned long long g_tcj_cta[160][2];
 #define TCJ_T(role, idx) do { if (blockIdx.x == 0 && lane == 0 && (idx) < 64) g_tcj_trace[role][idx] = clock64(); } while (0)
 #else
 #define TCJ_T(role, idx) do { } while (0)
@@ -241,9 +240,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
 #ifdef IIC_TCJ_DEBUG
   if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][0] = t; }
 #endif
-#ifdef IIC_TCJ_DEBUG
-  if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][0] = t; }
-#endif
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < NXP; ++s) { mbar_init(&x_full[s], 7); mbar_init(&x_free[s], 2); }
@@ -396,9 +392,6 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
   }
   asm volatile("tcgen05.fence::before_thread_sync;");
   __syncthreads();
-#ifdef IIC_TCJ_DEBUG
-  if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][1] = t; }
-#endif
 #ifdef IIC_TCJ_DEBUG
   if (threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); g_tcj_cta[blockIdx.x][1] = t; }
 #endif
