@@ -132,8 +132,9 @@ __global__ void __launch_bounds__(1024) global_epilogue_kernel(const double* __r
   global_epilogue_block(J, K, lamb, symmetric, losses_out, P_out, flags, sm);
 }
 
-// Every CTA rebuilds GJ = d(objective)/dJ in shared memory (K*K doubles -> floats), then produces a
-// slab of rows of gx = y GJ^T and gy = x GJ.
+// Every CTA rebuilds GJ = d(objective)/dJ in shared memory, then produces a slab of rows of gx = y GJ^T and gy = x GJ.
+// The joint is read from global memory ONCE (symmetrised into shared memory); the kernel is a chain of small dependent
+// phases, so every phase that went back to global memory for J cost a memory latency (19k cycles at (32, 10) before).
 __global__ void __launch_bounds__(256) global_backward_kernel(
     const float* __restrict__ x, long long x_sn, const float* __restrict__ y, long long y_sn, long long N,
     int K, const double* __restrict__ J, double lamb, int symmetric, const float* __restrict__ g_loss,
@@ -146,22 +147,29 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   double* pj = pi + K;             // K
   double* gi = pj + K;             // K : log(pi+eps) + pi/(pi+eps)
   double* gj = gi + K;             // K
-  float* GJ = reinterpret_cast<float*>(gj + K);   // K*K floats : dObj/dJ[i][j]
+  double* Js = gj + K;             // K*K : the (symmetrised) joint; overwritten in place by GP
+  float* GJ = reinterpret_cast<float*>(Js + (size_t)K * K);    // K*K floats : dObj/dJ[i][j]
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t KK = (size_t)K * K;
   const double eps = 1e-10;
+  // the rows of this CTA's slab are independent of everything below: get them moving first
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > N) r1 = N;
   const double g1 = g_loss ? (double)g_loss[0] : 0.0, g2 = g_no_lamb ? (double)g_no_lamb[0] : 0.0;
-  auto Jsym = [&](int i, int j) {
-    return symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
-  };
   double part = 0.0;
-  for (size_t e = tid; e < KK; e += nt) part += Jsym((int)(e / K), (int)(e % K));
-  const double S = block_sum(part, scratch);
+  for (size_t e = tid; e < KK; e += nt) {
+    const int i = (int)(e / K), j = (int)(e % K);
+    const double v = symmetric ? (J[(size_t)i * K + j] + J[(size_t)j * K + i]) / 2.0 : J[(size_t)i * K + j];
+    Js[e] = v;
+    part += v;
+  }
+  const double S = block_sum(part, scratch);        // (block_sum synchronises: Js is complete)
   for (int k = tid; k < K; k += nt) {
     double r = 0.0, c = 0.0;
     for (int q = 0; q < K; ++q) {
-      r += Jsym(k, q);
-      c += Jsym(q, k);
+      r += Js[(size_t)k * K + q];
+      c += Js[(size_t)q * K + k];
     }
     pi[k] = r / S;
     pj[k] = c / S;
@@ -170,32 +178,27 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   }
   __syncthreads();
   // GP = g1*GP(lamb) + g2*GP(1) + gP ;  tot = sum GP * P
-  auto GP = [&](int i, int j) {
-    const double p = Jsym(i, j) / S;
-    const double base = -log(p + eps) - p / (p + eps);
-    const double mterm = gj[j] + gi[i];
-    double v = g1 * (base + lamb * mterm) + g2 * (base + mterm);
-    if (gP) v += (double)gP[(size_t)i * K + j];
-    return v;
-  };
   double t_part = 0.0;
   for (size_t e = tid; e < KK; e += nt) {
     const int i = (int)(e / K), j = (int)(e % K);
-    t_part += GP(i, j) * (Jsym(i, j) / S);
+    const double p = Js[e] / S;
+    const double base = -log(p + eps) - p / (p + eps);
+    const double mterm = gj[j] + gi[i];
+    double v = g1 * (base + lamb * mterm) + g2 * (base + mterm);
+    if (gP) v += (double)gP[e];
+    Js[e] = v;                                       // each thread overwrites only the entries it has just read
+    t_part += v * p;
   }
-  const double tot = block_sum(t_part, scratch);
+  const double tot = block_sum(t_part, scratch);    // (GP complete)
   for (size_t e = tid; e < KK; e += nt) {
     const int i = (int)(e / K), j = (int)(e % K);
     double v;
-    if (symmetric) v = ((GP(i, j) - tot) / S + (GP(j, i) - tot) / S) / 2.0;   // adjoint of (J + J^T)/2
-    else v = (GP(i, j) - tot) / S;
+    if (symmetric) v = ((Js[e] - tot) / S + (Js[(size_t)j * K + i] - tot) / S) / 2.0;   // adjoint of (J + J^T)/2
+    else v = (Js[e] - tot) / S;
     GJ[e] = (float)v;
   }
   __syncthreads();
   // gx[n][i] = sum_j GJ[i][j] y[n][j] ; gy[n][j] = sum_i GJ[i][j] x[n][i]
-  const long long r0 = (long long)blockIdx.x * rows_per_cta;
-  long long r1 = r0 + rows_per_cta;
-  if (r1 > N) r1 = N;
   const long long total = (r1 - r0) * K;
   for (long long e = tid; e < total; e += nt) {
     const long long n = r0 + e / K;
@@ -315,11 +318,10 @@ extern "C" int iic_global_backward(const float* x, long long x_sn, const float* 
   IIC_REQUIRE(N > 0 && K > 0 && K <= 128, "iic_global_backward: bad sizes N=%lld K=%d", N, K);
   long long rpc;
   const int ctas = global_grid(current_device(), N, &rpc);
-  const size_t smem = (40 + 4 * (size_t)K) * sizeof(double) + (size_t)K * K * sizeof(float);
+  const size_t smem = (40 + 4 * (size_t)K + (size_t)K * K) * sizeof(double) + (size_t)K * K * sizeof(float);
   auto kern = global_backward_kernel;
-  if (smem > 48 * 1024) {
-    IIC_CHECK_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  }
+  // opted in once per device, for the largest K the entry point takes (128)
+  if (smem > 48 * 1024) IIC_CHECK_RC(ensure_dyn_smem((const void*)kern, (int)((40 + 4 * 128 + 128 * 128) * sizeof(double) + 128 * 128 * sizeof(float))));
   if (gx_sn <= 0) gx_sn = K;            // 0 = dense rows
   if (gy_sn <= 0) gy_sn = K;
   kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy, gx_sn, gy_sn, rpc);

@@ -87,6 +87,21 @@ def _state(device: torch.device) -> _StreamState:
     return st
 
 
+_side_streams = {}
+overlap_global_backward = False    # run the small global-term gradient kernels beside the local ones (see IICTermsFunction.backward)
+
+
+def _side_stream(device: torch.device) -> "torch.cuda.Stream":
+    """A second stream paired with the current stream of `device` (created once, outside any graph capture if the first
+    backward runs eagerly, as every warm-up does)."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    st = _side_streams.get(key)
+    if st is None:
+        st = torch.cuda.Stream(device=device)
+        _side_streams[key] = st
+    return st
+
+
 def flags_tensor(device) -> torch.Tensor:
     """The sticky int32 flag word (IIC_FLAG_*) of the current stream of `device`."""
     return _state(torch.device(device)).flags
@@ -937,17 +952,33 @@ class IICTermsFunction(torch.autograd.Function):
             written.add((si, blk))
             return dst, None
 
-        gi, si_ = 0, 0
-        for ti, (cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask, npatch) in enumerate(ctx.meta):
+        # The global terms' gradient kernels are one small CTA each (~8 us of latency-bound work at (32, 10)); the local ones
+        # fill the GPU for ~100 us.  With both kinds present the global ones go to a side stream, forked here and joined
+        # before anything reads their output: inside a captured CUDA graph that makes them parallel branches.
+        n_local = sum(1 for m in ctx.meta if m[0] is LocalTerm)
+        use_side = overlap_global_backward and n_local > 0 and n_local < len(ctx.meta)
+        side, main, deferred = None, None, []
+        # saved-tensor and gradient offsets of every term, then the launch order: with a side stream the global terms go
+        # first, so that the fork point lies before the first local kernel on the main stream
+        offs, gi, si_ = [], 0, 0
+        for m in ctx.meta:
+            offs.append((si_, gi))
+            if m[0] is LocalTerm:
+                si_ += 4 + (1 if m[8] else 0)
+                gi += 1
+            else:
+                si_ += 3
+                gi += 3
+        order = list(range(len(ctx.meta)))
+        if use_side:
+            order.sort(key=lambda t_: ctx.meta[t_][0] is LocalTerm)
+        for ti in order:
+            cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask, npatch = ctx.meta[ti]
+            si_, gi = offs[ti]
             if cls is LocalTerm:
                 x, y, Wx, Wy = sv[si_:si_ + 4]
-                si_ += 4
-                mask = None
-                if has_mask:
-                    mask = sv[si_]
-                    si_ += 1
+                mask = sv[si_ + 4] if has_mask else None
                 g = grads[gi]
-                gi += 1
                 if g is None:
                     continue
                 (gx, ax), (gy, ay) = target(2 * ti, x), target(2 * ti + 1, y)
@@ -957,17 +988,31 @@ class IICTermsFunction(torch.autograd.Function):
                     _local_backward_into(x, y, mask, Wx, Wy, g.contiguous(), pad, patch[0], patch[1], step[0], step[1], gx, gy)
             else:
                 x, y, J = sv[si_:si_ + 3]
-                si_ += 3
                 g1, g2, gP = grads[gi:gi + 3]
-                gi += 3
                 if g1 is None and g2 is None and gP is None:
                     continue
                 (gx, ax), (gy, ay) = target(2 * ti, x), target(2 * ti + 1, y)
+                if use_side:
+                    if side is None:
+                        main = torch.cuda.current_stream(x.device)
+                        side = _side_stream(x.device)
+                    side.wait_stream(main)        # the upstream gradients and any zero fill of the targets are queued on main
+                    with torch.cuda.stream(side):
+                        _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
+                    if ax is not None:
+                        deferred.append((ax, gx))
+                    if ay is not None:
+                        deferred.append((ay, gy))
+                    continue
                 _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
             if ax is not None:
                 ax += gx
             if ay is not None:
                 ay += gy
+        if side is not None:
+            main.wait_stream(side)                # join: every later reader (and the allocator) sees the side work done
+            for acc, g_ in deferred:
+                acc += g_
         return (None, None, None, *[G[i] if any_grad[i] else None for i in range(n_src)])
 
 
