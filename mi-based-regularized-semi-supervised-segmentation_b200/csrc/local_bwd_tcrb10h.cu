@@ -42,8 +42,8 @@ constexpr int NRAW = 6;
 constexpr int WROWS = T * KP;            // 48 rows per weight chunk
 constexpr int W_TILE = 2 * WROWS * 16;   // 1536: one MMA's B operand (two chunks)
 constexpr int W_IMG = 6 * W_TILE;        // (tx 0, 1, 2) x (MMA 1, MMA 2)
-constexpr int NTHREADS = 576;             // warps: 0 TMA, 3 TMEM (+ logit rows), 1 2 12 13 MMA issuers, 4-11 transform, 14-17 epilogue
-constexpr int NTHREADS_FL = 704;          // from-logits form: a second epilogue set (warps 18-21) takes pixel tile 1
+constexpr int NTHREADS = 704;             // warps: 0 TMA, 3 TMEM (+ logit rows), 1 2 12 13 MMA issuers, 4-11 transform, 14-17 and 18-21 epilogue
+constexpr int NTHREADS_FL = 704;          // (one epilogue set per pixel tile: the drain's global stores bound the kernel, see the epilogue)
 constexpr int SMEM_BYTES = NA * A_SLOT + 2 * W_IMG + NRAW * RAW_SLOT + 1024;   // both sweeps' weight images stay resident
 constexpr int NL = 4;                    // from-logits form: ring of output-tensor logit rows for the drain (two row pairs)
 constexpr int SMEM_BYTES_FL = SMEM_BYTES + NL * RAW_SLOT;
@@ -116,15 +116,23 @@ __device__ __forceinline__ void build_weight_row(const float* __restrict__ Wc, u
   t[3 * WROWS + row] = pack_h8(c3);
 }
 
-// the chunk of image rows that starts at global row r (rows of all images, B*H) inside the CTA share [r, R1)
-struct Chunk { int n, h0, nr; };
-__device__ __forceinline__ Chunk next_chunk(long long r, long long R1, int H, int rc) {
+// The chunk of image rows that starts at global row r (rows of all images, B*H) inside the CTA share [R0, R1).  Output
+// rows h0 .. h0+nr-1 take source rows h0-1 .. h0+nr (local q = 0 .. nr+1).  Consecutive chunks of one image share two source
+// rows (q = nr, nr+1 of one are q = 0, 1 of the next): those are staged ONCE -- the issuers add them into the next chunk's
+// accumulator buffer while they finish this one (`cont_next`), and the next chunk starts at q = 2 (`q0`, `cont_prev`).
+// With 7-row chunks the re-staged halo rows were 22 % of all stages.  A chunk never leaves a single row behind in its
+// run (a source row may belong to two chunks, not three).
+struct Chunk { int n, h0, nr, q0; bool cont_next; };
+__device__ __forceinline__ Chunk next_chunk(long long r, long long R0, long long R1, int H, int rc) {
   Chunk c;
   c.n = (int)(r / H);
   c.h0 = (int)(r - (long long)c.n * H);
-  c.nr = rc;
-  if (c.nr > H - c.h0) c.nr = H - c.h0;
-  if (c.nr > R1 - r) c.nr = (int)(R1 - r);
+  int run = H - c.h0;
+  if (run > R1 - r) run = (int)(R1 - r);
+  c.nr = rc < run ? rc : run;
+  if (run - c.nr == 1 && c.nr >= 3) c.nr -= 1;
+  c.q0 = (r > R0 && c.h0 > 0) ? 2 : 0;
+  c.cont_next = c.nr < run;
   return c;
 }
 
@@ -157,7 +165,7 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     for (int s = 0; s < NRAW; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], 4); }
     for (int s = 0; s < NA; ++s) { mbar_init(&a_full[s], 4); mbar_init(&a_empty[s], 2); }
     mbar_init(&w_full, 4);
-    const int ndset_i = (FROM_LOGITS && ntile == 2) ? 2 : 1;          // epilogue warp sets (one per pixel tile when from logits)
+    const int ndset_i = ntile == 2 ? 2 : 1;                           // epilogue warp sets (one per pixel tile)
     for (int s = 0; s < 2; ++s) { mbar_init(&accum_full[s], 4); mbar_init(&tmem_ready[s], 4 * ndset_i); }
     for (int s = 0; s < NL; ++s) { mbar_init(&l_full[s], 1); mbar_init(&l_empty[s], 4 * ndset_i); }
     mbar_fence_init();
@@ -180,8 +188,8 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
       unsigned sph = 0;
       for (int sweep = 0; sweep < 2; ++sweep)
       for (long long r = R0; r < R1;) {
-        const Chunk c = next_chunk(r, R1, P.H, rc);
-        for (int q = 0; q < c.nr + T - 1; ++q, ++t) {
+        const Chunk c = next_chunk(r, R0, R1, P.H, rc);
+        for (int q = c.q0; q < c.nr + T - 1; ++q, ++t) {
           { const int tt = t; (void)tt; TRACE(0, 0); }
           if (t >= NRAW) mbar_wait(&raw_empty[s], sph ^ 1u, 1);
           { const int tt = t; (void)tt; TRACE(0, 1); }
@@ -202,7 +210,7 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
       unsigned sph = 0;
       for (int sweep = 0; sweep < 2; ++sweep)
       for (long long r = R0; r < R1;) {
-        const Chunk c = next_chunk(r, R1, P.H, rc);
+        const Chunk c = next_chunk(r, R0, R1, P.H, rc);
         for (int orow = 0; orow < c.nr; ++orow, ++t) {
           if (t >= NL) mbar_wait(&l_empty[s], sph ^ 1u, 9);
           mbar_arrive_expect_tx(&l_full[s], raw_bytes);
@@ -228,14 +236,16 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1; ++i) {
       const uint64_t w_base = w_base0 + (uint64_t)(sweep * (W_IMG / 16));
-      const Chunk c = next_chunk(r, R1, P.H, rc);
+      const Chunk c = next_chunk(r, R0, R1, P.H, rc);
       const int buf = i & 1;
       if (lane == 0 && wid == 1) CTRACE(0);
       mbar_wait(&tmem_ready[buf], (unsigned)(i >> 1) & 1u, 6);   // this buffer's accumulators are zeroed
       if (lane == 0 && wid == 1) CTRACE(1);
       asm volatile("tcgen05.fence::after_thread_sync;");
       const int nq = c.nr + T - 1;
-      for (int q = 0; q < nq; ++q, ++tt) {
+      // the chunk after this one, when it shares this chunk's last two source rows
+      const int nr_next = c.cont_next ? next_chunk(r + c.nr, R0, R1, P.H, rc).nr : 0;
+      for (int q = c.q0; q < nq; ++q, ++tt) {
         // Split by the GLOBAL stage parity, like the transform groups, and with even ring depths: a ring slot then always
         // belongs to the same transform group and the same issuer pair, who wait on every phase of its barriers.  (Split
         // by the row index inside the chunk, a slot changes hands after a chunk with an odd number of rows, and an issuer
@@ -267,13 +277,41 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
               umma_bf16(d_tmem, a_34 + (uint64_t)tx, bt + (uint64_t)(W_TILE / 16), idesc_f16);
             }
           }
+        }
+        if (c.cont_next && q >= c.nr) {
+          // this source row is also row q2 = q - nr (0 or 1) of the NEXT chunk: add it into the other accumulator buffer,
+          // once the drain of the chunk before this one has zeroed it
+          mbar_wait(&tmem_ready[buf ^ 1], (unsigned)((i + 1) >> 1) & 1u, 6);
+          asm volatile("tcgen05.fence::after_thread_sync;");
+          if (lane == 0 && mine) {
+            const int q2 = q - c.nr;
+            const int ty_max = q2;                                     // q2 < T - 1
+            const int ty_min = q2 - nr_next + 1 > 0 ? q2 - nr_next + 1 : 0;
+            const uint32_t nn = (uint32_t)((ty_max - ty_min + 1) * KP);
+            const uint32_t idesc_f16 = (1u << 4) | ((nn >> 3) << 17) | (8u << 24);
+            const uint32_t d_tmem = tmem_base + (uint32_t)((buf ^ 1) * TBUF + (mt * RMAX + (q2 - ty_max)) * KP);
+            const uint64_t a_12 = make_desc_kmajor_noswz(smem_u32(a_ring + a * A_SLOT), A_CHUNK) + (uint64_t)(mt * 128 + 8 - PAD);
+            const uint64_t a_34 = a_12 + (uint64_t)(2 * A_CHUNK / 16);
+            const uint64_t b_base = w_base + (uint64_t)((T - 1 - ty_max) * KP);
+#pragma unroll
+            for (int tx = 0; tx < T; ++tx) {
+              const uint64_t bt = b_base + (uint64_t)tx * (2 * W_TILE / 16);
+              umma_bf16(d_tmem, a_12 + (uint64_t)tx, bt, idesc_f16);
+              umma_bf16(d_tmem, a_34 + (uint64_t)tx, bt + (uint64_t)(W_TILE / 16), idesc_f16);
+            }
+          }
+        }
+        if (lane == 0) {
           if (par == 0) TRACE(1 + mt, 2);
           umma_commit(&a_empty[a]);
-          if (q >= nq - 2) umma_commit(&accum_full[buf]);     // this issuer's last source row of the item
         }
         __syncwarp();
         if (++a == NA) { a = 0; aph ^= 1u; }
       }
+      // one arrival per issuing warp and item, after its last MMA into this buffer (a warp may have had no source row in the
+      // item's tail, or none at all in a two-row item that starts at q = 2)
+      if (lane == 0) umma_commit(&accum_full[buf]);
+      __syncwarp();
       r += c.nr;
     }
   } else if (wid >= 4 && wid < 12) {
@@ -285,8 +323,8 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     unsigned aph = 0, sph = 0;
     for (int sweep = 0; sweep < 2; ++sweep)
     for (long long r = R0; r < R1;) {
-      const Chunk c = next_chunk(r, R1, P.H, rc);
-      for (int q = 0; q < c.nr + T - 1; ++q, ++t) {
+      const Chunk c = next_chunk(r, R0, R1, P.H, rc);
+      for (int q = c.q0; q < c.nr + T - 1; ++q, ++t) {
         if ((t & 1) != grp) {                            // the other group's source row
           if (++a == NA) { a = 0; aph ^= 1u; }
           if (++s == NRAW) { s = 0; sph ^= 1u; }
@@ -341,16 +379,23 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
             }
           }
         }
+        // split of both pixels at once with packed fp32 ops: hi = the scaled value cut to 11 significant bits (a mask; exact
+        // in fp16), lo = value - hi (exact in fp32, rounded to fp16 by the pack below)
+        float2 hi[10], lo[10];
+#pragma unroll
+        for (int ch = 0; ch < 10; ++ch) {
+          const float2 sv = __fmul2_rn(make_float2(v[0][ch], v[1][ch]), make_float2(A_SCALE, A_SCALE));
+          hi[ch] = make_float2(__uint_as_float(__float_as_uint(sv.x) & 0xFFFFE000u), __uint_as_float(__float_as_uint(sv.y) & 0xFFFFE000u));
+          lo[ch] = __ffma2_rn(hi[ch], make_float2(-1.f, -1.f), sv);
+        }
 #pragma unroll
         for (int u = 0; u < 2; ++u) {
           const int px = tid + u * 128;
           uint32_t hp[5], lp[5];
 #pragma unroll
           for (int c2 = 0; c2 < 5; ++c2) {
-            const float s0 = v[u][2 * c2] * A_SCALE, s1 = v[u][2 * c2 + 1] * A_SCALE;
-            const __half2 hh = __floats2half2_rn(s0, s1);
-            const float2 hf = __half22float2(hh);
-            const __half2 ll = __floats2half2_rn(s0 - hf.x, s1 - hf.y);
+            const __half2 hh = u == 0 ? __floats2half2_rn(hi[2 * c2].x, hi[2 * c2 + 1].x) : __floats2half2_rn(hi[2 * c2].y, hi[2 * c2 + 1].y);
+            const __half2 ll = u == 0 ? __floats2half2_rn(lo[2 * c2].x, lo[2 * c2 + 1].x) : __floats2half2_rn(lo[2 * c2].y, lo[2 * c2 + 1].y);
             hp[c2] = *reinterpret_cast<const uint32_t*>(&hh);
             lp[c2] = *reinterpret_cast<const uint32_t*>(&ll);
           }
@@ -380,7 +425,7 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     // from logits the drain does twice the work per pixel (softmax of the output pixel + adjoint), so a second set of
     // four warps (18-21) takes pixel tile 1; each set drains and zeroes only its tile's accumulator columns
     const int dset = wid >= 18 ? 1 : 0;
-    const int ndset = (FROM_LOGITS && ntile == 2) ? 2 : 1;
+    const int ndset = ntile == 2 ? 2 : 1;
     const int mt0 = ndset == 2 ? dset : 0, mt1 = ndset == 2 ? dset + 1 : ntile;
     const int zc0 = ndset == 2 ? dset * RMAX * KP : 0, zc1 = ndset == 2 ? (dset + 1) * RMAX * KP : TBUF;
     float unscale = 1.f;
@@ -434,7 +479,7 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
     unsigned lph = 0;
     for (int sweep = 0; sweep < 2 && dset < ndset; ++sweep)
     for (long long r = R0; r < R1; ++i) {
-      const Chunk c = next_chunk(r, R1, P.H, rc);
+      const Chunk c = next_chunk(r, R0, R1, P.H, rc);
       const int buf = i & 1;
       if (lane == 0 && wid == 14) CTRACE(2);
       mbar_wait(&accum_full[buf], (unsigned)(i >> 1) & 1u, 8);

@@ -71,8 +71,8 @@ int main(int argc, char** argv) {
     long long ct[32][8];
     cudaMemcpyFromSymbol(ct, iic::bwdrb10h::g_ctrace, sizeof(ct));
     printf("chunk | issuer: tmem_ready wait enter, ok | drain: accum_full wait enter, ok, drained, zeroed   (clk, relative to the first trace stamp)\n");
-    for (int k = 0; k < 30; ++k)
-      printf("%3d | %8lld %8lld | %8lld %8lld %8lld %8lld\n", k, ct[k][0] - t0, ct[k][1] - t0, ct[k][2] - t0, ct[k][3] - t0, ct[k][4] - t0, ct[k][5] - t0);
+    for (int k = 0; k < 12; ++k)
+      printf("%3d | %8lld %8lld | %8lld %8lld %8lld %8lld | in stores %lld clk, in TMEM waits %lld clk\n", k, ct[k][0] - t0, ct[k][1] - t0, ct[k][2] - t0, ct[k][3] - t0, ct[k][4] - t0, ct[k][5] - t0, ct[k][6], ct[k][7]);
   }
 #endif
   std::vector<float> gx(n), gy(n);
