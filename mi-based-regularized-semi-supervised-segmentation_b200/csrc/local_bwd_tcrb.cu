@@ -294,9 +294,18 @@ local_bwd_tcrb_kernel(const __grid_constant__ CUtensorMap maps, const Params P) 
             for (int h = 0; h < 2; ++h) {
               if (orow + h < rv) {
                 float* dst = P.out + (size_t)n * P.out_sn + (size_t)(r0 + orow + h) * P.W + c;
+                // straight-line stores for the channels every covered head has (K >= 16; a branch per channel costs ~10
+                // instructions and a uniform-register reload per store), the yaml default K = 20 entirely
 #pragma unroll
-                for (int o = 0; o < 24; ++o)
-                  if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                for (int o = 0; o < 16; ++o) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                if (P.K == 20) {
+#pragma unroll
+                  for (int o = 16; o < 20; ++o) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                } else {
+#pragma unroll
+                  for (int o = 16; o < 24; ++o)
+                    if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                }
               }
             }
           }

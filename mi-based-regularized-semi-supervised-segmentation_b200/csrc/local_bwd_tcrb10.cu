@@ -326,8 +326,8 @@ local_bwd_tcrb10_kernel(const __grid_constant__ CUtensorMap map0, const __grid_c
               if (orow + h < c.nr) {
                 float* dst = P.out[sweep] + (size_t)c.n * P.out_sn[sweep] + (size_t)(c.h0 + orow + h) * P.W + col;
 #pragma unroll
-                for (int o = 0; o < 10; ++o)
-                  if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                for (int o = 0; o < 9; ++o) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);     // K is 9 or 10 here
+                if (P.K == 10) dst[(size_t)9 * plane] = g * __uint_as_float(v[h][9]);
               }
             }
           }

@@ -515,9 +515,15 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
               if (h < nrow) {
                 float* dst = P.out[sweep] + (size_t)c.n * P.out_sn[sweep] + (size_t)(c.h0 + orow + h) * P.W + col;
                 if (!FROM_LOGITS) {
+                  // (a branch per channel cost ~10 instructions and a uniform-register reload per store: the drain ran at
+                  // one store per ~68 clk and warp; K = 10 takes the straight-line form)
+                  if (P.K == 10) {
 #pragma unroll
-                  for (int o = 0; o < 10; ++o)
-                    if (o < P.K) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                    for (int o = 0; o < 10; ++o) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                  } else {
+#pragma unroll
+                    for (int o = 0; o < 9; ++o) dst[(size_t)o * plane] = g * __uint_as_float(v[h][o]);
+                  }
                 } else {
                   // softmax adjoint: d logit_o = inv_temp * p_o * (g_o - sum_k g_k p_k), p = softmax of the output
                   // tensor's own logits at this pixel (staged row: column c at index c + 4, conflict-free across lanes)
@@ -542,9 +548,13 @@ local_bwd_tcrb10h_kernel(const __grid_constant__ CUtensorMap map0, const __grid_
                     pr[o] *= inv;
                     dot = fmaf(g * __uint_as_float(v[h][o]), pr[o], dot);
                   }
+                  if (P.K == 10) {
 #pragma unroll
-                  for (int o = 0; o < 10; ++o)
-                    if (o < P.K) dst[(size_t)o * plane] = P.inv_temp * pr[o] * (g * __uint_as_float(v[h][o]) - dot);
+                    for (int o = 0; o < 10; ++o) dst[(size_t)o * plane] = P.inv_temp * pr[o] * (g * __uint_as_float(v[h][o]) - dot);
+                  } else {
+#pragma unroll
+                    for (int o = 0; o < 9; ++o) dst[(size_t)o * plane] = P.inv_temp * pr[o] * (g * __uint_as_float(v[h][o]) - dot);
+                  }
                 }
               }
             }
