@@ -120,8 +120,8 @@ def peaks():
 
 
 # dram bytes per launch of the dominant kernel from one `ncu --set full` capture; None until measured for the current kernel
-TRAFFIC_BWD = (218.0e6, "ncu --set full, profiles/r02_ncu_config2_kernels.txt (local_bwd_tcrb10h_kernel): dram__bytes_read 133.5 MB + "
-               "dram__bytes_write 84.5 MB per launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)")
+TRAFFIC_BWD = (211.2e6, "ncu --set full, profiles/r02_ncu_config2_kernels_tcjoint.txt (local_bwd_tcrb10h_kernel): dram__bytes_read 133.3 MB + "
+               "dram__bytes_write 77.9 MB per launch (algorithmic 256.9 MB; the tail of the gradient writes is still in L2)")
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -676,7 +676,7 @@ def run_b200(args):
                 "peak_source": peak_src, "launch_ms": round(t_bwd, 4),
                 "algorithmic_bytes_per_launch": alg_bytes_launch,
                 "note": "the local backward of the largest term, timed alone (single-op CUDA graph, CUDA events); it runs on the "
-                        "tensor cores (fp32-accurate split products) and is bound by operand fetch / MMA issue, not by HBM; "
+                        "tensor cores (fp32-accurate split products) and is bound by its MMA stream (12 MMAs per source row), not by HBM; "
                         "fp32_fma_frac compares its useful FMAs with the FP32 SIMT peak it replaced",
                 "fp32_fma_frac": round(fma_per_launch / (t_bwd * 1e-3) / fp32_peak, 4),
                 "step_breakdown_ms": {"local_joint+separate_reduce(+simplex)": round(t_joint, 4),

@@ -132,6 +132,8 @@ __global__ void __launch_bounds__(1024) global_epilogue_kernel(const double* __r
   global_epilogue_block(J, K, lamb, symmetric, losses_out, P_out, flags, sm);
 }
 
+constexpr int GLOBAL_BWD_STAGE_FLOATS = 2048;      // rows of x (and of y) staged in shared memory by global_backward_kernel
+
 // Every CTA rebuilds GJ = d(objective)/dJ in shared memory, then produces a slab of rows of gx = y GJ^T and gy = x GJ.
 // The joint is read from global memory ONCE (symmetrised into shared memory); the kernel is a chain of small dependent
 // phases, so every phase that went back to global memory for J cost a memory latency (19k cycles at (32, 10) before).
@@ -149,6 +151,7 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   double* gj = gi + K;             // K
   double* Js = gj + K;             // K*K : the (symmetrised) joint; overwritten in place by GP
   float* GJ = reinterpret_cast<float*>(Js + (size_t)K * K);    // K*K floats : dObj/dJ[i][j]
+  float* rows_s = GJ + (size_t)K * K;                          // staged x and y rows of this CTA's slab (small slabs only)
   const int tid = threadIdx.x, nt = blockDim.x;
   const size_t KK = (size_t)K * K;
   const double eps = 1e-10;
@@ -156,6 +159,17 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   const long long r0 = (long long)blockIdx.x * rows_per_cta;
   long long r1 = r0 + rows_per_cta;
   if (r1 > N) r1 = N;
+  // A small slab (config 2: 32 rows of 10) is staged in shared memory now, so that its global-memory latency overlaps the
+  // epilogue phases below instead of sitting in the row loop (K dependent loads per output there: ~6000 clk at K = 10).
+  const long long slab = (r1 - r0) * K;
+  const bool staged_rows = slab <= GLOBAL_BWD_STAGE_FLOATS;
+  if (staged_rows)
+    for (long long e = tid; e < slab; e += nt) {
+      const long long n = r0 + e / K;
+      const int c = (int)(e % K);
+      rows_s[e] = x[n * x_sn + c];
+      rows_s[slab + e] = y[n * y_sn + c];
+    }
   const double g1 = g_loss ? (double)g_loss[0] : 0.0, g2 = g_no_lamb ? (double)g_no_lamb[0] : 0.0;
   double part = 0.0;
   for (size_t e = tid; e < KK; e += nt) {
@@ -203,8 +217,8 @@ __global__ void __launch_bounds__(256) global_backward_kernel(
   for (long long e = tid; e < total; e += nt) {
     const long long n = r0 + e / K;
     const int c = (int)(e % K);
-    const float* xr = x + n * x_sn;
-    const float* yr = y + n * y_sn;
+    const float* xr = staged_rows ? rows_s + (n - r0) * K : x + n * x_sn;
+    const float* yr = staged_rows ? rows_s + slab + (n - r0) * K : y + n * y_sn;
     float ax = 0.f, ay = 0.f;
     for (int q = 0; q < K; ++q) {
       ax = fmaf(GJ[(size_t)c * K + q], yr[q], ax);
@@ -318,10 +332,10 @@ extern "C" int iic_global_backward(const float* x, long long x_sn, const float* 
   IIC_REQUIRE(N > 0 && K > 0 && K <= 128, "iic_global_backward: bad sizes N=%lld K=%d", N, K);
   long long rpc;
   const int ctas = global_grid(current_device(), N, &rpc);
-  const size_t smem = (40 + 4 * (size_t)K + (size_t)K * K) * sizeof(double) + (size_t)K * K * sizeof(float);
+  const size_t smem = (40 + 4 * (size_t)K + (size_t)K * K) * sizeof(double) + ((size_t)K * K + 2 * GLOBAL_BWD_STAGE_FLOATS) * sizeof(float);
   auto kern = global_backward_kernel;
   // opted in once per device, for the largest K the entry point takes (128)
-  if (smem > 48 * 1024) IIC_CHECK_RC(ensure_dyn_smem((const void*)kern, (int)((40 + 4 * 128 + 128 * 128) * sizeof(double) + 128 * 128 * sizeof(float))));
+  if (smem > 48 * 1024) IIC_CHECK_RC(ensure_dyn_smem((const void*)kern, (int)((40 + 4 * 128 + 128 * 128) * sizeof(double) + (128 * 128 + 2 * GLOBAL_BWD_STAGE_FLOATS) * sizeof(float))));
   if (gx_sn <= 0) gx_sn = K;            // 0 = dense rows
   if (gy_sn <= 0) gy_sn = K;
   kern<<<ctas, 256, smem, st>>>(x, x_sn, y, y_sn, N, K, J, lamb, symmetric, g_loss, g_no_lamb, gP, gx, gy, gx_sn, gy_sn, rpc);
