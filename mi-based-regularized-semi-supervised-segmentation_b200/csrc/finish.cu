@@ -70,7 +70,9 @@ struct FinBatch {
 // one whole global term.
 __device__ __forceinline__ void store_joint(const FinBatch& B, const FinItem& it, long long e, double v, int par) {
   it.J[e] = v;
-  if (B.world > 1) {
+  // small batches publish from the last CTA (one system-scope fence on the critical path instead of one per CTA before the
+  // ticket plus one after it); large batches publish from every CTA as they go
+  if (B.world > 1 && B.xchg_mode == 2) {
     const long long off = (it.J - B.J_all) + e;
     for (int p = 0; p < B.world; ++p) xchg_slot(B.peers.base[p], par, B.world, B.rank, B.capacity)[off] = v;
   }
@@ -314,7 +316,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
       base += nu;
     }
   }
-  if (B.world > 1) __threadfence_system(); else __threadfence();
+  if (B.world > 1 && B.xchg_mode == 2) __threadfence_system(); else __threadfence();
   __syncthreads();
   if (tid == 0) last_s = (atomicAdd(B.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
@@ -323,7 +325,17 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
 
   // ---- phase 2, last CTA only ----
   if (B.world > 1) {
-    __threadfence_system();
+    if (B.xchg_mode == 2) {
+      __threadfence_system();
+    } else {
+      // this rank's joints (just reduced by all CTAs, L2-resident) into its slot of every rank's buffer
+      for (long long e = tid; e < B.E_total; e += FIN_THREADS) {
+        const double v = __ldcg(B.J_all + e);
+        for (int p = 0; p < B.world; ++p) xchg_slot(B.peers.base[p], par, B.world, B.rank, B.capacity)[e] = v;
+      }
+      __syncthreads();
+      if (tid < B.world) __threadfence_system();      // cumulative: the CTA's stores above are ordered before the flags
+    }
     if (tid < B.world) {
       XchgHeader* ph = reinterpret_cast<XchgHeader*>(B.peers.base[tid]);
       st_release_sys(&ph->flags[par][B.rank], seq);
@@ -338,10 +350,12 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     }
     __syncthreads();
     const double* src = xchg_slot(B.peers.base[B.rank], par, B.world, 0, B.capacity);
+    const bool stage_now = B.do_epilogue && B.E_total <= (long long)(FIN_WARPS * 33);   // the epilogue below reads shared memory
     for (long long e = tid; e < B.E_total; e += FIN_THREADS) {
       double s = 0.0;
       for (int r = 0; r < B.world; ++r) s += __ldcg(src + (size_t)r * B.capacity + e);     // rank order: bit-identical everywhere
       B.J_all[e] = s;
+      if (stage_now) (&sm[0][0])[e] = s;
     }
     __syncthreads();
     if (tid == 0) *reinterpret_cast<volatile unsigned long long*>(&hdr->seq) = seq;
@@ -353,7 +367,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
   // small batches (config 2: 900 + 100 doubles): all joints into shared memory -- the phase-1 scratch is free now
   const bool staged = B.E_total <= (long long)(FIN_WARPS * 33);
   double* Js = &sm[0][0];
-  if (staged) {
+  if (staged && B.world == 1) {                         // (with several ranks the rank sum above has filled Js)
     for (long long e = tid; e < B.E_total; e += FIN_THREADS) Js[e] = __ldcg(B.J_all + e);
     __syncthreads();
   }
