@@ -11,12 +11,14 @@
 //     overlapping atoms: tools/mn_major_micro.cu shows the hardware takes them and applies the swizzle to the absolute
 //     address.  One MMA (M = 128, N = 192, K = 16 pixels) adds 16 pixels of two y rows into all nine displacements:
 //     D[(x row a, x slot), (shift, y row r, y slot)], dy = a - r.
-// Per CTA (one per SM, its share of the B*H image rows): eight warps stage the x row pairs and eight the y row pairs
-// straight from global memory (thread = two pixels of a row, 8-byte loads, the next pair's loads in flight while this one is split,
-// packed and stored with swizzled 16-byte stores; the simplex assertion of iic_loss.py:113 rides along) -> one issuing
-// lane -> two TMEM accumulator sets taken in turn by y row pair -> four warps read each set out as soon as its pair is done
-// (fp32 register sums: short tensor-core accumulation runs keep the truncation bias of the TMEM adds below 2e-6) and at
-// the end add the (part x part) products and the two y rows and write this CTA's slot in the [d][i][j] layout of iic_finish.
+// Per CTA (one per SM, its share of the B*H image rows): seven warps stage the x row pairs and seven the y row pairs
+// straight from global memory (thread = two pixels of a row, 8-byte loads, the next pair's loads in flight while this one
+// is split, packed and stored with swizzled 16-byte stores; the simplex assertion of iic_loss.py:113 rides along) -> two
+// issuing warps, alternate pairs (these MMAs hold the issuing lane for as long as they execute) -> two TMEM accumulator
+// sets taken in turn by y row pair -> four warps read each set out as soon as its pair is done (fp32 register sums: short
+// tensor-core accumulation runs keep the truncation bias of the TMEM adds near 1e-6) and at the end add the
+// (part x part) products and the two y rows and write this CTA's slot in the [d][i][j] layout of iic_finish.
+// DESIGN.md 4.1c has the measurements behind each of these choices.
 #include <cuda_fp16.h>
 #include <stdlib.h>
 
@@ -50,7 +52,8 @@ struct Params {
   float* partial;      // [gridDim.x][9][K][K]
   int* flags;          // nullable: simplex assertion on x
 #ifdef IIC_TCJ_DEBUG
-  int dbg;             // harness only: 1 = no MMAs, 2 = no transform work, 8 = no global loads, 16 = issuer does not wait
+  int dbg;             // harness only: 1 = no MMAs, 2 = no transform work, 8 = no global loads, 64 = drain without TMEM loads,
+                       // 128 = issuers do not wait for the drain
 #endif
 };
 #ifdef IIC_TCJ_DEBUG
