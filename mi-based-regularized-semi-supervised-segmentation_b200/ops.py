@@ -88,7 +88,8 @@ def _state(device: torch.device) -> _StreamState:
 
 
 _side_streams = {}
-overlap_global_backward = False    # run the small global-term gradient kernels beside the local ones (see IICTermsFunction.backward)
+overlap_global_backward = False    # run the small global-term gradient kernels beside the local ones (see IICTermsFunction.backward);
+                                   # measured at config 2: no gain (0.1639 vs 0.1614-0.1626 ms per step), so off
 
 
 def _side_stream(device: torch.device) -> "torch.cuda.Stream":
@@ -952,14 +953,15 @@ class IICTermsFunction(torch.autograd.Function):
             written.add((si, blk))
             return dst, None
 
-        # The global terms' gradient kernels are one small CTA each (~8 us of latency-bound work at (32, 10)); the local ones
-        # fill the GPU for ~100 us.  With both kinds present the global ones go to a side stream, forked here and joined
-        # before anything reads their output: inside a captured CUDA graph that makes them parallel branches.
+        # The global terms' gradient kernels are one small CTA each (~7 us of latency-bound work at (32, 10)); the local ones
+        # fill the GPU for ~75 us with one persistent CTA per SM.  With both kinds present the global ones go to a side
+        # stream that forks BEFORE the local launches and is joined after them: inside a captured CUDA graph they are
+        # parallel branches, and the small CTA (128 threads) fits on an SM beside a local-backward CTA.  The global kernels
+        # are launched after the local ones, so that they never hold an SM the persistent kernel is waiting for.
         n_local = sum(1 for m in ctx.meta if m[0] is LocalTerm)
         use_side = overlap_global_backward and n_local > 0 and n_local < len(ctx.meta)
-        side, main, deferred = None, None, []
-        # saved-tensor and gradient offsets of every term, then the launch order: with a side stream the global terms go
-        # first, so that the fork point lies before the first local kernel on the main stream
+        side, main, deferred, gjobs = None, None, [], []
+        # saved-tensor and gradient offsets of every term
         offs, gi, si_ = [], 0, 0
         for m in ctx.meta:
             offs.append((si_, gi))
@@ -971,11 +973,16 @@ class IICTermsFunction(torch.autograd.Function):
                 gi += 3
         order = list(range(len(ctx.meta)))
         if use_side:
+            # global terms first: their targets are allocated (and zero-filled where needed) on the main stream before the fork
             order.sort(key=lambda t_: ctx.meta[t_][0] is LocalTerm)
         for ti in order:
             cls, pad, patch, step, logits, inv_t, lamb, symmetric, has_mask, npatch = ctx.meta[ti]
             si_, gi = offs[ti]
             if cls is LocalTerm:
+                if use_side and side is None and gjobs:
+                    main = torch.cuda.current_stream(sv[si_].device)
+                    side = _side_stream(sv[si_].device)
+                    side.wait_stream(main)        # fork: upstream gradients and the global targets' zero fills are queued on main
                 x, y, Wx, Wy = sv[si_:si_ + 4]
                 mask = sv[si_ + 4] if has_mask else None
                 g = grads[gi]
@@ -993,26 +1000,32 @@ class IICTermsFunction(torch.autograd.Function):
                     continue
                 (gx, ax), (gy, ay) = target(2 * ti, x), target(2 * ti + 1, y)
                 if use_side:
-                    if side is None:
-                        main = torch.cuda.current_stream(x.device)
-                        side = _side_stream(x.device)
-                    side.wait_stream(main)        # the upstream gradients and any zero fill of the targets are queued on main
-                    with torch.cuda.stream(side):
-                        _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
-                    if ax is not None:
-                        deferred.append((ax, gx))
-                    if ay is not None:
-                        deferred.append((ay, gy))
+                    gjobs.append((x, y, J, lamb, symmetric, g1, g2, gP, gx, gy, ax, ay))
                     continue
                 _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
             if ax is not None:
                 ax += gx
             if ay is not None:
                 ay += gy
-        if side is not None:
-            main.wait_stream(side)                # join: every later reader (and the allocator) sees the side work done
-            for acc, g_ in deferred:
-                acc += g_
+        if gjobs:
+            if side is None:                      # no local term had a gradient after all: plain launches
+                for (x, y, J, lamb, symmetric, g1, g2, gP, gx, gy, ax, ay) in gjobs:
+                    _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
+                    if ax is not None:
+                        ax += gx
+                    if ay is not None:
+                        ay += gy
+            else:
+                with torch.cuda.stream(side):
+                    for (x, y, J, lamb, symmetric, g1, g2, gP, gx, gy, ax, ay) in gjobs:
+                        _global_backward_into(x, y, J.view(x.shape[1], x.shape[1]), lamb, symmetric, g1, g2, gP, gx, gy)
+                        if ax is not None:
+                            deferred.append((ax, gx))
+                        if ay is not None:
+                            deferred.append((ay, gy))
+                main.wait_stream(side)            # join: every later reader (and the allocator) sees the side work done
+                for acc, g_ in deferred:
+                    acc += g_
         return (None, None, None, *[G[i] if any_grad[i] else None for i in range(n_src)])
 
 
