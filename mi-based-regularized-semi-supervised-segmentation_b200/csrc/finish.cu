@@ -257,16 +257,19 @@ __device__ void warp_global_term(const FinItem& it, const double* J, bool staged
       r += Jsym(k, q);
       c += Jsym(q, k);
     }
-    pi[k] = r / S;
-    pj[k] = c / S;
+    // the logs of the marginals, once per cluster (they were taken per ENTRY: 3 fp64 logs for each of the K*K entries made
+    // this one warp the critical path of the whole finish launch, ~10 us at K = 10)
+    pi[k] = log(r / S + eps);
+    pj[k] = log(c / S + eps);
   }
   __syncwarp();
+  const double inv_S = 1.0 / S;
   double l1 = 0.0, l2 = 0.0;
   for (int e = lane; e < KK; e += 32) {
     const int i = e / K, j = e - i * K;
-    const double p = Jsym(i, j) / S;
+    const double p = Jsym(i, j) * inv_S;
     if (it.P_out) it.P_out[e] = (float)p;
-    const double lp = log(p + eps), lj = log(pj[j] + eps), li = log(pi[i] + eps);
+    const double lp = log(p + eps), lj = pj[j], li = pi[i];
     l1 += -p * (lp - lamb * lj - lamb * li);
     l2 += -p * (lp - lj - li);
   }
@@ -279,6 +282,14 @@ __device__ void warp_global_term(const FinItem& it, const double* J, bool staged
   __syncwarp();
 }
 
+#ifdef IIC_FIN_TRACE
+__device__ unsigned long long g_fin_trace[16];
+__device__ __forceinline__ unsigned long long fin_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define FIN_T(i) do { if (threadIdx.x == 0) g_fin_trace[i] = fin_now(); } while (0)
+#else
+#define FIN_T(i) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_constant__ FinBatch B) {
   __shared__ double sm[FIN_WARPS][33];
   __shared__ double unit_loss[FIN_MAX_UNITS];
@@ -288,6 +299,9 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
   __shared__ unsigned long long seq_s;
   __shared__ int last_s;
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+#ifdef IIC_FIN_TRACE
+  if (tid == 0) atomicMin(&g_fin_trace[0], fin_now());
+#endif
 
   XchgHeader* hdr = nullptr;
   int par = 0;
@@ -316,12 +330,18 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
       base += nu;
     }
   }
+#ifdef IIC_FIN_TRACE
+  if (tid == 0) atomicMax(&g_fin_trace[1], fin_now());
+  if (tid == 0 && blockIdx.x == 0) g_fin_trace[7] = fin_now();                 // a CTA with one local unit
+  if (tid == 0 && blockIdx.x == gridDim.x - 1) g_fin_trace[8] = fin_now();     // (900 elements = 29 units: the global item is unit 29 -> CTA 0 again)
+#endif
   if (B.world > 1 && B.xchg_mode == 2) __threadfence_system(); else __threadfence();
   __syncthreads();
   if (tid == 0) last_s = (atomicAdd(B.ticket, 1u) == gridDim.x - 1) ? 1 : 0;
   __syncthreads();
   if (!last_s) return;
   __threadfence();
+  FIN_T(2);
 
   // ---- phase 2, last CTA only ----
   if (B.world > 1) {
@@ -372,6 +392,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     __syncthreads();
   }
   const double* Jbase = staged ? Js : B.J_all;
+  FIN_T(3);
 
   // per (term, patch): m = min over every displacement and both cluster axes (iic_loss.py:124), NaN-propagating
   int npatch_total = 0;
@@ -393,6 +414,7 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     }
   }
   __syncthreads();
+  FIN_T(4);
 
   // displacement units, dealt to the warps round robin
   {
@@ -423,21 +445,41 @@ __global__ void __launch_bounds__(FIN_THREADS, 1) finish_kernel(const __grid_con
     }
   }
   __syncthreads();
+  FIN_T(5);
   // per local term: the displacement losses in index order (deterministic), mean over displacements and patches
-  if (tid < B.n) {
+  // (one warp per term, lanes over its units, a fixed shuffle tree: deterministic, and not a serial chain of fp64 adds)
+  for (int t = wid; t < B.n; t += FIN_WARPS) {
+    FIN_T(10);
     int ubase = 0;
-    for (int i = 0; i < tid; ++i) ubase += B.it[i].kind == IIC_ITEM_GLOBAL_ROWS ? 1 : B.it[i].n_patches * B.it[i].T * B.it[i].T;
-    const FinItem& it = B.it[tid];
+    for (int i = 0; i < t; ++i) ubase += B.it[i].kind == IIC_ITEM_GLOBAL_ROWS ? 1 : B.it[i].n_patches * B.it[i].T * B.it[i].T;
+    const FinItem& it = B.it[t];
     if (it.kind == IIC_ITEM_LOCAL) {
       const int nu = it.n_patches * it.T * it.T;
-      double total = 0.0;
-      for (int u = 0; u < nu; ++u) total += unit_loss[ubase + u];
+      double part = 0.0;
+      for (int u = lane; u < nu; u += 32) part += unit_loss[ubase + u];
+      double total = warp_sum(part);
       total *= 1.0 / ((double)nu);
-      it.loss_out[0] = (float)total;
-      if (total != total && B.flags) atomicOr(B.flags, IIC_FLAG_NAN_LOSS);
+      FIN_T(9);
+      if (lane == 0) {
+        it.loss_out[0] = (float)total;
+        if (total != total && B.flags) atomicOr(B.flags, IIC_FLAG_NAN_LOSS);
+      }
     }
   }
+  FIN_T(6);
 }
+
+#ifdef IIC_FIN_TRACE
+extern "C" int iic_debug_fin_trace(unsigned long long* host16, int reset) {
+  if (reset) {
+    unsigned long long z[16];
+    for (int i = 0; i < 16; ++i) z[i] = 0;
+    z[0] = ~0ull;
+    return cudaMemcpyToSymbol(g_fin_trace, z, sizeof(z)) == cudaSuccess ? 0 : 1;
+  }
+  return cudaMemcpyFromSymbol(host16, g_fin_trace, 16 * sizeof(unsigned long long)) == cudaSuccess ? 0 : 1;
+}
+#endif
 
 // ---- large batches -----------------------------------------------------------------------------------------------------
 // Second half of the exchange with all SMs: wait for every rank's flag, add the ranks' slots in rank order, last CTA
