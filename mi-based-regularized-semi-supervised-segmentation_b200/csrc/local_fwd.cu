@@ -392,7 +392,7 @@ int local_joint_tc_try(const float* x, long long x_sn, long long x_sc, long long
 size_t local_joint_tcp_slot_floats(int K, int pad);
 int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                           long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial, int max_ctas,
-                          int* ncta, int* flags, int* checked, cudaStream_t st);
+                          int* ncta, int* flags, int* checked, int from_logits, float inv_temp, cudaStream_t st);
 int local_joint_tcp_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                         long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial,
                         size_t partial_floats, double* J_out, SlotInfo* info, cudaStream_t st);
@@ -461,7 +461,7 @@ static int local_joint_impl(const float* x, long long x_sn, long long x_sc, long
       const int sms = sm_count_cached(device);
       if (sms > 0 && sms <= pl.slots_per_patch) {
         rc = local_joint_tcj10_try(x, x_sn, x_sc, x_sh, y, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace, sms, &ncta,
-                                   flags, &checked, st);
+                                   flags, &checked, 0, 1.f, st);
         if (rc == 0 && checked) flags = nullptr;
       }
     }
@@ -595,8 +595,14 @@ extern "C" int iic_local_joint_from_logits(const float* lx, long long x_sn, long
               "iic_local_joint_from_logits: workspace too small (%zu < %zu)", workspace_bytes,
               (size_t)sms * E * sizeof(float));
   int ncta = 0, checked = 0;
-  const int rc = local_joint_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad,
-                                      (float*)workspace, sms, &ncta, nullptr, &checked, 1, inv_temperature, st);
+  // large maps: the tensor-core joint with the softmax in its staging warps (csrc/local_fwd_tcj10.cu); else the FFMA2 kernel
+  int rc = -1;
+  if (!options().no_tc && !options().no_tcj10 && pad == 1)
+    rc = local_joint_tcj10_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad, (float*)workspace, sms, &ncta,
+                               nullptr, &checked, 1, inv_temperature, st);
+  if (rc < 0)
+    rc = local_joint_fast_try(lx, x_sn, x_sc, x_sh, ly, y_sn, y_sc, y_sh, B, K, H, W, pad,
+                              (float*)workspace, sms, &ncta, nullptr, &checked, 1, inv_temperature, st);
   if (rc < 0) {
     set_error("iic_local_joint_from_logits: shape not covered by the fused kernel (needs padding 1, K == 10, "
               "W %% 4 == 0, 16-byte aligned rows); apply the softmax and call iic_local_joint");

@@ -51,6 +51,8 @@ struct Params {
   int B, H, W, K;
   float* partial;      // [gridDim.x][9][K][K]
   int* flags;          // nullable: simplex assertion on x
+  int from_logits;     // the maps hold the cluster head's LOGITS: softmax(logit * inv_temp) over the channels in the staging
+  float inv_temp;      // warps (contrastyou/trainer/_utils.py:15-23 fused), before the split
 #ifdef IIC_TCJ_DEBUG
   int dbg;             // harness only: 1 = no MMAs, 2 = no transform work, 8 = no global loads, 64 = drain without TMEM loads,
                        // 128 = issuers do not wait for the drain
@@ -114,6 +116,28 @@ __device__ __forceinline__ void load_tile(Tile& t, const Params& P, const Chunk&
 #pragma unroll
   for (int ch = 0; ch < 10; ++ch)
     t.f[ch] = __ldg(reinterpret_cast<const float2*>(ptr + (FULLK ? ch : min(ch, P.K - 1)) * sc));
+}
+
+// The cluster head's SoftmaxWithT on one thread's two pixels, in place (from-logits form).  Channels beyond K hold clamped
+// duplicates of channel K - 1 and are zeroed by the store's per-channel factor, so they only must not enter max and sum.
+template <bool FULLK>
+__device__ __forceinline__ void softmax_tile(Tile& t, int K, float inv_temp) {
+  float2 mx = t.f[0];
+#pragma unroll
+  for (int ch = 1; ch < 10; ++ch)
+    if (FULLK || ch < K) mx = make_float2(fmaxf(mx.x, t.f[ch].x), fmaxf(mx.y, t.f[ch].y));
+  float2 sum = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int ch = 0; ch < 10; ++ch) {
+    if (FULLK || ch < K) {
+      t.f[ch] = make_float2(__expf((t.f[ch].x - mx.x) * inv_temp), __expf((t.f[ch].y - mx.y) * inv_temp));
+      sum = __fadd2_rn(sum, t.f[ch]);
+    }
+  }
+  const float2 inv = make_float2(1.f / sum.x, 1.f / sum.y);
+#pragma unroll
+  for (int ch = 0; ch < 10; ++ch)
+    if (FULLK || ch < K) t.f[ch] = __fmul2_rn(t.f[ch], inv);
 }
 
 // Split, pack and store one thread's two pixels into the pair buffer(s): pixel b = column + boff, the row's three 16-byte
@@ -204,6 +228,7 @@ __device__ __forceinline__ void stage_pairs(const Params& P, long long R0, long 
     if (count >= NRING) mbar_wait(&released[count % NRING], (unsigned)(count / NRING - 1) & 1u, IS_Y ? 3 : 2);
     const int slot = count % NRING;
     if (!TCJ_DBG(2)) {
+      if (P.from_logits) softmax_tile<FULLK>(cur, P.K, P.inv_temp);
       if (!IS_Y && P.flags && cur.mul != 0.f) {
         // simplex(x_out) of iic_loss.py:113 on the rows of the map
         float2 sum = cur.f[0];
@@ -407,10 +432,11 @@ __global__ void __launch_bounds__(NTHREADS, 1) local_joint_tcj10_kernel(const Pa
 // *checked = 1 when `flags` was given and the simplex assertion on x ran inside the kernel.
 int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long long x_sh, const float* y, long long y_sn,
                           long long y_sc, long long y_sh, int B, int K, int H, int W, int pad, float* partial, int max_ctas,
-                          int* ncta, int* flags, int* checked, cudaStream_t st) {
+                          int* ncta, int* flags, int* checked, int from_logits, float inv_temp, cudaStream_t st) {
   using namespace fwdtcj10;
   *checked = 0;
   if (pad != PAD || K < 2 || K > 10 || W < 8 || W > MAXW) return -1;
+  if (from_logits && K != 10) return -1;           // the fused forward takes exactly the shapes every fused backward takes
   const long long rows = (long long)B * H;
   if (rows < 8LL * max_ctas) return -1;            // small maps: the pipeline fill dominates, the FFMA2 kernel is faster
   Params P;
@@ -418,7 +444,9 @@ int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long l
   P.y = y; P.y_sn = y_sn; P.y_sc = y_sc; P.y_sh = y_sh;
   P.B = B; P.H = H; P.W = W; P.K = K;
   P.partial = partial;
-  P.flags = flags;
+  P.flags = from_logits ? nullptr : flags;      // a softmax output needs no simplex assertion
+  P.from_logits = from_logits;
+  P.inv_temp = inv_temp;
   auto rows16 = [&](const float* b, long long sn, long long sc, long long sh) {
     return (reinterpret_cast<uintptr_t>(b) & 15) == 0 && sn % 4 == 0 && sc % 4 == 0 && sh % 4 == 0;
   };
@@ -426,7 +454,7 @@ int local_joint_tcj10_try(const float* x, long long x_sn, long long x_sc, long l
 #ifdef IIC_TCJ_DEBUG
   P.dbg = 0;
 #endif
-  *checked = flags != nullptr;
+  *checked = P.flags != nullptr;
   *ncta = max_ctas;
   IIC_CHECK_RC(ensure_dyn_smem((const void*)local_joint_tcj10_kernel, SMEM_BYTES));
   local_joint_tcj10_kernel<<<max_ctas, NTHREADS, SMEM_BYTES, st>>>(P);

@@ -41,7 +41,7 @@ int main(int argc, char** argv) {
     Params P;
     P.x = dx_; P.x_sn = sn; P.x_sc = sc; P.x_sh = W;
     P.y = dy_; P.y_sn = sn; P.y_sc = sc; P.y_sh = W;
-    P.B = B; P.H = H; P.W = W; P.K = K; P.partial = part; P.flags = nullptr; P.dbg = m;
+    P.B = B; P.H = H; P.W = W; P.K = K; P.partial = part; P.flags = nullptr; P.from_logits = 0; P.inv_temp = 1.f; P.dbg = m;
     local_joint_tcj10_kernel<<<148, NTHREADS, SMEM_BYTES>>>(P);
     cudaError_t err = cudaDeviceSynchronize();
     if (err != cudaSuccess) { printf("mode %d: %s\n", m, cudaGetErrorString(err)); return 1; }
