@@ -26,3 +26,16 @@ def test_broken_protocols_are_caught(name):
 @pytest.mark.parametrize("name", list(S.FORWARD_CONFIGS))
 def test_joint_kernel_protocols_hold(name):
     assert S.check(name, S.FORWARD_CONFIGS[name], runs=15) is None
+
+
+@pytest.mark.parametrize("name", [n for n in S.JOINT10_CONFIGS if "(bug)" not in n])
+def test_config2_joint_protocol_holds(name):
+    """csrc/local_fwd_tcj10.cu: x ring released by the issuers' x_free commits, y ring by y_done, accumulator sets by the drain."""
+    assert S.check(name, S.JOINT10_CONFIGS[name], runs=15) is None
+
+
+def test_config2_joint_ring_release_through_y_done_is_caught():
+    """The first ring-4 version of the joint (it hung on the GPU): a waiter two phases behind on a parity barrier."""
+    name = "tcj10 ring 4 released through y_done (bug)"
+    bad = S.check(name, S.JOINT10_CONFIGS[name], runs=25)
+    assert bad is not None and ("Race" in bad or "Deadlock" in bad)
