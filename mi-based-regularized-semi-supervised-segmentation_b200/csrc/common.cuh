@@ -53,6 +53,7 @@ struct Options {
   int no_tcj10 = 0;           // IIC_B200_NO_TCJ10: FFMA2 joint instead of the tensor-core joint for K <= 10, padding 1
   int tc10_tf32 = 0;          // IIC_B200_TC10_TF32: the tf32 + bf16-correction K = 10 backward instead of the fp16-split one
   int no_fused_epilogue = 0;  // IIC_B200_NO_FUSED_EPILOGUE: slot reduce and epilogue as two launches
+  int fin_last_cta_epilogue = 0;  // IIC_B200_FIN_LAST_CTA_EPILOGUE: small batches run their epilogues in the finish launch's last CTA
   int xchg_timeout_ms = 0;    // IIC_B200_XCHG_TIMEOUT_MS: bound of the peer wait in the joint exchange
 };
 const Options& options();

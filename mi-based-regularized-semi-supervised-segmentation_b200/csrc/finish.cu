@@ -633,7 +633,11 @@ extern "C" int iic_finish(const iic_finish_item* items_host, int n_items, double
   // small batches (config 2: one local + one global term): the last CTA exchanges and runs the epilogues itself;
   // anything larger: phase 1 here, then the rank sum and the epilogues as multi-CTA launches
   const bool small = fused && epi_units <= FIN_SMALL_UNITS && epi_patches <= FIN_MAX_PATCHES && E_total <= (long long)FIN_WARPS * 33;
-  B.do_epilogue = small ? 1 : 0;
+  // The epilogues of a small batch can run in the last CTA too (one launch instead of two), but they are fp64 work that one
+  // SM gets through slowly: at config 2 the step is 4.7 us faster with the units spread over SMs by the batched epilogue
+  // launch (0.1557 vs 0.1604 ms on the same box), so that is the default and the last-CTA form an option.
+  const bool last_cta_epilogue = small && options().fin_last_cta_epilogue;
+  B.do_epilogue = last_cta_epilogue ? 1 : 0;
   B.xchg_mode = small ? 1 : 2;
   int sms = sm_count_cached(current_device());
   if (sms <= 0) sms = 148;
@@ -642,8 +646,8 @@ extern "C" int iic_finish(const iic_finish_item* items_host, int n_items, double
   unsigned int* tickets = reinterpret_cast<unsigned int*>(workspace);
   finish_kernel<<<(unsigned)grid, FIN_THREADS, 0, st>>>(B);
   IIC_CHECK_CUDA(cudaGetLastError());
-  if (small) return 0;
-  if (world > 1) {
+  if (last_cta_epilogue) return 0;
+  if (world > 1 && !small) {                 // (a small batch was exchanged and summed by the last CTA)
     long long g2 = (E_total + FIN_THREADS - 1) / FIN_THREADS;
     if (g2 > sms) g2 = sms;
     xchg_sum_kernel<<<(unsigned)g2, FIN_THREADS, 0, st>>>(J_all, E_total, B.peers, rank, world, xchg_capacity, B.timeout_ns, flags,

@@ -54,6 +54,7 @@ static const OptionEntry kOptions[] = {
     {"no_tcj10", "IIC_B200_NO_TCJ10", &Options::no_tcj10},
     {"tc10_tf32", "IIC_B200_TC10_TF32", &Options::tc10_tf32},
     {"no_fused_epilogue", "IIC_B200_NO_FUSED_EPILOGUE", &Options::no_fused_epilogue},
+    {"fin_last_cta_epilogue", "IIC_B200_FIN_LAST_CTA_EPILOGUE", &Options::fin_last_cta_epilogue},
     {"xchg_timeout_ms", "IIC_B200_XCHG_TIMEOUT_MS", &Options::xchg_timeout_ms},
 };
 static Options g_options;

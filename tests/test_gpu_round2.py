@@ -62,7 +62,8 @@ def test_dispatch_branches_without_env(iic, cuda_device, B, K, H, W, pad, patch)
     _check_local(iic, cuda_device, B, K, H, W, pad, patch, 777 + B + K + W)
 
 
-@pytest.mark.parametrize("opt", ["tcp_p1", "tcrb_p1", "tc10_force", "tc10_tf32", "no_tc", "no_fast", "no_tma", "no_fused_epilogue"])
+@pytest.mark.parametrize("opt", ["tcp_p1", "tcrb_p1", "tc10_force", "tc10_tf32", "no_tc", "no_fast", "no_tma", "no_fused_epilogue",
+                                 "fin_last_cta_epilogue"])
 def test_forced_kernel_families(iic, cuda_device, opt):
     """The same small inputs through the kernel family a switch forces must agree with the oracle (and therefore with
     the default dispatch).  K = 20 / padding 1 for the packed joint and the row-block backward, K = 10 for the rest."""
@@ -200,6 +201,22 @@ def test_fused_and_unfused_epilogue_agree(iic, cuda_device):
             res.append((loss.item(), xd.grad.clone()))
     assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0])
     assert relmax(res[0][1].cpu().numpy(), res[1][1].cpu().numpy()) <= 1e-5
+    # a small batch: the default (finish launch + one multi-CTA epilogue launch) against the epilogue in the finish launch's last CTA
+    x, y = views(rng, 2, 10, 40, 56)
+    g0 = torch.rand(2, 8, 10, device=cuda_device).softmax(2)
+    res = []
+    for v in (0, 1):
+        with option(iic, "fin_last_cta_epilogue", v):
+            xd = torch.from_numpy(x).to(cuda_device).requires_grad_(True)
+            yd = torch.from_numpy(y).to(cuda_device).requires_grad_(True)
+            gx = g0[0].clone().requires_grad_(True)
+            gy = g0[1].clone().requires_grad_(True)
+            ll, lg = iic.iic_losses([(iic.IIDSegmentationSmallPathLoss(padding=1, patch_size=512), xd, yd), (iic.IIDLoss(), gx, gy)])
+            (ll + lg[0]).backward()
+            res.append((ll.item(), lg[0].item(), xd.grad.clone(), gx.grad.clone()))
+    assert abs(res[0][0] - res[1][0]) <= 1e-6 * abs(res[1][0]) and abs(res[0][1] - res[1][1]) <= 1e-6 * abs(res[1][1])
+    assert relmax(res[0][2].cpu().numpy(), res[1][2].cpu().numpy()) <= 1e-5
+    assert relmax(res[0][3].cpu().numpy(), res[1][3].cpu().numpy()) <= 1e-5
 
 
 def test_global_term_through_finish(iic, cuda_device):

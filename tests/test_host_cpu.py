@@ -53,7 +53,7 @@ def test_options_are_read_once_and_settable(built):
     assert lib.iic_b200_get_option(b"xchg_timeout_ms") > 0
     # every documented switch exists in the table
     for name in ("no_tma", "no_tc", "no_tc10", "no_tcj10", "no_fast", "tcp_p1", "tcrb_p1", "tc10_force", "tc10_tf32",
-                 "no_fused_epilogue", "xchg_timeout_ms"):
+                 "no_fused_epilogue", "fin_last_cta_epilogue", "xchg_timeout_ms"):
         assert lib.iic_b200_get_option(name.encode()) >= 0, name
     assert lib.iic_b200_set_option(b"no_such_switch", 1) != 0
     assert lib.iic_b200_get_option(b"no_such_switch") == -1
