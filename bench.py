@@ -394,7 +394,7 @@ def count_own_launches(torch, fn):
 
 def static_launch_count(wl, world):
     """Fallback for gpu_launches when the profiler is unavailable: kernels of libiic_b200.so per step, from the dispatch
-    rules (joint 1; finish 1, +1 batched epilogue for large batches, +1 rank sum when they are exchanged; backward 1 per
+    rules (joint 1; finish 1 + 1 batched epilogue launch, +1 rank sum when a large batch is exchanged; backward 1 per
     local term, or 2 sweeps + 2 weight images on the K = 20 / K = 128 tensor-core kernels; global backward 1; UDA 2)."""
     n, units, entries = 0, 0, 0
     for kind, S, K, H, W, pad, patch, w in wl["groups"]:
@@ -408,7 +408,7 @@ def static_launch_count(wl, world):
             units += S
             entries += S * K * K
     big = units > 32 or entries > 1056
-    n += 1 + (1 if big else 0) + (1 if (big and world > 1) else 0)
+    n += 2 + (1 if (big and world > 1) else 0)
     if wl["uda"]:
         n += 2
     return n
