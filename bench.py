@@ -649,7 +649,7 @@ def run_b200(args):
         t_epi = timed_graph(lambda: iops.ops.local_epilogue(J0, K, pad, 1.0))
         t_bwd = timed_graph(lambda: iops.ops.local_backward(xs, ys, None, Wx0, Wy0, one, pad, patch, patch, half, half))
         xr, yr = xs.clone().requires_grad_(True), ys.clone().requires_grad_(True)
-        t_fwd = timed_graph(lambda: crits[gi_dom](xr, yr))            # joint + ONE finish launch
+        t_fwd = timed_graph(lambda: crits[gi_dom](xr, yr))            # joint + finish launch + epilogue launch
     finally:
         iops._dist_enabled = saved_dp
     alg_bytes_launch = 16.0 * K * B * H * W                   # read both maps + write both gradients, fp32
