@@ -42,10 +42,11 @@ const char* iic_b200_last_error(void);
 /* number of SMs of `device` (148 on B200); <0 on error */
 int iic_b200_sm_count(int device);
 /* Dispatch switches.  The library reads IIC_B200_* environment variables ONCE (at first use) as defaults; after that
- * only these calls change them.  Names: "no_tma", "no_tc", "no_tc10", "no_fast" (skip a kernel family), "tcp_p1",
- * "tcrb_p1", "tc10_force" (force a tensor-core kernel outside the shapes it is normally chosen for), "tc10_tf32" (the
- * tf32 + bf16-correction form of the K = 10 backward instead of the fp16-split one), "no_fused_epilogue",
- * "xchg_timeout_ms".  Results are the same whatever the switches; only the kernel that runs changes (the parity tests
+ * only these calls change them.  Names: "no_tma", "no_tc", "no_tc10", "no_tcj10", "no_fast" (skip a kernel family),
+ * "tcp_p1", "tcrb_p1", "tc10_force" (force a tensor-core kernel outside the shapes it is normally chosen for),
+ * "tc10_tf32" (the tf32 + bf16-correction form of the K = 10 backward instead of the fp16-split one),
+ * "no_fused_epilogue" (per-term epilogue launches), "fin_last_cta_epilogue" (a small batch's epilogues inside the finish
+ * launch instead of the batched epilogue launch), "xchg_timeout_ms".  Results are the same whatever the switches; only the kernel that runs changes (the parity tests
  * use them to reach every dispatch branch).  set: 0 = ok; get: the value, -1 for an unknown name. */
 int iic_b200_set_option(const char* name, int value);
 int iic_b200_get_option(const char* name);
